@@ -1,0 +1,141 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  extern "C" surface over the CPU restatement.
+#include "ygz_oracle.h"
+#include "cvprims.h"
+#include "orb_extractor.h"
+#include <atomic>
+#include <cstring>
+#include <thread>
+
+using namespace orc;
+static_assert(sizeof(orc_keypoint) == sizeof(KeyPoint) && sizeof(KeyPoint) == 28, "KeyPoint POD layout");
+
+struct orc_extractor { Extractor ex; orc_extractor(int a, float b, int c, int d, int e) : ex(a, b, c, d, e) {} };
+
+extern "C" {
+
+void orc_resize_linear_u8(const uint8_t* s, int sw, int sh, int ss, uint8_t* d, int dw, int dh, int ds) {
+    resize_linear_u8(s, sw, sh, ss, d, dw, dh, ds);
+}
+void orc_border_reflect101(const uint8_t* s, int w, int h, int ss, uint8_t* d, int border, int ds) {
+    border_reflect101(s, w, h, ss, d, border, ds);
+}
+void orc_gauss7_sigma2_u8(const uint8_t* s, int w, int h, int ss, uint8_t* d, int ds) {
+    gauss7_sigma2_u8(s, w, h, ss, d, ds);
+}
+int orc_fast9_16(const uint8_t* img, int w, int h, int stride, int t, int nms, orc_keypoint* out, int cap) {
+    std::vector<KeyPoint> v;
+    fast9_16(img, w, h, stride, t, nms != 0, v);
+    int n = (int)v.size();
+    if (n > cap) return -n;
+    if (n) std::memcpy(out, v.data(), (size_t)n * sizeof(KeyPoint));
+    return n;
+}
+void orc_fast_atan2_array(const float* y, const float* x, float* out, int n) {
+    for (int i = 0; i < n; i++) out[i] = fast_atan2(y[i], x[i]);
+}
+void orc_cosf_sinf_array(const float* deg, float* c, float* s, int n) {
+    const float factorPI = (float)(M_PI / 180.f);
+    for (int i = 0; i < n; i++) {
+        float a = deg[i] * factorPI;
+        c[i] = (float)std::cos(a);
+        s[i] = (float)std::sin(a);
+    }
+}
+
+orc_extractor* orc_extractor_create(int nf, float sf, int nl, int ini, int mn) { return new orc_extractor(nf, sf, nl, ini, mn); }
+void orc_extractor_destroy(orc_extractor* h) { delete h; }
+
+void orc_extractor_tables(orc_extractor* h, float* sc, float* isc, float* s2, float* is2, int* fpl, int* um) {
+    Extractor& e = h->ex;
+    for (int i = 0; i < e.nlevels; i++) {
+        if (sc) sc[i] = e.mvScaleFactor[i];
+        if (isc) isc[i] = e.mvInvScaleFactor[i];
+        if (s2) s2[i] = e.mvLevelSigma2[i];
+        if (is2) is2[i] = e.mvInvLevelSigma2[i];
+        if (fpl) fpl[i] = e.mnFeaturesPerLevel[i];
+    }
+    if (um) for (int i = 0; i < 16; i++) um[i] = e.umax[i];
+}
+
+static int emit(const std::vector<KeyPoint>& k, const std::vector<uint8_t>& d, orc_keypoint* kps, uint8_t* desc, int cap) {
+    int n = (int)k.size();
+    if (n > cap) return -n;
+    if (n) {
+        std::memcpy(kps, k.data(), (size_t)n * sizeof(KeyPoint));
+        if (desc) std::memcpy(desc, d.data(), (size_t)n * 32);
+    }
+    return n;
+}
+
+int orc_extract(orc_extractor* h, const uint8_t* img, int w, int hh, int stride, orc_keypoint* kps, uint8_t* desc, int cap) {
+    std::vector<KeyPoint> k;
+    std::vector<uint8_t> d;
+    h->ex.extract(img, w, hh, stride, k, d);
+    return emit(k, d, kps, desc, cap);
+}
+
+int orc_extract_frame(orc_extractor* h, const uint8_t* img, int w, int hh, int stride, int n_existing,
+                      orc_keypoint* kps, uint8_t* desc, int cap) {
+    std::vector<KeyPoint> k((KeyPoint*)kps, (KeyPoint*)kps + n_existing);
+    std::vector<uint8_t> d;
+    h->ex.ComputePyramid(img, w, hh, stride);
+    h->ex.extract_frame(k, d);
+    return emit(k, d, kps, desc, cap);
+}
+
+int orc_level_size(orc_extractor* h, int level, int* w, int* hh) {
+    if (level < 0 || level >= h->ex.nlevels) return -1;
+    *w = h->ex.pyramid[level].w;
+    *hh = h->ex.pyramid[level].h;
+    return 0;
+}
+int orc_get_level(orc_extractor* h, int level, int blurred, uint8_t* out) {
+    if (level < 0 || level >= h->ex.nlevels) return -1;
+    const Image& im = blurred ? h->ex.blurred[level] : h->ex.pyramid[level];
+    std::memcpy(out, im.px.data(), im.px.size());
+    return (int)im.px.size();
+}
+static int copy_keys(const std::vector<KeyPoint>& v, orc_keypoint* out, int cap) {
+    int n = (int)v.size();
+    if (n > cap) return -n;
+    if (n) std::memcpy(out, v.data(), (size_t)n * sizeof(KeyPoint));
+    return n;
+}
+int orc_get_candidates(orc_extractor* h, int level, orc_keypoint* out, int cap) {
+    if (level < 0 || level >= (int)h->ex.candidates.size()) return 0;
+    return copy_keys(h->ex.candidates[level], out, cap);
+}
+int orc_get_level_keys(orc_extractor* h, int level, orc_keypoint* out, int cap) {
+    if (level < 0 || level >= (int)h->ex.level_keys.size()) return 0;
+    return copy_keys(h->ex.level_keys[level], out, cap);
+}
+int orc_distribute_octtree(orc_extractor* h, const orc_keypoint* keys, int n, int minX, int maxX, int minY, int maxY,
+                           int N, orc_keypoint* out, int cap) {
+    std::vector<KeyPoint> in((const KeyPoint*)keys, (const KeyPoint*)keys + n);
+    return copy_keys(h->ex.DistributeOctTree(in, minX, maxX, minY, maxY, N), out, cap);
+}
+
+long orc_extract_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t* imgs, int n_frames, int w, int hh, int threads) {
+    std::atomic<int> next(0);
+    std::atomic<long> total(0);
+    auto work = [&]() {
+        Extractor ex(nf, sf, nl, ini, mn);
+        std::vector<KeyPoint> k;
+        std::vector<uint8_t> d;
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n_frames) break;
+            ex.extract(imgs + (size_t)i * w * hh, w, hh, w, k, d);
+            total += (long)k.size();
+        }
+    };
+    if (threads <= 1) work();
+    else {
+        std::vector<std::thread> ts;
+        for (int t = 0; t < threads; t++) ts.emplace_back(work);
+        for (auto& t : ts) t.join();
+    }
+    return total.load();
+}
+
+}  // extern "C"

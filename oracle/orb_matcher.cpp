@@ -1,0 +1,397 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ygz_oracle.h).  CPU restatement of ygz::ORBmatcher
+// (/root/reference/src/ORBmatcher.cc) and the Frame grid helpers it uses
+// (/root/reference/src/Frame.cc:314-330, 424-493) over flat array views of the pointer graph.
+#include "ygz_oracle.h"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+const int TH_HIGH = 100;      // src/ORBmatcher.cc:36
+const int TH_LOW = 50;        // :37
+const int HISTO_LENGTH = 30;  // :38
+const int GRID_COLS = 64, GRID_ROWS = 48;   // include/Frame.h:38-39
+
+// ---- src/ORBmatcher.cc:1507-1523
+inline int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t va, vb;
+        std::memcpy(&va, a + 4 * i, 4);
+        std::memcpy(&vb, b + 4 * i, 4);
+        dist += __builtin_popcount(va ^ vb);
+    }
+    return dist;
+}
+
+// ---- src/Frame.cc:314-330 + :483-493
+struct Grid {
+    std::vector<int> cell[GRID_COLS][GRID_ROWS];
+    float invW, invH;
+    explicit Grid(const orc_frame_view* f) {
+        invW = static_cast<float>(GRID_COLS) / (f->max_x - f->min_x);
+        invH = static_cast<float>(GRID_ROWS) / (f->max_y - f->min_y);
+        for (int i = 0; i < f->n; i++) {
+            int px = (int)std::round((f->keys[i].x - f->min_x) * invW);
+            int py = (int)std::round((f->keys[i].y - f->min_y) * invH);
+            if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+            cell[px][py].push_back(i);
+        }
+    }
+};
+
+// ---- src/Frame.cc:424-481
+std::vector<int> features_in_area(const orc_frame_view* f, const Grid& g, float x, float y, float r,
+                                  int minLevel = -1, int maxLevel = -1) {
+    std::vector<int> out;
+    const int nMinCellX = std::max(0, (int)std::floor((x - f->min_x - r) * g.invW));
+    if (nMinCellX >= GRID_COLS) return out;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - f->min_x + r) * g.invW));
+    if (nMaxCellX < 0) return out;
+    const int nMinCellY = std::max(0, (int)std::floor((y - f->min_y - r) * g.invH));
+    if (nMinCellY >= GRID_ROWS) return out;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - f->min_y + r) * g.invH));
+    if (nMaxCellY < 0) return out;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+            for (int idx : g.cell[ix][iy]) {
+                const orc_keypoint& kp = f->keys[idx];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float distx = kp.x - x, disty = kp.y - y;
+                if (std::fabs(distx) < r && std::fabs(disty) < r) out.push_back(idx);
+            }
+    return out;
+}
+
+// ---- src/ORBmatcher.cc:1471-1502
+void three_maxima(const int* sz, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = sz[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+inline bool mp_bad(const orc_map_points* m, int i) { return m->bad && m->bad[i]; }
+inline int mp_obs(const orc_map_points* m, int i) { return m->observations ? m->observations[i] : 1; }
+inline float uright(const orc_frame_view* f, int i) { return f->u_right ? f->u_right[i] : -1.f; }
+
+}  // namespace
+
+extern "C" {
+
+int orc_hamming256(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+void orc_three_maxima(const int* sz, int L, int* i1, int* i2, int* i3) {
+    int a = -1, b = -1, c = -1;
+    three_maxima(sz, L, a, b, c);
+    *i1 = a; *i2 = b; *i3 = c;
+}
+
+int orc_features_in_area(const orc_frame_view* f, float x, float y, float r, int minL, int maxL, int* out, int cap) {
+    Grid g(f);
+    std::vector<int> v = features_in_area(f, g, x, y, r, minL, maxL);
+    if ((int)v.size() > cap) return -(int)v.size();
+    std::copy(v.begin(), v.end(), out);
+    return (int)v.size();
+}
+
+void orc_bf_top2(const uint8_t* q, int nq, const uint8_t* t, int nt, int* bi, int* bd, int* sd) {
+    for (int i = 0; i < nq; i++) {
+        int best = 256, second = 256, idx = -1;
+        for (int j = 0; j < nt; j++) {
+            int d = descriptor_distance(q + 32 * (size_t)i, t + 32 * (size_t)j);
+            if (d < best) { second = best; best = d; idx = j; }
+            else if (d < second) second = d;
+        }
+        bi[i] = idx; bd[i] = best; sd[i] = second;
+    }
+}
+
+// ---- src/ORBmatcher.cc:155-263
+int orc_search_by_bow(float nnratio, int check_ori, const orc_frame_view* kf, const orc_map_points* mps,
+                      const orc_frame_view* f, int* out) {
+    for (int i = 0; i < f->n; i++) out[i] = -1;
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int ki = 0, fi = 0;
+    while (ki < kf->fv_nodes && fi < f->fv_nodes) {
+        const uint32_t kn = kf->fv_node_id[ki], fn = f->fv_node_id[fi];
+        if (kn == fn) {
+            for (int a = kf->fv_offset[ki]; a < kf->fv_offset[ki + 1]; a++) {
+                const int realIdxKF = (int)kf->fv_index[a];
+                const int pMP = kf->map_point[realIdxKF];
+                if (pMP < 0) continue;
+                if (mp_bad(mps, pMP)) continue;
+                const uint8_t* dKF = kf->desc + 32 * (size_t)realIdxKF;
+                int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+                for (int b = f->fv_offset[fi]; b < f->fv_offset[fi + 1]; b++) {
+                    const int realIdxF = (int)f->fv_index[b];
+                    if (out[realIdxF] >= 0) continue;
+                    const int dist = descriptor_distance(dKF, f->desc + 32 * (size_t)realIdxF);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = realIdxF; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 <= TH_LOW) {
+                    if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        out[bestIdxF] = pMP;
+                        if (check_ori) rotHist[rot_bin(kf->keys[realIdxKF].angle, f->keys[bestIdxF].angle)].push_back(bestIdxF);
+                        nmatches++;
+                    }
+                }
+            }
+            ki++; fi++;
+        } else if (kn < fn) {
+            while (ki < kf->fv_nodes && kf->fv_node_id[ki] < fn) ki++;     // lower_bound(Fit->first)
+        } else {
+            while (fi < f->fv_nodes && f->fv_node_id[fi] < kn) fi++;
+        }
+    }
+    if (check_ori) {
+        int sz[HISTO_LENGTH], i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)rotHist[i].size();
+        three_maxima(sz, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int idx : rotHist[i]) { out[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:43-133
+int orc_search_by_projection_points(float nnratio, orc_frame_view* F, const orc_map_points* mps,
+                                    const int* query_ids, int nq, float th, int check_level) {
+    int nmatches = 0;
+    const bool bFactor = th != 1.0;
+    Grid g(F);
+    for (int q = 0; q < nq; q++) {
+        const int pMP = query_ids[q];
+        if (!mps->track_in_view[pMP]) continue;
+        if (mp_bad(mps, pMP)) continue;
+        const int nPredictedLevel = mps->track_scale_level[pMP];
+        float r = mps->track_view_cos[pMP] > 0.998 ? 2.5f : 4.0f;
+        if (bFactor) r *= th;
+        std::vector<int> vIndices = check_level
+            ? features_in_area(F, g, mps->track_proj_x[pMP], mps->track_proj_y[pMP], r * F->scale_factors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel)
+            : features_in_area(F, g, mps->track_proj_x[pMP], mps->track_proj_y[pMP], r * F->scale_factors[nPredictedLevel], -1, -1);
+        if (vIndices.empty()) continue;
+        const uint8_t* MPd = mps->desc + 32 * (size_t)pMP;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : vIndices) {
+            if (F->map_point[idx] >= 0)
+                if (mp_obs(mps, F->map_point[idx]) > 0) continue;
+            if (uright(F, idx) > 0) {
+                const float er = std::fabs(mps->track_proj_xr[pMP] - uright(F, idx));
+                if (er > r * F->scale_factors[nPredictedLevel]) continue;
+            }
+            const int dist = descriptor_distance(MPd, F->desc + 32 * (size_t)idx);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+                bestLevel = F->keys[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = F->keys[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            F->map_point[bestIdx] = pMP;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:1218-1350
+int orc_search_by_projection_last(int check_ori, orc_frame_view* C, const orc_frame_view* L,
+                                  const orc_map_points* mps, float th, int mono, int check_level) {
+    int nmatches = 0;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    const float* R = C->Rcw; const float* t = C->tcw;
+    // twc = -Rcw^T tcw ; tlc = Rlw twc + tlw
+    float twc[3], tlc[3];
+    for (int i = 0; i < 3; i++) twc[i] = -1 * (R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+    for (int i = 0; i < 3; i++) tlc[i] = L->Rcw[i * 3 + 0] * twc[0] + L->Rcw[i * 3 + 1] * twc[1] + L->Rcw[i * 3 + 2] * twc[2] + L->tcw[i];
+    const bool bForward = tlc[2] > C->mb && !mono;
+    const bool bBackward = -tlc[2] > C->mb && !mono;
+    Grid g(C);
+    for (int i = 0; i < L->n; i++) {
+        const int pMP = L->map_point[i];
+        if (pMP < 0) continue;
+        if (L->outlier && L->outlier[i]) continue;
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        const float xc = R[0] * Pw[0] + R[1] * Pw[1] + R[2] * Pw[2] + t[0];
+        const float yc = R[3] * Pw[0] + R[4] * Pw[1] + R[5] * Pw[2] + t[1];
+        const float zc = R[6] * Pw[0] + R[7] * Pw[1] + R[8] * Pw[2] + t[2];
+        const float invzc = (float)(1.0 / zc);
+        if (invzc < 0) continue;
+        float u = C->fx * xc * invzc + C->cx;
+        float v = C->fy * yc * invzc + C->cy;
+        if (u < C->min_x || u > C->max_x) continue;
+        if (v < C->min_y || v > C->max_y) continue;
+        const int nLastOctave = L->keys[i].octave;
+        const float radius = th * C->scale_factors[nLastOctave];
+        std::vector<int> vIndices2;
+        if (!check_level) vIndices2 = features_in_area(C, g, u, v, radius);
+        else if (bForward) vIndices2 = features_in_area(C, g, u, v, radius, nLastOctave);
+        else if (bBackward) vIndices2 = features_in_area(C, g, u, v, radius, 0, nLastOctave);
+        else vIndices2 = features_in_area(C, g, u, v, radius, nLastOctave - 1, nLastOctave + 1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = mps->desc + 32 * (size_t)pMP;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (C->map_point[i2] >= 0)
+                if (mp_obs(mps, C->map_point[i2]) > 0) continue;
+            if (uright(C, i2) > 0) {
+                const float ur = u - C->mbf * invzc;
+                const float er = std::fabs(ur - uright(C, i2));
+                if (er > radius) continue;
+            }
+            const int dist = descriptor_distance(dMP, C->desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            C->map_point[bestIdx2] = pMP;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(L->keys[i].angle, C->keys[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int sz[HISTO_LENGTH], i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)rotHist[i].size();
+        three_maxima(sz, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != i1 && i != i2 && i != i3)
+                for (int idx : rotHist[i]) { C->map_point[idx] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:1352-1469
+int orc_search_by_projection_kf(int check_ori, orc_frame_view* C, const orc_frame_view* KF,
+                                const orc_map_points* mps, const uint8_t* found, float th, int ORBdist) {
+    int nmatches = 0;
+    const float* R = C->Rcw; const float* t = C->tcw;
+    float Ow[3];
+    for (int i = 0; i < 3; i++) Ow[i] = -1 * (R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    Grid g(C);
+    for (int i = 0; i < KF->n; i++) {
+        const int pMP = KF->map_point[i];
+        if (pMP < 0) continue;
+        if (mp_bad(mps, pMP) || (found && found[pMP])) continue;
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        const float xc = R[0] * Pw[0] + R[1] * Pw[1] + R[2] * Pw[2] + t[0];
+        const float yc = R[3] * Pw[0] + R[4] * Pw[1] + R[5] * Pw[2] + t[1];
+        const float zc = R[6] * Pw[0] + R[7] * Pw[1] + R[8] * Pw[2] + t[2];
+        const float invzc = (float)(1.0 / zc);
+        const float u = C->fx * xc * invzc + C->cx;
+        const float v = C->fy * yc * invzc + C->cy;
+        if (u < C->min_x || u > C->max_x) continue;
+        if (v < C->min_y || v > C->max_y) continue;
+        const float PO[3] = {Pw[0] - Ow[0], Pw[1] - Ow[1], Pw[2] - Ow[2]};
+        const float dist3D = std::sqrt(PO[0] * PO[0] + PO[1] * PO[1] + PO[2] * PO[2]);
+        const float maxDistance = 1.2f * mps->max_dist[pMP];     // src/MapPoint.cc:338-341
+        const float minDistance = 0.8f * mps->min_dist[pMP];     // :333-336
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        // MapPoint::PredictScale src/MapPoint.cc:359-373
+        const float ratio = mps->max_dist[pMP] / dist3D;
+        int nPredictedLevel = (int)std::ceil(std::log(ratio) / C->log_scale_factor);
+        if (nPredictedLevel < 0) nPredictedLevel = 0;
+        else if (nPredictedLevel >= C->n_levels) nPredictedLevel = C->n_levels - 1;
+        const float radius = th * C->scale_factors[nPredictedLevel];
+        const std::vector<int> vIndices2 = features_in_area(C, g, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* dMP = mps->desc + 32 * (size_t)pMP;
+        int bestDist = 256, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            if (C->map_point[i2] >= 0) continue;
+            const int dist = descriptor_distance(dMP, C->desc + 32 * (size_t)i2);
+            if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {
+            C->map_point[bestIdx2] = pMP;
+            nmatches++;
+            if (check_ori) rotHist[rot_bin(KF->keys[i].angle, C->keys[bestIdx2].angle)].push_back(bestIdx2);
+        }
+    }
+    if (check_ori) {
+        int sz[HISTO_LENGTH], i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)rotHist[i].size();
+        three_maxima(sz, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; i++)
+            if (i != i1 && i != i2 && i != i3)
+                for (int idx : rotHist[i]) { C->map_point[idx] = -1; nmatches--; }
+    }
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:375-478
+int orc_search_for_initialization(float nnratio, int check_ori, const orc_frame_view* F1, const orc_frame_view* F2,
+                                  float* prev, int* m12, int windowSize) {
+    int nmatches = 0;
+    for (int i = 0; i < F1->n; i++) m12[i] = -1;
+    std::vector<int> rotHist[HISTO_LENGTH];
+    std::vector<int> vMatchedDistance(F2->n, INT_MAX);
+    std::vector<int> vnMatches21(F2->n, -1);
+    Grid g(F2);
+    for (int i1 = 0; i1 < F1->n; i1++) {
+        const int level1 = F1->keys[i1].octave;
+        if (level1 > 0) continue;
+        std::vector<int> vIndices2 = features_in_area(F2, g, prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1);
+        if (vIndices2.empty()) continue;
+        const uint8_t* d1 = F1->desc + 32 * (size_t)i1;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int i2 : vIndices2) {
+            const int dist = descriptor_distance(d1, F2->desc + 32 * (size_t)i2);
+            if (vMatchedDistance[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= TH_LOW) {
+            if (bestDist < (float)bestDist2 * nnratio) {
+                if (vnMatches21[bestIdx2] >= 0) { m12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                m12[i1] = bestIdx2;
+                vnMatches21[bestIdx2] = i1;
+                vMatchedDistance[bestIdx2] = bestDist;
+                nmatches++;
+                if (check_ori) rotHist[rot_bin(F1->keys[i1].angle, F2->keys[bestIdx2].angle)].push_back(i1);
+            }
+        }
+    }
+    if (check_ori) {
+        int sz[HISTO_LENGTH], i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)rotHist[i].size();
+        three_maxima(sz, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int idx1 : rotHist[i])
+                if (m12[idx1] >= 0) { m12[idx1] = -1; nmatches--; }
+        }
+    }
+    for (int i1 = 0; i1 < F1->n; i1++)
+        if (m12[i1] >= 0) { prev[2 * i1] = F2->keys[m12[i1]].x; prev[2 * i1 + 1] = F2->keys[m12[i1]].y; }
+    return nmatches;
+}
+
+}  // extern "C"

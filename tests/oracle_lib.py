@@ -1,0 +1,246 @@
+"""ctypes binding of the CPU oracle (oracle/libygz_oracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int)
+u32p = C.POINTER(C.c_uint32)
+
+
+def _ptr(a, t):
+    if a is None:
+        return C.cast(None, t)
+    return a.ctypes.data_as(t)
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int), ("keys", C.c_void_p), ("desc", u8p), ("u_right", f32p), ("outlier", u8p),
+                ("map_point", i32p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("mb", C.c_float), ("mbf", C.c_float),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("n_levels", C.c_int), ("scale_factors", f32p), ("inv_scale_factors", f32p),
+                ("log_scale_factor", C.c_float), ("Rcw", C.c_float * 9), ("tcw", C.c_float * 3),
+                ("fv_nodes", C.c_int), ("fv_node_id", u32p), ("fv_offset", i32p), ("fv_index", u32p)]
+
+
+class MapPoints(C.Structure):
+    _fields_ = [("m", C.c_int), ("world_pos", f32p), ("desc", u8p), ("bad", u8p), ("observations", i32p),
+                ("min_dist", f32p), ("max_dist", f32p), ("track_in_view", u8p), ("track_proj_x", f32p),
+                ("track_proj_y", f32p), ("track_proj_xr", f32p), ("track_scale_level", i32p),
+                ("track_view_cos", f32p)]
+
+
+class SiaProblem(C.Structure):
+    _fields_ = [("n_levels", C.c_int), ("ref_levels", C.POINTER(u8p)), ("cur_levels", C.POINTER(u8p)),
+                ("level_w", i32p), ("level_h", i32p), ("inv_scale_factors", f32p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("n", C.c_int), ("ref_px", f32p), ("world_xyz", f32p), ("valid", u8p),
+                ("ref_q", C.c_float * 4), ("ref_t", C.c_float * 3),
+                ("cur_q", C.c_float * 4), ("cur_t", C.c_float * 3)]
+
+
+def build(native=False):
+    target = "libygz_oracle_native.so" if native else "libygz_oracle.so"
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, target], check=True)
+    return os.path.join(ORACLE_DIR, target)
+
+
+_LIB = {}
+
+
+def lib(native=False):
+    if native in _LIB:
+        return _LIB[native]
+    target = os.path.join(ORACLE_DIR, "libygz_oracle_native.so" if native else "libygz_oracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".h", ".inc"))]
+    if (not os.path.exists(target)) or any(os.path.getmtime(s) > os.path.getmtime(target) for s in srcs):
+        build(native)
+    L = C.CDLL(target)
+    L.orc_extractor_create.restype = C.c_void_p
+    L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.orc_extractor_destroy.argtypes = [C.c_void_p]
+    L.orc_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.orc_extract_frame.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.orc_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
+    L.orc_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p]
+    L.orc_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orc_get_level_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.orc_extractor_tables.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, i32p, i32p]
+    L.orc_distribute_octtree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_int]
+    L.orc_extract_batch.restype = C.c_long
+    L.orc_extract_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_resize_linear_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+    L.orc_border_reflect101.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int]
+    L.orc_gauss7_sigma2_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+    L.orc_fast9_16.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.orc_fast_atan2_array.argtypes = [f32p, f32p, f32p, C.c_int]
+    L.orc_cosf_sinf_array.argtypes = [f32p, f32p, f32p, C.c_int]
+    L.orc_hamming256.argtypes = [u8p, u8p]
+    L.orc_search_by_bow.argtypes = [C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(MapPoints),
+                                    C.POINTER(FrameView), i32p]
+    L.orc_search_by_projection_points.argtypes = [C.c_float, C.POINTER(FrameView), C.POINTER(MapPoints), i32p,
+                                                  C.c_int, C.c_float, C.c_int]
+    L.orc_search_by_projection_last.argtypes = [C.c_int, C.POINTER(FrameView), C.POINTER(FrameView),
+                                                C.POINTER(MapPoints), C.c_float, C.c_int, C.c_int]
+    L.orc_search_by_projection_kf.argtypes = [C.c_int, C.POINTER(FrameView), C.POINTER(FrameView),
+                                              C.POINTER(MapPoints), u8p, C.c_float, C.c_int]
+    L.orc_search_for_initialization.argtypes = [C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView),
+                                                f32p, i32p, C.c_int]
+    L.orc_three_maxima.argtypes = [i32p, C.c_int, i32p, i32p, i32p]
+    L.orc_features_in_area.argtypes = [C.POINTER(FrameView), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
+                                       i32p, C.c_int]
+    L.orc_bf_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p]
+    L.orc_sia_run.argtypes = [C.POINTER(SiaProblem), C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p,
+                              f32p, C.c_int, i32p]
+    L.orc_se3_exp.argtypes = [f32p, f32p, f32p]
+    L.orc_se3_mul.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p]
+    L.orc_se3_inv.argtypes = [f32p, f32p, f32p, f32p]
+    _LIB[native] = L
+    return L
+
+
+class Extractor:
+    """Oracle ORBextractor (restates src/ORBextractor.cc)."""
+
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, native=False):
+        self.L = lib(native)
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = self.L.orc_extractor_create(nfeatures, scale, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        try:
+            self.L.orc_extractor_destroy(self.h)
+        except Exception:
+            pass
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        fpl = np.zeros(n, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.orc_extractor_tables(self.h, _ptr(sc, f32p), _ptr(isc, f32p), _ptr(s2, f32p), _ptr(is2, f32p),
+                                    _ptr(fpl, i32p), _ptr(um, i32p))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, features_per_level=fpl, umax=um)
+
+    def extract(self, img, cap=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = cap or (self.nfeatures * 2 + 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_extract(self.h, _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0],
+                               kps.ctypes.data, _ptr(desc, u8p), cap)
+        assert n >= 0, n
+        return kps[:n].copy(), desc[:n].copy()
+
+    def extract_frame(self, img, existing, cap=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        ne = len(existing)
+        cap = cap or (self.nfeatures * 2 + ne + 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        kps[:ne] = existing
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_extract_frame(self.h, _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], ne,
+                                     kps.ctypes.data, _ptr(desc, u8p), cap)
+        assert n >= 0, n
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        self.L.orc_level_size(self.h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def level(self, level, blurred=False):
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        self.L.orc_get_level(self.h, level, int(blurred), _ptr(out, u8p))
+        return out
+
+    def candidates(self, level, cap=200000):
+        out = np.zeros(cap, KP_DTYPE)
+        n = self.L.orc_get_candidates(self.h, level, out.ctypes.data, cap)
+        assert n >= 0
+        return out[:n].copy()
+
+    def level_keys(self, level, cap=20000):
+        out = np.zeros(cap, KP_DTYPE)
+        n = self.L.orc_get_level_keys(self.h, level, out.ctypes.data, cap)
+        assert n >= 0
+        return out[:n].copy()
+
+    def distribute(self, keys, minX, maxX, minY, maxY, N):
+        keys = np.ascontiguousarray(keys, KP_DTYPE)
+        out = np.zeros(max(len(keys), 1), KP_DTYPE)
+        n = self.L.orc_distribute_octtree(self.h, keys.ctypes.data, len(keys), minX, maxX, minY, maxY, N,
+                                          out.ctypes.data, len(out))
+        assert n >= 0
+        return out[:n].copy()
+
+
+def resize(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_ptr(src, u8p), src.shape[1], src.shape[0], src.strides[0], _ptr(dst, u8p), dw, dh, dw)
+    return dst
+
+
+def border101(src, b):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((src.shape[0] + 2 * b, src.shape[1] + 2 * b), np.uint8)
+    lib().orc_border_reflect101(_ptr(src, u8p), src.shape[1], src.shape[0], src.strides[0], _ptr(dst, u8p), b, dst.shape[1])
+    return dst
+
+
+def gauss7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().orc_gauss7_sigma2_u8(_ptr(src, u8p), src.shape[1], src.shape[0], src.strides[0], _ptr(dst, u8p), src.shape[1])
+    return dst
+
+
+def fast9(img, threshold, nms=True, cap=400000):
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_fast9_16(C.cast(img.ctypes.data, u8p), img.shape[1], img.shape[0], img.strides[0], threshold,
+                           int(nms), out.ctypes.data, cap)
+    assert n >= 0
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    y = np.ascontiguousarray(y, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(y)
+    lib().orc_fast_atan2_array(_ptr(y, f32p), _ptr(x, f32p), _ptr(out, f32p), len(y))
+    return out
+
+
+def cos_sin_deg(deg):
+    deg = np.ascontiguousarray(deg, np.float32)
+    c = np.zeros_like(deg)
+    s = np.zeros_like(deg)
+    lib().orc_cosf_sinf_array(_ptr(deg, f32p), _ptr(c, f32p), _ptr(s, f32p), len(deg))
+    return c, s
+
+
+def bf_top2(q, t):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    bi = np.zeros(len(q), np.int32)
+    bd = np.zeros(len(q), np.int32)
+    sd = np.zeros(len(q), np.int32)
+    lib().orc_bf_top2(_ptr(q, u8p), len(q), _ptr(t, u8p), len(t), _ptr(bi, i32p), _ptr(bd, i32p), _ptr(sd, i32p))
+    return bi, bd, sd
