@@ -1,0 +1,235 @@
+/* ygz_b200 — C ABI of the B200-native ORB-YGZ-SLAM image front end (libygz_b200.so).
+ *
+ * The reference has no FFI layer: the boundary is the C++ class surface in namespace ygz, compiled
+ * into libygz-SLAM.so and used directly by Tracking.cc / Frame.cc.  The host-side
+ * mirror of those classes lives in include/ygz/{ORBextractor,ORBmatcher,SparseImageAlign}.h and is a
+ * thin C++ layer over the entry points below; each entry point cites the reference interface it
+ * replaces (file:line relative to /root/reference).
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * ygz_status on error, never throws (reference failure convention: "0 features / 0 matches",
+ * SURVEY.md §8b "Errors").  Handles own their device buffers and one CUDA stream; a handle may be
+ * used from one host thread at a time, different handles concurrently (include/ORBextractor.h is
+ * stateful and not re-entrant either; L/R extractors run on two threads, src/Frame.cc:728-731).
+ */
+#ifndef YGZ_B200_H
+#define YGZ_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    YGZ_OK = 0,
+    YGZ_ERR_ARG = -1,        /* bad argument / unsupported size */
+    YGZ_ERR_CUDA = -2,       /* CUDA runtime error (ygz_last_error() has the text) */
+    YGZ_ERR_CAPACITY = -3,   /* caller buffer or internal pool too small */
+    YGZ_ERR_NO_DEVICE = -4
+} ygz_status;
+
+const char* ygz_last_error(void);
+int ygz_device_count(void);
+/* name (<=255 chars), SM count, L2 bytes of device `dev` */
+int ygz_device_info(int dev, char* name, int* sm_count, size_t* l2_bytes);
+
+/* == cv::KeyPoint (28 bytes, same field order): the element type of mvKeys (include/Frame.h) */
+typedef struct { float x, y, size, angle, response; int octave, class_id; } ygz_keypoint;
+
+/* ------------------------------------------------------------------ ORBextractor
+ * replaces ygz::ORBextractor (include/ORBextractor.h:45-172, src/ORBextractor.cc). */
+typedef struct {
+    int nfeatures;        /* ORBextractor ctor args, include/ORBextractor.h:59-60 */
+    float scale_factor;
+    int nlevels;
+    int ini_th_fast;
+    int min_th_fast;
+    int width, height;    /* frame geometry the handle is sized for */
+    int max_batch;        /* frames per launch (1 for the per-frame drop-in path) */
+    int device;           /* CUDA device ordinal */
+} ygz_orb_config;
+
+typedef struct ygz_orb ygz_orb;
+
+int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out);
+int ygz_orb_destroy(ygz_orb* h);
+/* Getters of include/ORBextractor.h:82-104 (arrays of nlevels floats) and mnFeaturesPerLevel */
+int ygz_orb_tables(ygz_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                   int* features_per_level);
+int ygz_orb_level_size(ygz_orb* h, int level, int* w, int* hgt);
+int ygz_orb_max_keypoints(ygz_orb* h);    /* upper bound of keypoints per frame (caller buffer size) */
+
+/* ORBextractor::operator()(InputArray image, mask, keypoints, descriptors), src/ORBextractor.cc:970-1028,
+ * for a batch of n independent frames (n = 1 is the reference call).  HOST buffers:
+ *   images   n frames, frame f at images + f*frame_stride, rows row_stride bytes apart, CV_8UC1
+ *   kps      n * cap entries; desc n * cap * 32 bytes; counts n ints (keypoints of frame f)
+ * Host->device and device->host copies are part of the call. */
+int ygz_orb_extract(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride,
+                    ygz_keypoint* kps, uint8_t* desc, int* counts, int cap);
+
+/* ORBextractor::operator()(Frame*, keypoints, descriptors, ORBSLAM_KEYPOINT, leftEye),
+ * src/ORBextractor.cc:1031-1127, single frame: kps[0..n_existing) are the frame's pre-existing
+ * (direct-tracked) keys whose descriptors are recomputed first (:1088-1099); new keys are appended.
+ * The pyramid is (re)built from `image` (Frame ctor -> ComputePyramid, src/Frame.cc:311,807). */
+int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int n_existing,
+                          ygz_keypoint* kps, uint8_t* desc, int* count, int cap);
+
+/* ORBextractor::ComputePyramid (src/ORBextractor.cc:1129-1150) only: builds levels on the device. */
+int ygz_orb_compute_pyramid(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride);
+/* mvImagePyramid[level] of frame f (include/ORBextractor.h:106), continuous w*h bytes (step == cols,
+ * as Frame clones it, src/Frame.cc:810-813).  border > 0 additionally reproduces the EDGE_THRESHOLD
+ * REFLECT_101 frame of src/ORBextractor.cc:1141-1146 into a (w+2b)*(h+2b) buffer. */
+int ygz_orb_get_level(ygz_orb* h, int frame, int level, int border, uint8_t* out);
+
+/* Split phases for device-resident timing (bench.py `value`) and stage-level parity tests. */
+int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride);
+int ygz_orb_run(ygz_orb* h, int n);                       /* all kernels, inputs already in HBM */
+int ygz_orb_download(ygz_orb* h, int n, ygz_keypoint* kps, uint8_t* desc, int* counts, int cap);
+int ygz_orb_sync(ygz_orb* h);
+/* FAST candidates of (frame, level) before DistributeOctTree, in the reference's order (cell
+ * row-major, raster inside a cell), coordinates relative to (16,16) (src/ORBextractor.cc:773-777). */
+int ygz_orb_get_candidates(ygz_orb* h, int frame, int level, ygz_keypoint* out, int cap);
+/* device-timed repeats of ygz_orb_run on the handle's stream (CUDA events): total ms and per-stage ms
+ * stage_ms[5] = {pyramid, fast_cells, octree, orient+describe, total}; launches = kernels per run */
+int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches);
+/* device pointers for zero-copy chaining into the matcher / aligner of the same process */
+int ygz_orb_device_outputs(ygz_orb* h, void** d_kps, void** d_desc, void** d_counts, int* cap);
+int ygz_orb_device_level(ygz_orb* h, int level, void** d_ptr, int* pitch, size_t* frame_stride);
+void* ygz_orb_stream(ygz_orb* h);
+
+/* ------------------------------------------------------------------ ORBmatcher
+ * replaces the Hamming search core of ygz::ORBmatcher (include/ORBmatcher.h:38-220, src/ORBmatcher.cc). */
+
+/* ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1507-1523 (host, pure) */
+int ygz_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+typedef struct ygz_matcher ygz_matcher;
+int ygz_matcher_create(int device, int max_queries, int max_targets, int max_pairs, ygz_matcher** out);
+int ygz_matcher_destroy(ygz_matcher* h);
+
+/* Dense brute force: for each of nq query descriptors the best / second-best of nt targets
+ * (first index wins ties, as the `dist < bestDist` scans of src/ORBmatcher.cc:207-213). HOST buffers. */
+int ygz_hamming_bf_top2(ygz_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                        int* best_idx, int* best_dist, int* second_dist);
+/* Candidate-list distances: dist[p] = Hamming(q[pair_q[p]], t[pair_t[p]]) for n_pairs pairs — the
+ * inner loop of every Search* variant (BoW bucket, grid window, row band). */
+int ygz_hamming_pairs(ygz_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt,
+                      const int* pair_q, const int* pair_t, int n_pairs, int* dist);
+
+/* Flat views of the pointer graph the Search* functions walk (Frame / KeyFrame / MapPoint). */
+typedef struct {
+    int n;                          /* Frame::N */
+    const ygz_keypoint* keys;       /* mvKeys */
+    const uint8_t* desc;            /* mDescriptors, n x 32 */
+    const float* u_right;           /* mvuRight (NULL: all -1) */
+    const uint8_t* outlier;         /* mvbOutlier (NULL: none) */
+    int* map_point;                 /* mvpMapPoints as indices into ygz_map_points, -1 = NULL */
+    float fx, fy, cx, cy, mb, mbf;  /* Frame statics, include/Frame.h:231-236 */
+    float min_x, min_y, max_x, max_y;         /* mnMinX.. */
+    int n_levels;
+    const float* scale_factors;     /* mvScaleFactors */
+    const float* inv_scale_factors; /* mvInvScaleFactors */
+    float log_scale_factor;         /* mfLogScaleFactor */
+    float Rcw[9];                   /* mTcw rotation, row-major */
+    float tcw[3];                   /* mTcw translation */
+    int fv_nodes;                   /* DBoW2::FeatureVector (map<NodeId, vector<uint>>) as CSR, ids ascending */
+    const uint32_t* fv_node_id;
+    const int* fv_offset;           /* fv_nodes + 1 */
+    const uint32_t* fv_index;
+} ygz_frame_view;
+
+typedef struct {
+    int m;
+    const float* world_pos;         /* m x 3, MapPoint::GetWorldPos */
+    const uint8_t* desc;            /* m x 32, MapPoint::GetDescriptor */
+    const uint8_t* bad;             /* isBad (NULL: none) */
+    const int* observations;        /* Observations (NULL: all 1) */
+    const float* min_dist;          /* mfMinDistance */
+    const float* max_dist;          /* mfMaxDistance */
+    const uint8_t* track_in_view;   /* written by Frame::isInFrustum, src/Frame.cc:363-422 */
+    const float* track_proj_x;
+    const float* track_proj_y;
+    const float* track_proj_xr;
+    const int* track_scale_level;
+    const float* track_view_cos;
+} ygz_map_points;
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:155-263.
+ * out_matches[f->n] = map-point index or -1; returns nmatches (>= 0) or a negative ygz_status. */
+int ygz_search_by_bow(ygz_matcher* h, float nnratio, int check_orientation, const ygz_frame_view* kf,
+                      const ygz_map_points* mps, const ygz_frame_view* f, int* out_matches);
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, checkLevel), src/ORBmatcher.cc:43-126 */
+int ygz_search_by_projection_points(ygz_matcher* h, float nnratio, ygz_frame_view* f, const ygz_map_points* mps,
+                                    const int* query_ids, int nq, float th, int check_level);
+/* ORBmatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono, checkLevel), src/ORBmatcher.cc:1218-1350 */
+int ygz_search_by_projection_last(ygz_matcher* h, int check_orientation, ygz_frame_view* cur,
+                                  const ygz_frame_view* last, const ygz_map_points* mps, float th, int mono,
+                                  int check_level);
+/* ORBmatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist), src/ORBmatcher.cc:1352-1469 */
+int ygz_search_by_projection_kf(ygz_matcher* h, int check_orientation, ygz_frame_view* cur,
+                                const ygz_frame_view* kf, const ygz_map_points* mps, const uint8_t* already_found,
+                                float th, int orb_dist);
+/* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:375-478 */
+int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_orientation, const ygz_frame_view* f1,
+                                  const ygz_frame_view* f2, float* prev_matched_xy, int* matches12, int window);
+
+/* Batched device-resident SearchByBoW over n independent (KF, F) pairs whose keypoints/descriptors are
+ * extractor outputs already in HBM (stream front end, BASELINE C2): pair p matches frame kf_idx[p]
+ * against frame f_idx[p] of the extractor batch; FeatureVectors are given per frame as node ids per
+ * feature (node_of_feature[frame][cap], 0xFFFFFFFF = none).  All KF features carry a map point.
+ * out_matches: n x cap ints (host), out_nmatches: n ints. */
+int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
+                            const int* kf_idx, const int* f_idx, int n_pairs, const uint32_t* node_of_feature,
+                            int* out_matches, int* out_nmatches);
+/* same, results left on the device; timing variant for bench.py (ms over `iters` repeats) */
+int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
+                                 int n_pairs, int iters, float* ms);
+
+/* ------------------------------------------------------------------ SparseImgAlign
+ * replaces ygz::SparseImgAlign (include/SparseImageAlign.h:14-113, src/SparseImageAlign.cc) and its
+ * Gauss-Newton driver (include/NLSSolver_impl.hpp:17-91). */
+typedef struct {
+    int n_levels;
+    const uint8_t* const* ref_levels;   /* HOST level images of the reference frame, continuous (stride == w) */
+    const uint8_t* const* cur_levels;
+    const int* level_w;
+    const int* level_h;
+    const float* inv_scale_factors;     /* ref_frame->mvInvScaleFactors */
+    float fx, fy, cx, cy;
+    int n;                              /* ref_frame->N */
+    const float* ref_px;                /* n x 2: mvKeys[i].pt */
+    const float* world_xyz;             /* n x 3: mvpMapPoints[i]->GetWorldPos() */
+    const uint8_t* valid;               /* n: map point non-null && !isBad && !mvbOutlier[i] */
+    float ref_q[4], ref_t[3];           /* ref_frame->mTcw as unit quaternion (x,y,z,w) + translation */
+    float cur_q[4], cur_t[3];           /* cur_frame->mTcw (initial guess) */
+} ygz_sia_problem;
+
+typedef struct ygz_sia ygz_sia;
+int ygz_sia_create(int device, int max_problems, int max_features, int max_level_pixels, ygz_sia** out);
+int ygz_sia_destroy(ygz_sia* h);
+/* SparseImgAlign::run(Frame* ref, Frame* cur, SE3f& TCR), src/SparseImageAlign.cc:20-49, for a batch of
+ * n_problems independent alignments (n_problems = 1 is the reference call).  Levels max_level..min_level
+ * (SparseImgAlign(nLevels-1, 1), src/Tracking.cc:207), n_iter Gauss-Newton iterations per level, eps as
+ * eps_ (src/SparseImageAlign.cc:17).  Outputs per problem: T_cur_from_ref (q[4], t[3]), H (36 floats,
+ * getFisherInformation's H_), n_tracked = n_meas_/patch_area_ (the return value of run). */
+int ygz_sia_run(ygz_sia* h, const ygz_sia_problem* problems, int n_problems, int max_level, int min_level,
+                int n_iter, float eps, float* out_q, float* out_t, float* out_H, int* out_n_tracked);
+/* per-iteration record of the last ygz_sia_run for problem `problem`: 8 floats per evaluated iteration
+ * {level, iter, chi2, n_meas, max|x|, accepted, 0, 0} (the verbose_ printout of NLSSolver_impl.hpp:76-83) */
+int ygz_sia_last_trace(ygz_sia* h, int problem, float* out, int cap, int* n);
+/* device-timed repeats (inputs resident) for bench.py */
+int ygz_sia_time(ygz_sia* h, int n_problems, int max_level, int min_level, int n_iter, float eps, int iters,
+                 float* ms);
+
+/* ------------------------------------------------------------------ throughput counters (multi-GPU)
+ * The only cross-rank exchange of the path is one all-gather of these; the library
+ * fills them, the launcher (torch.distributed / NCCL) gathers them. */
+typedef struct {
+    uint64_t frames, keypoints, matches, sia_iters, bytes_in, bytes_out, kernel_launches, elapsed_ns;
+} ygz_counters;
+int ygz_orb_counters(ygz_orb* h, ygz_counters* out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YGZ_B200_H */

@@ -1,0 +1,807 @@
+// ORBmatcher Hamming-distance search on the device + the host-side greedy/ratio/rotation passes that
+// reproduce the reference's sequential semantics (/root/reference/src/ORBmatcher.cc).
+//
+//   k_hamming_bf_top2   warp-per-query 256-bit popcount brute force, best / second best       (:1507-1523 inner loop)
+//   k_hamming_pairs     candidate-list distances (BoW bucket, grid window)                     (:197-214, :86-113, :1289-1311)
+//   k_bow_match_batch   whole SearchByBoW(KF,F) on the device for a batch of frame pairs       (:155-263)
+//
+// The Search* entry points walk flat views of the pointer graph on the host (candidate enumeration through the
+// 64x48 frame grid of src/Frame.cc:314-330,424-493), compute every candidate distance in one launch, then run the
+// order-dependent accept logic on the host exactly in the reference's order.
+#include "common.cuh"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <vector>
+
+using namespace ygz_b200;
+
+namespace {
+
+constexpr int TH_HIGH = 100;        // src/ORBmatcher.cc:36
+constexpr int TH_LOW = 50;          // :37
+constexpr int HISTO_LENGTH = 30;    // :38
+constexpr int GRID_COLS = 64;       // include/Frame.h:38
+constexpr int GRID_ROWS = 48;       // include/Frame.h:39
+
+// ---------------------------------------------------------------------------------------------- device
+__device__ __forceinline__ int hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// merge two (best, idx, second) triples; earlier index wins ties, `second` = second smallest value of the multiset
+__device__ __forceinline__ void merge_top2(int& b, int& bi, int& s, int ob, int obi, int os) {
+    if (ob < b || (ob == b && obi < bi)) { s = min(b, os); b = ob; bi = obi; }
+    else s = min(s, ob);
+}
+
+constexpr int BF_WARPS = 8;
+constexpr int BF_QPW = 4;           // queries per warp
+constexpr int BF_TILE = 256;        // targets per shared-memory tile
+
+// One warp owns BF_QPW queries (registers); the CTA streams target tiles through shared memory stored as
+// 8 word-planes so that lane j reading target j is bank-conflict free.
+__global__ void __launch_bounds__(BF_WARPS * 32) k_hamming_bf_top2(const uint32_t* __restrict__ q, int nq,
+                                                                   const uint32_t* __restrict__ t, int nt,
+                                                                   int* __restrict__ best_idx, int* __restrict__ best_d,
+                                                                   int* __restrict__ second_d) {
+    __shared__ uint32_t tile[8][BF_TILE];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = (blockIdx.x * BF_WARPS + warp) * BF_QPW;
+    uint32_t qr[BF_QPW][8];
+#pragma unroll
+    for (int k = 0; k < BF_QPW; k++)
+#pragma unroll
+        for (int w = 0; w < 8; w++) qr[k][w] = (q0 + k < nq) ? q[(size_t)(q0 + k) * 8 + w] : 0u;
+    int b[BF_QPW], bi[BF_QPW], s[BF_QPW];
+#pragma unroll
+    for (int k = 0; k < BF_QPW; k++) { b[k] = 256; bi[k] = INT_MAX; s[k] = 256; }
+    for (int t0 = 0; t0 < nt; t0 += BF_TILE) {
+        const int m = min(BF_TILE, nt - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * 8; i += BF_WARPS * 32) {      // coalesced global read, transposed smem write
+            const int j = i >> 3, w = i & 7;
+            tile[w][j] = t[(size_t)(t0 + j) * 8 + w];
+        }
+        __syncthreads();
+        for (int j = lane; j < m; j += 32) {
+            uint32_t tw[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) tw[w] = tile[w][j];
+#pragma unroll
+            for (int k = 0; k < BF_QPW; k++) {
+                int d = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) d += __popc(qr[k][w] ^ tw[w]);
+                // lanes see targets in increasing index order, so `<` keeps the first index on ties
+                if (d < b[k]) { s[k] = b[k]; b[k] = d; bi[k] = t0 + j; }
+                else if (d < s[k]) s[k] = d;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < BF_QPW; k++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, b[k], o);
+            const int obi = __shfl_xor_sync(0xffffffffu, bi[k], o);
+            const int os = __shfl_xor_sync(0xffffffffu, s[k], o);
+            merge_top2(b[k], bi[k], s[k], ob, obi, os);
+        }
+        if (lane == 0 && q0 + k < nq) {
+            best_idx[q0 + k] = (b[k] < 256) ? bi[k] : -1;
+            best_d[q0 + k] = b[k];
+            second_d[q0 + k] = s[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_hamming_pairs(const uint4* __restrict__ q, const uint4* __restrict__ t,
+                                                       const int* __restrict__ pq, const int* __restrict__ pt, int n,
+                                                       int* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* a = q + (size_t)pq[i] * 2;
+    const uint4* b = t + (size_t)pt[i] * 2;
+    dist[i] = hamming256(__ldg(a), __ldg(a + 1), __ldg(b), __ldg(b + 1));
+}
+
+// ---- batched device-resident SearchByBoW (src/ORBmatcher.cc:155-263)
+// One CTA per (KF, F) pair.  Features of both frames are sorted by (vocabulary node, feature index) — the
+// iteration order of two DBoW2::FeatureVector maps whose per-node vectors hold ascending feature indices — then
+// one warp per common node runs the reference's sequential loop over that node's KF features with the F
+// candidates spread over the lanes (a frame feature belongs to exactly one node, so nodes are independent).
+constexpr int BOW_THREADS = 256;
+constexpr int BOW_MAX_FEATS = 2048;
+
+__device__ inline void bitonic_sort_u64(unsigned long long* a, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+struct BowBatchArgs {
+    const ygz_keypoint* kps;     // [frames][cap]
+    const uint4* desc;           // [frames][cap][2]
+    const int* counts;           // [frames]
+    const uint32_t* node;        // [frames][cap]
+    int cap;
+    const int* kf_idx;           // [pairs]
+    const int* f_idx;
+    float nnratio;
+    int check_ori;
+    int* matches;                // [pairs][cap]
+    int* nmatches;               // [pairs]
+};
+
+__global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A) {
+    __shared__ unsigned long long skf[BOW_MAX_FEATS];    // (node << 32) | feature index, sorted
+    __shared__ unsigned long long sf[BOW_MAX_FEATS];
+    __shared__ short match_of_f[BOW_MAX_FEATS];          // KF feature matched to F feature (or -1)
+    __shared__ signed char bin_of_f[BOW_MAX_FEATS];
+    __shared__ int hist[HISTO_LENGTH];
+    __shared__ int s_keep[3];
+    __shared__ int s_n;
+    const int pair = blockIdx.x;
+    const int kf = A.kf_idx[pair], fr = A.f_idx[pair];
+    const int nk = min(A.counts[kf], BOW_MAX_FEATS), nf = min(A.counts[fr], BOW_MAX_FEATS);
+    const ygz_keypoint* kkp = A.kps + (size_t)kf * A.cap;
+    const ygz_keypoint* fkp = A.kps + (size_t)fr * A.cap;
+    const uint4* kd = A.desc + (size_t)kf * A.cap * 2;
+    const uint4* fd = A.desc + (size_t)fr * A.cap * 2;
+    int pk = 1; while (pk < nk) pk <<= 1;
+    int pf = 1; while (pf < nf) pf <<= 1;
+    for (int i = threadIdx.x; i < pk; i += BOW_THREADS)
+        skf[i] = i < nk ? (((unsigned long long)A.node[(size_t)kf * A.cap + i] << 32) | (unsigned)i) : ~0ull;
+    for (int i = threadIdx.x; i < pf; i += BOW_THREADS)
+        sf[i] = i < nf ? (((unsigned long long)A.node[(size_t)fr * A.cap + i] << 32) | (unsigned)i) : ~0ull;
+    for (int i = threadIdx.x; i < BOW_MAX_FEATS; i += BOW_THREADS) { match_of_f[i] = -1; bin_of_f[i] = -1; }
+    if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    bitonic_sort_u64(skf, pk);
+    bitonic_sort_u64(sf, pf);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = BOW_THREADS / 32;
+    // each warp scans the KF segment starts; segment s is handled by warp (s % nwarps)
+    int seg = 0;
+    for (int i0 = 0; i0 < nk;) {
+        const uint32_t node = (uint32_t)(skf[i0] >> 32);
+        int i1 = i0 + 1;
+        while (i1 < nk && (uint32_t)(skf[i1] >> 32) == node) i1++;
+        if (node != 0xFFFFFFFFu && (seg % nwarps) == warp) {
+            // F segment with the same node (lower_bound)
+            int lo = 0, hi = nf;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(sf[mid] >> 32) < node) lo = mid + 1; else hi = mid; }
+            int j1 = lo;
+            while (j1 < nf && (uint32_t)(sf[j1] >> 32) == node) j1++;
+            const int j0 = lo;
+            for (int i = i0; i < i1 && j1 > j0; i++) {
+                const int realIdxKF = (int)(skf[i] & 0xFFFFFFFFu);
+                const uint4 a0 = __ldg(kd + realIdxKF * 2), a1 = __ldg(kd + realIdxKF * 2 + 1);
+                int b = 256, bi = INT_MAX, s = 256;
+                for (int j = j0 + lane; j < j1; j += 32) {
+                    const int realIdxF = (int)(sf[j] & 0xFFFFFFFFu);
+                    if (match_of_f[realIdxF] >= 0) continue;                      // :200-201
+                    const int d = hamming256(a0, a1, __ldg(fd + realIdxF * 2), __ldg(fd + realIdxF * 2 + 1));
+                    // order inside the bucket = position j (ascending); keep position for the tie-break
+                    if (d < b) { s = b; b = d; bi = j; }
+                    else if (d < s) s = d;
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const int ob = __shfl_xor_sync(0xffffffffu, b, o);
+                    const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const int os = __shfl_xor_sync(0xffffffffu, s, o);
+                    merge_top2(b, bi, s, ob, obi, os);
+                }
+                if (lane == 0 && b <= TH_LOW && (float)b < A.nnratio * (float)s) {    // :216-217
+                    const int bestIdxF = (int)(sf[bi] & 0xFFFFFFFFu);
+                    match_of_f[bestIdxF] = (short)realIdxKF;
+                    if (A.check_ori) {
+                        float rot = kkp[realIdxKF].angle - fkp[bestIdxF].angle;        // :221-226
+                        if (rot < 0.0f) rot += 360.0f;
+                        int bin = (int)roundf(rot * (1.0f / HISTO_LENGTH));
+                        if (bin == HISTO_LENGTH) bin = 0;
+                        bin_of_f[bestIdxF] = (signed char)bin;
+                        atomicAdd(&hist[bin], 1);
+                    }
+                    atomicAdd(&s_n, 1);
+                }
+                __syncwarp();
+            }
+        }
+        seg++;
+        i0 = i1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (A.check_ori) {                      // ComputeThreeMaxima :1471-1502
+            int max1 = 0, max2 = 0, max3 = 0;
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                const int sz = hist[i];
+                if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; i3 = i2; i2 = i1; i1 = i; }
+                else if (sz > max2) { max3 = max2; max2 = sz; i3 = i2; i2 = i; }
+                else if (sz > max3) { max3 = sz; i3 = i; }
+            }
+            if (max2 < 0.1f * (float)max1) { i2 = -1; i3 = -1; }
+            else if (max3 < 0.1f * (float)max1) { i3 = -1; }
+        }
+        s_keep[0] = i1; s_keep[1] = i2; s_keep[2] = i3;
+    }
+    __syncthreads();
+    int removed = 0;
+    int* out = A.matches + (size_t)pair * A.cap;
+    for (int i = threadIdx.x; i < A.cap; i += BOW_THREADS) {
+        int m = i < nf ? match_of_f[i] : -1;
+        if (m >= 0 && A.check_ori) {
+            const int bin = bin_of_f[i];
+            if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { m = -1; removed++; }
+        }
+        out[i] = m;
+    }
+    if (removed) atomicSub(&s_n, removed);
+    __syncthreads();
+    if (threadIdx.x == 0) A.nmatches[pair] = s_n;
+}
+
+// ---------------------------------------------------------------------------------------------- host helpers
+struct Grid {     // Frame::AssignFeaturesToGrid src/Frame.cc:314-330, PosInGrid :483-493
+    std::vector<int> cell[GRID_COLS][GRID_ROWS];
+    float invW, invH;
+    explicit Grid(const ygz_frame_view* f) {
+        invW = static_cast<float>(GRID_COLS) / (f->max_x - f->min_x);
+        invH = static_cast<float>(GRID_ROWS) / (f->max_y - f->min_y);
+        for (int i = 0; i < f->n; i++) {
+            const int px = (int)std::round((f->keys[i].x - f->min_x) * invW);
+            const int py = (int)std::round((f->keys[i].y - f->min_y) * invH);
+            if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+            cell[px][py].push_back(i);
+        }
+    }
+};
+
+// Frame::GetFeaturesInArea src/Frame.cc:424-481 — appends to `out`
+void features_in_area(const ygz_frame_view* f, const Grid& g, float x, float y, float r, int minLevel, int maxLevel,
+                      std::vector<int>& out) {
+    const int nMinCellX = std::max(0, (int)std::floor((x - f->min_x - r) * g.invW));
+    if (nMinCellX >= GRID_COLS) return;
+    const int nMaxCellX = std::min(GRID_COLS - 1, (int)std::ceil((x - f->min_x + r) * g.invW));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)std::floor((y - f->min_y - r) * g.invH));
+    if (nMinCellY >= GRID_ROWS) return;
+    const int nMaxCellY = std::min(GRID_ROWS - 1, (int)std::ceil((y - f->min_y + r) * g.invH));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++)
+            for (int idx : g.cell[ix][iy]) {
+                const ygz_keypoint& kp = f->keys[idx];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                if (std::fabs(kp.x - x) < r && std::fabs(kp.y - y) < r) out.push_back(idx);
+            }
+}
+
+void three_maxima(const int* sz, int L, int& ind1, int& ind2, int& ind3) {   // src/ORBmatcher.cc:1471-1502
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = sz[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+inline int rot_bin(float a1, float a2) {      // :221-226
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)std::round(rot * (1.0f / HISTO_LENGTH));
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+struct RotHist {
+    std::vector<int> bins[HISTO_LENGTH];
+    void add(int bin, int v) { bins[bin].push_back(v); }
+    // calls drop(v) for every entry outside the three fullest bins
+    template <class F> void prune(F drop) {
+        int sz[HISTO_LENGTH], i1 = -1, i2 = -1, i3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)bins[i].size();
+        three_maxima(sz, HISTO_LENGTH, i1, i2, i3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == i1 || i == i2 || i == i3) continue;
+            for (int v : bins[i]) drop(v);
+        }
+    }
+};
+
+inline bool mp_bad(const ygz_map_points* m, int i) { return m->bad && m->bad[i]; }
+inline int mp_obs(const ygz_map_points* m, int i) { return m->observations ? m->observations[i] : 1; }
+inline float uright(const ygz_frame_view* f, int i) { return f->u_right ? f->u_right[i] : -1.f; }
+
+}  // namespace
+
+struct ygz_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int max_q = 0, max_t = 0, max_pairs = 0;
+    uint8_t *d_q = nullptr, *d_t = nullptr;
+    int *d_pq = nullptr, *d_pt = nullptr, *d_dist = nullptr;
+    int *d_bi = nullptr, *d_bd = nullptr, *d_sd = nullptr;
+    // batch BoW
+    int *d_kf_idx = nullptr, *d_f_idx = nullptr, *d_matches = nullptr, *d_nmatches = nullptr;
+    uint32_t* d_node = nullptr;
+    int bow_pairs_cap = 0, bow_cap = 0, bow_frames = 0;
+    BowBatchArgs last_args{};
+    int last_pairs = 0;
+};
+
+static int matcher_free(ygz_matcher* h) {
+    if (!h) return YGZ_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_pq); cudaFree(h->d_pt); cudaFree(h->d_dist);
+    cudaFree(h->d_bi); cudaFree(h->d_bd); cudaFree(h->d_sd);
+    cudaFree(h->d_kf_idx); cudaFree(h->d_f_idx); cudaFree(h->d_matches); cudaFree(h->d_nmatches); cudaFree(h->d_node);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return YGZ_OK;
+}
+
+// distances of all (query, target) pairs in one launch; host buffers in, host dist out
+static int pair_distances(ygz_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const std::vector<int>& pq,
+                          const std::vector<int>& pt, std::vector<int>& dist) {
+    const int n = (int)pq.size();
+    dist.resize(n);
+    if (n == 0) return YGZ_OK;
+    return ygz_hamming_pairs(h, q, nq, t, nt, pq.data(), pt.data(), n, dist.data());
+}
+
+extern "C" {
+
+int ygz_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 8; i++) {
+        uint32_t x, y;
+        std::memcpy(&x, a + 4 * i, 4);
+        std::memcpy(&y, b + 4 * i, 4);
+        d += __builtin_popcount(x ^ y);
+    }
+    return d;
+}
+
+int ygz_matcher_create(int device, int max_queries, int max_targets, int max_pairs, ygz_matcher** out) {
+    YGZ_ARG_CHECK(out && max_queries >= 1 && max_targets >= 1 && max_pairs >= 1);
+    if (ygz_device_count() <= device) { set_last_error("no such CUDA device"); return YGZ_ERR_NO_DEVICE; }
+    YGZ_CUDA_TRY(cudaSetDevice(device));
+    ygz_matcher* h = new ygz_matcher();
+    h->device = device; h->max_q = max_queries; h->max_t = max_targets; h->max_pairs = max_pairs;
+#define TRY_OR_FREE(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); matcher_free(h); return YGZ_ERR_CUDA; } } while (0)
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    TRY_OR_FREE(cudaEventCreate(&h->ev0));
+    TRY_OR_FREE(cudaEventCreate(&h->ev1));
+    TRY_OR_FREE(cudaMalloc(&h->d_q, (size_t)max_queries * 32));
+    TRY_OR_FREE(cudaMalloc(&h->d_t, (size_t)max_targets * 32));
+    TRY_OR_FREE(cudaMalloc(&h->d_pq, (size_t)max_pairs * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_pt, (size_t)max_pairs * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_dist, (size_t)max_pairs * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_bi, (size_t)max_queries * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_bd, (size_t)max_queries * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_sd, (size_t)max_queries * 4));
+#undef TRY_OR_FREE
+    *out = h;
+    return YGZ_OK;
+}
+
+int ygz_matcher_destroy(ygz_matcher* h) { return matcher_free(h); }
+
+int ygz_hamming_bf_top2(ygz_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, int* best_idx, int* best_dist,
+                        int* second_dist) {
+    YGZ_ARG_CHECK(h && nq >= 0 && nt >= 0 && nq <= h->max_q && nt <= h->max_t);
+    if (nq == 0) return YGZ_OK;
+    YGZ_ARG_CHECK(q && best_idx && best_dist && second_dist && (nt == 0 || t));
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+    if (nt) YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_t, t, (size_t)nt * 32, cudaMemcpyHostToDevice, h->stream));
+    const int qpb = BF_WARPS * BF_QPW;
+    k_hamming_bf_top2<<<ceil_div(nq, qpb), BF_WARPS * 32, 0, h->stream>>>((const uint32_t*)h->d_q, nq, (const uint32_t*)h->d_t, nt,
+                                                                         h->d_bi, h->d_bd, h->d_sd);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    YGZ_CUDA_TRY(cudaMemcpyAsync(best_idx, h->d_bi, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(best_dist, h->d_bd, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(second_dist, h->d_sd, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return YGZ_OK;
+}
+
+int ygz_hamming_pairs(ygz_matcher* h, const uint8_t* q, int nq, const uint8_t* t, int nt, const int* pair_q, const int* pair_t,
+                      int n_pairs, int* dist) {
+    YGZ_ARG_CHECK(h && nq >= 0 && nt >= 0 && n_pairs >= 0 && nq <= h->max_q && nt <= h->max_t);
+    if (n_pairs == 0) return YGZ_OK;
+    YGZ_ARG_CHECK(q && t && pair_q && pair_t && dist);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_q, q, (size_t)nq * 32, cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_t, t, (size_t)nt * 32, cudaMemcpyHostToDevice, h->stream));
+    for (int off = 0; off < n_pairs; off += h->max_pairs) {          // chunk through the pair buffers
+        const int m = std::min(h->max_pairs, n_pairs - off);
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_pq, pair_q + off, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_pt, pair_t + off, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+        k_hamming_pairs<<<ceil_div(m, 256), 256, 0, h->stream>>>((const uint4*)h->d_q, (const uint4*)h->d_t, h->d_pq, h->d_pt, m, h->d_dist);
+        YGZ_CUDA_TRY(cudaGetLastError());
+        YGZ_CUDA_TRY(cudaMemcpyAsync(dist + off, h->d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return YGZ_OK;
+}
+
+// ---- src/ORBmatcher.cc:155-263
+int ygz_search_by_bow(ygz_matcher* h, float nnratio, int check_ori, const ygz_frame_view* kf, const ygz_map_points* mps,
+                      const ygz_frame_view* f, int* out) {
+    YGZ_ARG_CHECK(h && kf && mps && f && out);
+    for (int i = 0; i < f->n; i++) out[i] = -1;
+    // 1) enumerate every (KF feature, F feature) pair that shares a vocabulary node, in the reference's loop order
+    struct Job { int kfIdx, first, count; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt;
+    int ki = 0, fi = 0;
+    while (ki < kf->fv_nodes && fi < f->fv_nodes) {
+        const uint32_t kn = kf->fv_node_id[ki], fn = f->fv_node_id[fi];
+        if (kn == fn) {
+            for (int a = kf->fv_offset[ki]; a < kf->fv_offset[ki + 1]; a++) {
+                const int realIdxKF = (int)kf->fv_index[a];
+                const int pMP = kf->map_point[realIdxKF];
+                if (pMP < 0 || mp_bad(mps, pMP)) continue;
+                Job j{realIdxKF, (int)pq.size(), f->fv_offset[fi + 1] - f->fv_offset[fi]};
+                for (int b = f->fv_offset[fi]; b < f->fv_offset[fi + 1]; b++) { pq.push_back(realIdxKF); pt.push_back((int)f->fv_index[b]); }
+                jobs.push_back(j);
+            }
+            ki++; fi++;
+        } else if (kn < fn) {
+            while (ki < kf->fv_nodes && kf->fv_node_id[ki] < fn) ki++;
+        } else {
+            while (fi < f->fv_nodes && f->fv_node_id[fi] < kn) fi++;
+        }
+    }
+    // 2) all distances in one launch
+    std::vector<int> dist;
+    int rc = pair_distances(h, kf->desc, kf->n, f->desc, f->n, pq, pt, dist);
+    if (rc) return rc;
+    // 3) greedy accept in the reference's order
+    int nmatches = 0;
+    RotHist rh;
+    for (const Job& j : jobs) {
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int realIdxF = pt[p];
+            if (out[realIdxF] >= 0) continue;
+            const int d = dist[p];
+            if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdxF = realIdxF; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist1 <= TH_LOW && static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+            out[bestIdxF] = kf->map_point[j.kfIdx];
+            if (check_ori) rh.add(rot_bin(kf->keys[j.kfIdx].angle, f->keys[bestIdxF].angle), bestIdxF);
+            nmatches++;
+        }
+    }
+    if (check_ori) rh.prune([&](int idx) { out[idx] = -1; nmatches--; });
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:43-126
+int ygz_search_by_projection_points(ygz_matcher* h, float nnratio, ygz_frame_view* F, const ygz_map_points* mps,
+                                    const int* query_ids, int nq, float th, int check_level) {
+    YGZ_ARG_CHECK(h && F && mps && (nq == 0 || query_ids));
+    const bool bFactor = th != 1.0;
+    Grid g(F);
+    struct Job { int pMP, first, count, level; float r; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt, cand;
+    for (int q = 0; q < nq; q++) {
+        const int pMP = query_ids[q];
+        if (!mps->track_in_view[pMP] || mp_bad(mps, pMP)) continue;
+        const int lvl = mps->track_scale_level[pMP];
+        float r = mps->track_view_cos[pMP] > 0.998 ? 2.5f : 4.0f;     // RadiusByViewingCos :128-133
+        if (bFactor) r *= th;
+        cand.clear();
+        features_in_area(F, g, mps->track_proj_x[pMP], mps->track_proj_y[pMP], r * F->scale_factors[lvl],
+                         check_level ? lvl - 1 : -1, check_level ? lvl : -1, cand);
+        if (cand.empty()) continue;
+        Job j{pMP, (int)pq.size(), (int)cand.size(), lvl, r};
+        for (int idx : cand) { pq.push_back(pMP); pt.push_back(idx); }
+        jobs.push_back(j);
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, mps->desc, mps->m, F->desc, F->n, pq, pt, dist);
+    if (rc) return rc;
+    int nmatches = 0;
+    for (const Job& j : jobs) {
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int idx = pt[p];
+            if (F->map_point[idx] >= 0 && mp_obs(mps, F->map_point[idx]) > 0) continue;       // :89-91
+            if (uright(F, idx) > 0) {                                                          // :93-97
+                const float er = std::fabs(mps->track_proj_xr[j.pMP] - uright(F, idx));
+                if (er > j.r * F->scale_factors[j.level]) continue;
+            }
+            const int d = dist[p];
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestLevel2 = bestLevel; bestLevel = F->keys[idx].octave; bestIdx = idx; }
+            else if (d < bestDist2) { bestLevel2 = F->keys[idx].octave; bestDist2 = d; }
+        }
+        if (bestDist <= TH_HIGH) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;           // :117-118
+            F->map_point[bestIdx] = j.pMP;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+static inline void project(const ygz_frame_view* C, const float* Pw, float& xc, float& yc, float& zc) {
+    const float* R = C->Rcw; const float* t = C->tcw;
+    xc = R[0] * Pw[0] + R[1] * Pw[1] + R[2] * Pw[2] + t[0];
+    yc = R[3] * Pw[0] + R[4] * Pw[1] + R[5] * Pw[2] + t[1];
+    zc = R[6] * Pw[0] + R[7] * Pw[1] + R[8] * Pw[2] + t[2];
+}
+
+// ---- src/ORBmatcher.cc:1218-1350
+int ygz_search_by_projection_last(ygz_matcher* h, int check_ori, ygz_frame_view* C, const ygz_frame_view* L,
+                                  const ygz_map_points* mps, float th, int mono, int check_level) {
+    YGZ_ARG_CHECK(h && C && L && mps);
+    const float* R = C->Rcw; const float* t = C->tcw;
+    float twc[3], tlc[3];
+    for (int i = 0; i < 3; i++) twc[i] = -1 * (R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+    for (int i = 0; i < 3; i++) tlc[i] = L->Rcw[i * 3 + 0] * twc[0] + L->Rcw[i * 3 + 1] * twc[1] + L->Rcw[i * 3 + 2] * twc[2] + L->tcw[i];
+    const bool bForward = tlc[2] > C->mb && !mono;
+    const bool bBackward = -tlc[2] > C->mb && !mono;
+    Grid g(C);
+    struct Job { int i, pMP, first, count; float u, invzc, radius; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt, cand;
+    for (int i = 0; i < L->n; i++) {
+        const int pMP = L->map_point[i];
+        if (pMP < 0) continue;
+        if (L->outlier && L->outlier[i]) continue;
+        float xc, yc, zc;
+        project(C, mps->world_pos + 3 * (size_t)pMP, xc, yc, zc);
+        const float invzc = (float)(1.0 / zc);
+        if (invzc < 0) continue;
+        const float u = C->fx * xc * invzc + C->cx;
+        const float v = C->fy * yc * invzc + C->cy;
+        if (u < C->min_x || u > C->max_x) continue;
+        if (v < C->min_y || v > C->max_y) continue;
+        const int nLastOctave = L->keys[i].octave;
+        const float radius = th * C->scale_factors[nLastOctave];
+        cand.clear();
+        if (!check_level) features_in_area(C, g, u, v, radius, -1, -1, cand);
+        else if (bForward) features_in_area(C, g, u, v, radius, nLastOctave, -1, cand);
+        else if (bBackward) features_in_area(C, g, u, v, radius, 0, nLastOctave, cand);
+        else features_in_area(C, g, u, v, radius, nLastOctave - 1, nLastOctave + 1, cand);
+        if (cand.empty()) continue;
+        Job j{i, pMP, (int)pq.size(), (int)cand.size(), u, invzc, radius};
+        for (int idx : cand) { pq.push_back(pMP); pt.push_back(idx); }
+        jobs.push_back(j);
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, mps->desc, mps->m, C->desc, C->n, pq, pt, dist);
+    if (rc) return rc;
+    int nmatches = 0;
+    RotHist rh;
+    for (const Job& j : jobs) {
+        int bestDist = 256, bestIdx2 = -1;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int i2 = pt[p];
+            if (C->map_point[i2] >= 0 && mp_obs(mps, C->map_point[i2]) > 0) continue;
+            if (uright(C, i2) > 0) {
+                const float ur = j.u - C->mbf * j.invzc;
+                if (std::fabs(ur - uright(C, i2)) > j.radius) continue;
+            }
+            if (dist[p] < bestDist) { bestDist = dist[p]; bestIdx2 = i2; }
+        }
+        if (bestDist <= TH_HIGH) {
+            C->map_point[bestIdx2] = j.pMP;
+            nmatches++;
+            if (check_ori) rh.add(rot_bin(L->keys[j.i].angle, C->keys[bestIdx2].angle), bestIdx2);
+        }
+    }
+    if (check_ori) rh.prune([&](int idx) { C->map_point[idx] = -1; nmatches--; });
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:1352-1469
+int ygz_search_by_projection_kf(ygz_matcher* h, int check_ori, ygz_frame_view* C, const ygz_frame_view* KF,
+                                const ygz_map_points* mps, const uint8_t* found, float th, int ORBdist) {
+    YGZ_ARG_CHECK(h && C && KF && mps);
+    const float* R = C->Rcw; const float* t = C->tcw;
+    float Ow[3];
+    for (int i = 0; i < 3; i++) Ow[i] = -1 * (R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+    Grid g(C);
+    struct Job { int i, pMP, first, count; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt, cand;
+    for (int i = 0; i < KF->n; i++) {
+        const int pMP = KF->map_point[i];
+        if (pMP < 0) continue;
+        if (mp_bad(mps, pMP) || (found && found[pMP])) continue;
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        float xc, yc, zc;
+        project(C, Pw, xc, yc, zc);
+        const float invzc = (float)(1.0 / zc);
+        const float u = C->fx * xc * invzc + C->cx;
+        const float v = C->fy * yc * invzc + C->cy;
+        if (u < C->min_x || u > C->max_x) continue;
+        if (v < C->min_y || v > C->max_y) continue;
+        const float PO[3] = {Pw[0] - Ow[0], Pw[1] - Ow[1], Pw[2] - Ow[2]};
+        const float dist3D = std::sqrt(PO[0] * PO[0] + PO[1] * PO[1] + PO[2] * PO[2]);
+        const float maxDistance = 1.2f * mps->max_dist[pMP], minDistance = 0.8f * mps->min_dist[pMP];   // src/MapPoint.cc:333-341
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float ratio = mps->max_dist[pMP] / dist3D;                                                // PredictScale src/MapPoint.cc:359-373
+        int lvl = (int)std::ceil(std::log(ratio) / C->log_scale_factor);
+        if (lvl < 0) lvl = 0; else if (lvl >= C->n_levels) lvl = C->n_levels - 1;
+        const float radius = th * C->scale_factors[lvl];
+        cand.clear();
+        features_in_area(C, g, u, v, radius, lvl - 1, lvl + 1, cand);
+        if (cand.empty()) continue;
+        Job j{i, pMP, (int)pq.size(), (int)cand.size()};
+        for (int idx : cand) { pq.push_back(pMP); pt.push_back(idx); }
+        jobs.push_back(j);
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, mps->desc, mps->m, C->desc, C->n, pq, pt, dist);
+    if (rc) return rc;
+    int nmatches = 0;
+    RotHist rh;
+    for (const Job& j : jobs) {
+        int bestDist = 256, bestIdx2 = -1;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int i2 = pt[p];
+            if (C->map_point[i2] >= 0) continue;
+            if (dist[p] < bestDist) { bestDist = dist[p]; bestIdx2 = i2; }
+        }
+        if (bestDist <= ORBdist) {
+            C->map_point[bestIdx2] = j.pMP;
+            nmatches++;
+            if (check_ori) rh.add(rot_bin(KF->keys[j.i].angle, C->keys[bestIdx2].angle), bestIdx2);
+        }
+    }
+    if (check_ori) rh.prune([&](int idx) { C->map_point[idx] = -1; nmatches--; });
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:375-478
+int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_ori, const ygz_frame_view* F1,
+                                  const ygz_frame_view* F2, float* prev, int* m12, int windowSize) {
+    YGZ_ARG_CHECK(h && F1 && F2 && prev && m12);
+    for (int i = 0; i < F1->n; i++) m12[i] = -1;
+    Grid g(F2);
+    struct Job { int i1, first, count; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt, cand;
+    for (int i1 = 0; i1 < F1->n; i1++) {
+        const int level1 = F1->keys[i1].octave;
+        if (level1 > 0) continue;
+        cand.clear();
+        features_in_area(F2, g, prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1, cand);
+        if (cand.empty()) continue;
+        Job j{i1, (int)pq.size(), (int)cand.size()};
+        for (int idx : cand) { pq.push_back(i1); pt.push_back(idx); }
+        jobs.push_back(j);
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, F1->desc, F1->n, F2->desc, F2->n, pq, pt, dist);
+    if (rc) return rc;
+    int nmatches = 0;
+    RotHist rh;
+    std::vector<int> vMatchedDistance(F2->n, INT_MAX), vnMatches21(F2->n, -1);
+    for (const Job& j : jobs) {
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int i2 = pt[p], d = dist[p];
+            if (vMatchedDistance[i2] <= d) continue;
+            if (d < bestDist) { bestDist2 = bestDist; bestDist = d; bestIdx2 = i2; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist <= TH_LOW && bestDist < (float)bestDist2 * nnratio) {
+            if (vnMatches21[bestIdx2] >= 0) { m12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+            m12[j.i1] = bestIdx2;
+            vnMatches21[bestIdx2] = j.i1;
+            vMatchedDistance[bestIdx2] = bestDist;
+            nmatches++;
+            if (check_ori) rh.add(rot_bin(F1->keys[j.i1].angle, F2->keys[bestIdx2].angle), j.i1);
+        }
+    }
+    if (check_ori) rh.prune([&](int idx1) { if (m12[idx1] >= 0) { m12[idx1] = -1; nmatches--; } });
+    for (int i1 = 0; i1 < F1->n; i1++)
+        if (m12[i1] >= 0) { prev[2 * i1] = F2->keys[m12[i1]].x; prev[2 * i1 + 1] = F2->keys[m12[i1]].y; }
+    return nmatches;
+}
+
+// ---- batched device-resident SearchByBoW
+static int bow_batch_prepare(ygz_matcher* h, ygz_orb* orb, int n_pairs, int* cap_out, int* frames_out) {
+    void *d_kps, *d_desc, *d_counts;
+    int cap;
+    int rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap);
+    if (rc) return rc;
+    if (cap > BOW_MAX_FEATS) { set_last_error("batched SearchByBoW supports up to 2048 features per frame"); return YGZ_ERR_CAPACITY; }
+    if (n_pairs > h->bow_pairs_cap || cap != h->bow_cap) {
+        cudaFree(h->d_kf_idx); cudaFree(h->d_f_idx); cudaFree(h->d_matches); cudaFree(h->d_nmatches);
+        h->d_kf_idx = h->d_f_idx = h->d_matches = h->d_nmatches = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_kf_idx, (size_t)n_pairs * 4));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_f_idx, (size_t)n_pairs * 4));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_matches, (size_t)n_pairs * cap * 4));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_nmatches, (size_t)n_pairs * 4));
+        h->bow_pairs_cap = n_pairs;
+        h->bow_cap = cap;
+    }
+    *cap_out = cap;
+    (void)frames_out;
+    return YGZ_OK;
+}
+
+int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, const int* kf_idx, const int* f_idx,
+                            int n_pairs, const uint32_t* node_of_feature, int* out_matches, int* out_nmatches) {
+    YGZ_ARG_CHECK(h && orb && kf_idx && f_idx && n_pairs >= 1 && node_of_feature && out_matches && out_nmatches);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    int cap = 0, rc;
+    if ((rc = bow_batch_prepare(h, orb, n_pairs, &cap, nullptr))) return rc;
+    int max_frame = 0;
+    for (int i = 0; i < n_pairs; i++) max_frame = std::max(max_frame, std::max(kf_idx[i], f_idx[i]));
+    const int frames = max_frame + 1;
+    if (frames > h->bow_frames) {
+        cudaFree(h->d_node); h->d_node = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_node, (size_t)frames * cap * 4));
+        h->bow_frames = frames;
+    }
+    void *d_kps, *d_desc, *d_counts;
+    ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, nullptr);
+    // the extractor's stream produced the inputs: order our stream after it
+    YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_node, node_of_feature, (size_t)frames * cap * 4, cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_kf_idx, kf_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_f_idx, f_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+    BowBatchArgs A;
+    A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
+    A.node = h->d_node; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
+    A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
+    k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, h->stream>>>(A);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    h->last_args = A;
+    h->last_pairs = n_pairs;
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_matches, h->d_matches, (size_t)n_pairs * cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_nmatches, h->d_nmatches, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return YGZ_OK;
+}
+
+int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, int n_pairs, int iters, float* ms) {
+    YGZ_ARG_CHECK(h && orb && ms && iters >= 1 && h->last_pairs >= 1 && n_pairs == h->last_pairs);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    BowBatchArgs A = h->last_args;
+    A.nnratio = nnratio; A.check_ori = check_ori;
+    YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < iters; i++) k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, h->stream>>>(A);
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
+    YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return YGZ_OK;
+}
+
+}  // extern "C"

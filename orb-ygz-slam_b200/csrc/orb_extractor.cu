@@ -1,0 +1,607 @@
+// Host side of the batched ORB extractor: geometry / table construction that mirrors the
+// ORBextractor constructor and cell loop (src/ORBextractor.cc:412-470, 725-762, 1129-1133), device
+// buffers, kernel launches and the extern "C" entry points declared in include/ygz_b200.h.
+#include "orb_kernels.cuh"
+#include "trig_glibc.cuh"
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <vector>
+
+namespace ygz_b200 {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+
+static const int8_t h_pattern[256 * 4] = {
+#include "orb_pattern.inc"
+};
+
+struct LevelHost {
+    int w, h, pitch;
+    size_t frame_stride;
+    uint8_t* d_base = nullptr;
+    ResizeTabX* d_tx = nullptr;
+    ResizeTabY* d_ty = nullptr;
+};
+
+}  // namespace ygz_b200
+
+using namespace ygz_b200;
+
+struct ygz_orb {
+    ygz_orb_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    OrbParams P;
+    std::vector<LevelHost> lv;
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> feat_per_level;
+    std::vector<CellDesc> cells;
+    CellDesc* d_cells = nullptr;
+    uint32_t* d_pool = nullptr;
+    uint16_t* d_cell_count = nullptr;
+    uint32_t* d_keys = nullptr;
+    uint16_t* d_keynode = nullptr;
+    int* d_nkeys = nullptr;
+    uint32_t* d_sel = nullptr;
+    int* d_nsel = nullptr;
+    ygz_keypoint* d_kps = nullptr;
+    uint8_t* d_desc = nullptr;
+    int* d_counts = nullptr;
+    ExistingKey* d_existing = nullptr;
+    int existing_cap = 0;
+    size_t fast_smem = 0, oct_smem = 0;
+    int launches_per_run = 0;
+    ygz_counters ctr = {};
+    int last_n = 0;
+};
+
+static void build_resize_tables(int ssize, int dsize, std::vector<ResizeTabX>* tx, std::vector<ResizeTabY>* ty) {
+    // cv::resize INTER_LINEAR table construction (imgproc/resize.cpp): fx = (float)((dx+0.5)*scale - 0.5),
+    // sx = cvFloor(fx), coefficients saturate_cast<short>(w * 2048)
+    const double scale = 1.0 / ((double)dsize / ssize);
+    for (int d = 0; d < dsize; d++) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = host_cv_floor(f);
+        f -= s;
+        if (tx) {
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+            ResizeTabX t;
+            t.ofs = s;
+            t.a0 = (short)host_cv_round((1.f - f) * 2048);
+            t.a1 = (short)host_cv_round(f * 2048);
+            tx->push_back(t);
+        } else {
+            ResizeTabY t;   // vertical: fractional weights kept, row indices clipped
+            t.b0 = (short)host_cv_round((1.f - f) * 2048);
+            t.b1 = (short)host_cv_round(f * 2048);
+            t.y0 = (short)std::min(std::max(s, 0), ssize - 1);
+            t.y1 = (short)std::min(std::max(s + 1, 0), ssize - 1);
+            ty->push_back(t);
+        }
+    }
+}
+
+static int orb_free(ygz_orb* h) {
+    if (!h) return YGZ_OK;
+    cudaSetDevice(h->device);
+    for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_tx); cudaFree(L.d_ty); }
+    cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
+    cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return YGZ_OK;
+}
+
+extern "C" {
+
+const char* ygz_last_error(void) { return g_last_error.c_str(); }
+
+int ygz_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ygz_device_info(int dev, char* name, int* sm_count, size_t* l2_bytes) {
+    cudaDeviceProp p;
+    YGZ_CUDA_TRY(cudaGetDeviceProperties(&p, dev));
+    if (name) { std::strncpy(name, p.name, 255); name[255] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = (size_t)p.l2CacheSize;
+    return YGZ_OK;
+}
+
+int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
+    YGZ_ARG_CHECK(cfg && out);
+    YGZ_ARG_CHECK(cfg->nlevels >= 1 && cfg->nlevels <= MAX_LEVELS);
+    YGZ_ARG_CHECK(cfg->width >= 64 && cfg->height >= 64 && cfg->width <= 4096 && cfg->height <= 4096);
+    YGZ_ARG_CHECK(cfg->max_batch >= 1 && cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f);
+    YGZ_ARG_CHECK(cfg->ini_th_fast >= cfg->min_th_fast && cfg->min_th_fast >= 0 && cfg->ini_th_fast <= 255);
+    if (ygz_device_count() <= cfg->device) { set_last_error("no such CUDA device"); return YGZ_ERR_NO_DEVICE; }
+    YGZ_CUDA_TRY(cudaSetDevice(cfg->device));
+    ygz_orb* h = new ygz_orb();
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    const int nl = cfg->nlevels, B = cfg->max_batch;
+    std::memset(&h->P, 0, sizeof(h->P));
+
+    // ---- scale tables and features per level (src/ORBextractor.cc:416-445); scaleFactor is a double member
+    const double sf = (double)cfg->scale_factor;
+    h->scale.resize(nl); h->inv_scale.resize(nl); h->sigma2.resize(nl); h->inv_sigma2.resize(nl);
+    h->scale[0] = 1.0f; h->sigma2[0] = 1.0f;
+    for (int i = 1; i < nl; i++) {
+        h->scale[i] = (float)(h->scale[i - 1] * sf);
+        h->sigma2[i] = h->scale[i] * h->scale[i];
+    }
+    for (int i = 0; i < nl; i++) { h->inv_scale[i] = 1.0f / h->scale[i]; h->inv_sigma2[i] = 1.0f / h->sigma2[i]; }
+    h->feat_per_level.resize(nl);
+    {
+        float factor = (float)(1.0f / sf);
+        float nDesired = (float)(cfg->nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl)));
+        int sum = 0;
+        for (int l = 0; l < nl - 1; l++) {
+            h->feat_per_level[l] = host_cv_round(nDesired);
+            sum += h->feat_per_level[l];
+            nDesired *= factor;
+        }
+        h->feat_per_level[nl - 1] = std::max(cfg->nfeatures - sum, 0);
+    }
+    // ---- umax (src/ORBextractor.cc:453-467)
+    {
+        int umax[HALF_PATCH + 2] = {0};
+        int v, v0, vmax = host_cv_floor((float)(HALF_PATCH * std::sqrt(2.f) / 2 + 1));
+        int vmin = (int)std::ceil(HALF_PATCH * std::sqrt(2.f) / 2);
+        const double hp2 = HALF_PATCH * HALF_PATCH;
+        for (v = 0; v <= vmax; ++v) umax[v] = host_cv_round(std::sqrt(hp2 - v * v));
+        for (v = HALF_PATCH, v0 = 0; v >= vmin; --v) {
+            while (umax[v0] == umax[v0 + 1]) ++v0;
+            umax[v] = v0;
+            ++v0;
+        }
+        for (int i = 0; i < 16; i++) h->P.umax[i] = umax[i];
+    }
+
+    // ---- level geometry (:1131-1132), FAST cells (:739-762), octree roots (:537-551)
+    h->lv.resize(nl);
+    h->P.nlevels = nl;
+    h->P.ini_th = cfg->ini_th_fast;
+    h->P.min_th = cfg->min_th_fast;
+    int pool = 0, key_total = 0, sel_total = 0;
+    size_t fast_smem = 0, oct_smem = 0;
+    for (int l = 0; l < nl; l++) {
+        LevelHost& L = h->lv[l];
+        L.w = host_cv_round((float)cfg->width * h->inv_scale[l]);
+        L.h = host_cv_round((float)cfg->height * h->inv_scale[l]);
+        if (L.w < 1 || L.h < 1) { orb_free(h); set_last_error("pyramid level vanishes"); return YGZ_ERR_ARG; }
+        L.pitch = round_up(L.w, 32);
+        L.frame_stride = (size_t)L.pitch * L.h;
+        LevelDev& D = h->P.lv[l];
+        D.w = L.w; D.h = L.h; D.pitch = L.pitch; D.frame_stride = L.frame_stride;
+        D.scale = h->scale[l];
+        D.size = (float)(int)(31 * h->scale[l]);
+        D.cell_begin = (int)h->cells.size();
+        D.key_off = key_total;
+        const int minB = MIN_BORDER, maxBX = L.w - EDGE_THRESHOLD + 3, maxBY = L.h - EDGE_THRESHOLD + 3;
+        const float width = (float)(maxBX - minB), height = (float)(maxBY - minB);
+        const float W = 30;
+        const int nCols = (int)(width / W), nRows = (int)(height / W);
+        int key_cap = 0;
+        if (nCols > 0 && nRows > 0) {       // else: reference divides by zero; level yields nothing
+            const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+            for (int i = 0; i < nRows; i++) {
+                const float iniY = (float)(minB + i * hCell);
+                float maxY = iniY + hCell + 6;
+                if (iniY >= maxBY - 3) continue;
+                if (maxY > maxBY) maxY = (float)maxBY;
+                for (int j = 0; j < nCols; j++) {
+                    const float iniX = (float)(minB + j * wCell);
+                    float maxX = iniX + wCell + 6;
+                    if (iniX >= maxBX - 6) continue;
+                    if (maxX > maxBX) maxX = (float)maxBX;
+                    CellDesc c;
+                    c.level = (short)l;
+                    c.x0 = (short)iniX; c.y0 = (short)iniY;
+                    c.cw = (short)((int)maxX - (int)iniX); c.ch = (short)((int)maxY - (int)iniY);
+                    c.offx = (short)(j * wCell); c.offy = (short)(i * hCell);
+                    const int dw = std::max(c.cw - 6, 0), dh = std::max(c.ch - 6, 0);
+                    c.cap = (short)(((dw + 1) / 2) * ((dh + 1) / 2));
+                    c.out_off = pool;
+                    pool += c.cap;
+                    key_cap += c.cap;
+                    h->cells.push_back(c);
+                    if (dw > 0 && dh > 0) {
+                        size_t sm = round4(c.cw * c.ch) + round4((dw + 2) * (dh + 2)) + round4(dw * dh) + 2 * (size_t)(dw * dh + 160);
+                        fast_smem = std::max(fast_smem, sm);
+                    }
+                }
+            }
+        }
+        D.cell_end = (int)h->cells.size();
+        D.key_cap = key_cap;
+        key_total += key_cap;
+        // DistributeOctTree(minX=16, maxX, minY=16, maxY, N)
+        D.n_target = h->feat_per_level[l];
+        const int dx = maxBX - minB, dy = maxBY - minB;
+        int nIni = (dy > 0 && dx > 0) ? (int)std::round(static_cast<float>(dx) / dy) : 0;
+        if (nIni > MAX_ROOTS) { orb_free(h); set_last_error("aspect ratio > 16:1 unsupported"); return YGZ_ERR_ARG; }
+        D.n_roots = nIni;
+        D.root_h = dy;
+        if (nIni >= 1) {
+            const float hX = static_cast<float>(dx) / nIni;
+            D.hX = hX;
+            for (int i = 0; i < nIni; i++) {
+                D.root_x0[i] = (short)(int)(hX * static_cast<float>(i));
+                D.root_x1[i] = (short)(int)(hX * static_cast<float>(i + 1));
+            }
+        }
+        D.node_cap = std::max(D.n_target + 4, 4 * std::max(nIni, 1) + 4);
+        if (D.node_cap > 32000) { orb_free(h); set_last_error("nfeatures per level too large"); return YGZ_ERR_ARG; }
+        D.sel_off = sel_total;
+        sel_total += D.node_cap;
+        oct_smem = std::max(oct_smem, oct_smem_bytes(D.node_cap));
+    }
+    h->P.n_cells = (int)h->cells.size();
+    h->P.pool_size = std::max(pool, 1);
+    h->P.key_total = std::max(key_total, 1);
+    h->P.sel_total = sel_total;
+    h->P.out_cap = sel_total;
+    h->fast_smem = fast_smem;
+    h->oct_smem = oct_smem;
+    if (fast_smem > 200 * 1024 || oct_smem > 200 * 1024) { orb_free(h); set_last_error("shared memory budget exceeded"); return YGZ_ERR_ARG; }
+
+    // ---- device buffers
+#define TRY_OR_FREE(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); orb_free(h); return YGZ_ERR_CUDA; } } while (0)
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) TRY_OR_FREE(cudaEventCreate(&e));
+    for (int l = 0; l < nl; l++) {
+        LevelHost& L = h->lv[l];
+        TRY_OR_FREE(cudaMalloc(&L.d_base, L.frame_stride * B + 64));
+        h->P.lv[l].base = L.d_base;
+        if (l > 0) {
+            std::vector<ResizeTabX> tx;
+            std::vector<ResizeTabY> ty;
+            build_resize_tables(h->lv[l - 1].w, L.w, &tx, nullptr);
+            build_resize_tables(h->lv[l - 1].h, L.h, nullptr, &ty);
+            TRY_OR_FREE(cudaMalloc(&L.d_tx, tx.size() * sizeof(ResizeTabX)));
+            TRY_OR_FREE(cudaMalloc(&L.d_ty, ty.size() * sizeof(ResizeTabY)));
+            TRY_OR_FREE(cudaMemcpy(L.d_tx, tx.data(), tx.size() * sizeof(ResizeTabX), cudaMemcpyHostToDevice));
+            TRY_OR_FREE(cudaMemcpy(L.d_ty, ty.data(), ty.size() * sizeof(ResizeTabY), cudaMemcpyHostToDevice));
+            h->P.lv[l].tx = L.d_tx;
+            h->P.lv[l].ty = L.d_ty;
+        }
+    }
+    TRY_OR_FREE(cudaMalloc(&h->d_cells, std::max<size_t>(h->cells.size(), 1) * sizeof(CellDesc)));
+    if (!h->cells.empty())
+        TRY_OR_FREE(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMalloc(&h->d_pool, (size_t)h->P.pool_size * B * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_cell_count, (size_t)std::max(h->P.n_cells, 1) * B * 2));
+    TRY_OR_FREE(cudaMalloc(&h->d_keys, (size_t)h->P.key_total * B * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_keynode, (size_t)h->P.key_total * B * 2));
+    TRY_OR_FREE(cudaMalloc(&h->d_nkeys, (size_t)nl * B * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_sel, (size_t)h->P.sel_total * B * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_nsel, (size_t)nl * B * 4));
+    TRY_OR_FREE(cudaMalloc(&h->d_kps, (size_t)h->P.out_cap * B * sizeof(ygz_keypoint)));
+    TRY_OR_FREE(cudaMalloc(&h->d_desc, (size_t)h->P.out_cap * B * 32));
+    TRY_OR_FREE(cudaMalloc(&h->d_counts, (size_t)B * 4));
+    TRY_OR_FREE(cudaMemset(h->d_counts, 0, (size_t)B * 4));
+    TRY_OR_FREE(cudaMemset(h->d_nsel, 0, (size_t)nl * B * 4));
+    TRY_OR_FREE(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
+    TRY_OR_FREE(cudaDeviceSynchronize());
+#undef TRY_OR_FREE
+    *out = h;
+    return YGZ_OK;
+}
+
+int ygz_orb_destroy(ygz_orb* h) { return orb_free(h); }
+
+int ygz_orb_tables(ygz_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* fpl) {
+    YGZ_ARG_CHECK(h);
+    for (int i = 0; i < h->cfg.nlevels; i++) {
+        if (scale) scale[i] = h->scale[i];
+        if (inv_scale) inv_scale[i] = h->inv_scale[i];
+        if (sigma2) sigma2[i] = h->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = h->inv_sigma2[i];
+        if (fpl) fpl[i] = h->feat_per_level[i];
+    }
+    return YGZ_OK;
+}
+
+int ygz_orb_level_size(ygz_orb* h, int level, int* w, int* hgt) {
+    YGZ_ARG_CHECK(h && level >= 0 && level < h->cfg.nlevels);
+    if (w) *w = h->lv[level].w;
+    if (hgt) *hgt = h->lv[level].h;
+    return YGZ_OK;
+}
+
+int ygz_orb_max_keypoints(ygz_orb* h) { return h ? h->P.out_cap : YGZ_ERR_ARG; }
+void* ygz_orb_stream(ygz_orb* h) { return h ? (void*)h->stream : nullptr; }
+
+int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride) {
+    YGZ_ARG_CHECK(h && images && n >= 1 && n <= h->cfg.max_batch && row_stride >= h->cfg.width);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const LevelHost& L0 = h->lv[0];
+    if (frame_stride == (size_t)row_stride * L0.h) {
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(L0.d_base, L0.pitch, images, row_stride, L0.w, (size_t)L0.h * n,
+                                       cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int f = 0; f < n; f++)
+            YGZ_CUDA_TRY(cudaMemcpy2DAsync(L0.d_base + f * L0.frame_stride, L0.pitch, images + f * frame_stride, row_stride,
+                                           L0.w, L0.h, cudaMemcpyHostToDevice, h->stream));
+    }
+    h->ctr.bytes_in += (uint64_t)L0.w * L0.h * n;
+    h->last_n = n;
+    return YGZ_OK;
+}
+
+static int launch_pyramid(ygz_orb* h, int n) {
+    for (int l = 1; l < h->cfg.nlevels; l++) {
+        const LevelHost& S = h->lv[l - 1];
+        const LevelHost& D = h->lv[l];
+        dim3 block(64, 4);
+        dim3 grid(ceil_div(ceil_div(D.w, 4), 64), ceil_div(D.h, 4), n);
+        k_pyr_resize<<<grid, block, 0, h->stream>>>(S.d_base, S.pitch, S.frame_stride, S.w, D.d_base, D.pitch, D.frame_stride,
+                                                    D.w, D.h, D.d_tx, D.d_ty);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    return YGZ_OK;
+}
+
+static int launch_detect(ygz_orb* h, int n) {
+    if (h->P.n_cells > 0) {
+        dim3 grid(h->P.n_cells, n);
+        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    return YGZ_OK;
+}
+
+static int launch_octree(ygz_orb* h, int n) {
+    dim3 grid(h->cfg.nlevels, n);
+    k_octree<<<grid, OCT_THREADS, h->oct_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->d_keys,
+                                                            h->d_keynode, h->d_nkeys, h->d_sel, h->d_nsel);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    return YGZ_OK;
+}
+
+static int launch_describe(ygz_orb* h, int n, int n_existing) {
+    dim3 grid(h->P.sel_total, n);
+    k_orient_describe<<<grid, DESC_THREADS, 0, h->stream>>>(h->P, 0, n_existing, h->d_sel, h->d_nsel, nullptr, h->d_kps,
+                                                           h->d_desc, h->d_counts);
+    if (n_existing > 0) {
+        dim3 g2(n_existing, n);
+        k_orient_describe<<<g2, DESC_THREADS, 0, h->stream>>>(h->P, 1, n_existing, h->d_sel, h->d_nsel, h->d_existing,
+                                                             h->d_kps, h->d_desc, h->d_counts);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    return YGZ_OK;
+}
+
+int ygz_orb_run(ygz_orb* h, int n) {
+    YGZ_ARG_CHECK(h && n >= 1 && n <= h->cfg.max_batch);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = launch_pyramid(h, n))) return rc;
+    if ((rc = launch_detect(h, n))) return rc;
+    if ((rc = launch_octree(h, n))) return rc;
+    if ((rc = launch_describe(h, n, 0))) return rc;
+    h->launches_per_run = (h->cfg.nlevels - 1) + 3;
+    h->ctr.kernel_launches += h->launches_per_run;
+    h->ctr.frames += n;
+    h->last_n = n;
+    return YGZ_OK;
+}
+
+int ygz_orb_sync(ygz_orb* h) {
+    YGZ_ARG_CHECK(h);
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return YGZ_OK;
+}
+
+int ygz_orb_download(ygz_orb* h, int n, ygz_keypoint* kps, uint8_t* desc, int* counts, int cap) {
+    YGZ_ARG_CHECK(h && n >= 1 && n <= h->cfg.max_batch && counts && cap >= 0);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const int oc = h->P.out_cap;
+    YGZ_CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    const int m = std::min(cap, oc);
+    if (kps && m > 0)
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(ygz_keypoint), h->d_kps, (size_t)oc * sizeof(ygz_keypoint),
+                                       (size_t)m * sizeof(ygz_keypoint), n, cudaMemcpyDeviceToHost, h->stream));
+    if (desc && m > 0)
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)oc * 32, (size_t)m * 32, n,
+                                       cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    uint64_t tot = 0;
+    int rc = YGZ_OK;
+    for (int f = 0; f < n; f++) {
+        tot += counts[f];
+        if (counts[f] > cap) rc = YGZ_ERR_CAPACITY;
+    }
+    h->ctr.keypoints += tot;
+    h->ctr.bytes_out += (uint64_t)n * 4 + (uint64_t)n * m * (sizeof(ygz_keypoint) + 32);
+    if (rc) set_last_error("keypoint buffer too small (cap < count)");
+    return rc;
+}
+
+int ygz_orb_extract(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride, ygz_keypoint* kps,
+                    uint8_t* desc, int* counts, int cap) {
+    int rc;
+    if (!images || n <= 0) {            // operator() returns silently on an empty image (src/ORBextractor.cc:972-973)
+        if (counts) for (int i = 0; i < n; i++) counts[i] = 0;
+        return YGZ_OK;
+    }
+    if ((rc = ygz_orb_upload(h, images, n, frame_stride, row_stride))) return rc;
+    if ((rc = ygz_orb_run(h, n))) return rc;
+    return ygz_orb_download(h, n, kps, desc, counts, cap);
+}
+
+int ygz_orb_compute_pyramid(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride) {
+    int rc;
+    if ((rc = ygz_orb_upload(h, images, n, frame_stride, row_stride))) return rc;
+    if ((rc = launch_pyramid(h, n))) return rc;
+    h->ctr.kernel_launches += h->cfg.nlevels - 1;
+    return ygz_orb_sync(h);
+}
+
+int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int n_existing, ygz_keypoint* kps, uint8_t* desc,
+                          int* count, int cap) {
+    YGZ_ARG_CHECK(h && image && kps && desc && count && n_existing >= 0 && cap >= n_existing);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ygz_orb_upload(h, image, 1, (size_t)row_stride * h->cfg.height, row_stride))) return rc;
+    if (n_existing > h->existing_cap) {
+        cudaFree(h->d_existing);
+        h->d_existing = nullptr;
+        // outputs need room for the existing keys too
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_existing, (size_t)n_existing * sizeof(ExistingKey)));
+        h->existing_cap = n_existing;
+    }
+    if (n_existing + h->P.sel_total > h->P.out_cap) {
+        // grow the output arrays so existing + new keys fit
+        const int B = h->cfg.max_batch, oc = n_existing + h->P.sel_total;
+        cudaFree(h->d_kps); cudaFree(h->d_desc);
+        h->d_kps = nullptr; h->d_desc = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_kps, (size_t)oc * B * sizeof(ygz_keypoint)));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_desc, (size_t)oc * B * 32));
+        h->P.out_cap = oc;
+    }
+    std::vector<ExistingKey> ek(n_existing);
+    for (int i = 0; i < n_existing; i++) {
+        int oct = kps[i].octave;
+        if (oct < 0 || oct >= h->cfg.nlevels) { set_last_error("existing key octave out of range"); return YGZ_ERR_ARG; }
+        ek[i].x = kps[i].x * h->inv_scale[oct];        // tmp.pt *= mvInvScaleFactor[tmp.octave], :1095
+        ek[i].y = kps[i].y * h->inv_scale[oct];
+        ek[i].angle = kps[i].angle;
+        ek[i].octave = oct;
+    }
+    if (n_existing)
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_existing, ek.data(), (size_t)n_existing * sizeof(ExistingKey), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = launch_pyramid(h, 1))) return rc;
+    if ((rc = launch_detect(h, 1))) return rc;
+    if ((rc = launch_octree(h, 1))) return rc;
+    if ((rc = launch_describe(h, 1, n_existing))) return rc;
+    h->ctr.kernel_launches += (h->cfg.nlevels - 1) + 3 + (n_existing > 0);
+    h->ctr.frames += 1;
+    YGZ_CUDA_TRY(cudaMemcpyAsync(count, h->d_counts, 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (*count > cap) { set_last_error("keypoint buffer too small"); return YGZ_ERR_CAPACITY; }
+    const int n_new = *count - n_existing;
+    if (n_new > 0)
+        YGZ_CUDA_TRY(cudaMemcpyAsync(kps + n_existing, h->d_kps + n_existing, (size_t)n_new * sizeof(ygz_keypoint),
+                                     cudaMemcpyDeviceToHost, h->stream));
+    if (*count > 0)
+        YGZ_CUDA_TRY(cudaMemcpyAsync(desc, h->d_desc, (size_t)(*count) * 32, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ctr.keypoints += *count;
+    return YGZ_OK;
+}
+
+int ygz_orb_get_level(ygz_orb* h, int frame, int level, int border, uint8_t* out) {
+    YGZ_ARG_CHECK(h && out && frame >= 0 && frame < h->cfg.max_batch && level >= 0 && level < h->cfg.nlevels && border >= 0);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const LevelHost& L = h->lv[level];
+    YGZ_ARG_CHECK(border < L.w && border < L.h);
+    const int ow = L.w + 2 * border;
+    YGZ_CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)border * ow + border, ow, L.d_base + frame * L.frame_stride, L.pitch, L.w, L.h,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (border > 0) {      // copyMakeBorder(..., BORDER_REFLECT_101), src/ORBextractor.cc:1141-1146 (host index arithmetic)
+        auto refl = [](int p, int len) { if (p < 0) p = -p; if (p >= len) p = 2 * len - 2 - p; return p; };
+        for (int y = -border; y < L.h + border; y++) {
+            uint8_t* D = out + (size_t)(y + border) * ow;
+            const uint8_t* S = out + (size_t)(refl(y, L.h) + border) * ow + border;
+            if (y < 0 || y >= L.h) for (int x = 0; x < L.w; x++) D[x + border] = S[x];
+        }
+        for (int y = 0; y < L.h + 2 * border; y++) {
+            uint8_t* D = out + (size_t)y * ow;
+            for (int x = -border; x < 0; x++) D[x + border] = D[refl(x, L.w) + border];
+            for (int x = L.w; x < L.w + border; x++) D[x + border] = D[refl(x, L.w) + border];
+        }
+    }
+    return YGZ_OK;
+}
+
+int ygz_orb_get_candidates(ygz_orb* h, int frame, int level, ygz_keypoint* out, int cap) {
+    YGZ_ARG_CHECK(h && frame >= 0 && frame < h->cfg.max_batch && level >= 0 && level < h->cfg.nlevels);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int n = 0;
+    YGZ_CUDA_TRY(cudaMemcpy(&n, h->d_nkeys + (size_t)frame * h->cfg.nlevels + level, 4, cudaMemcpyDeviceToHost));
+    if (n > cap) return -n - 100;
+    std::vector<uint32_t> k(n);
+    if (n) YGZ_CUDA_TRY(cudaMemcpy(k.data(), h->d_keys + (size_t)frame * h->P.key_total + h->P.lv[level].key_off, (size_t)n * 4,
+                                   cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+        out[i].x = (float)(k[i] & 0xFFF);
+        out[i].y = (float)((k[i] >> 12) & 0xFFF);
+        out[i].size = 7.f; out[i].angle = -1.f;
+        out[i].response = (float)(k[i] >> 24);
+        out[i].octave = 0; out[i].class_id = -1;
+    }
+    return n;
+}
+
+int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches) {
+    YGZ_ARG_CHECK(h && n >= 1 && n <= h->cfg.max_batch && iters >= 1 && stage_ms);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    float acc[5] = {0, 0, 0, 0, 0};
+    int rc;
+    for (int it = 0; it < iters; it++) {
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+        if ((rc = launch_pyramid(h, n))) return rc;
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+        if ((rc = launch_detect(h, n))) return rc;
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+        if ((rc = launch_octree(h, n))) return rc;
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+        if ((rc = launch_describe(h, n, 0))) return rc;
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+        YGZ_CUDA_TRY(cudaEventSynchronize(h->ev[4]));
+        for (int s = 0; s < 4; s++) {
+            float ms = 0;
+            YGZ_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]));
+            acc[s] += ms;
+        }
+        float ms = 0;
+        YGZ_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4]));
+        acc[4] += ms;
+    }
+    for (int s = 0; s < 5; s++) stage_ms[s] = acc[s];
+    if (launches) *launches = ((h->cfg.nlevels - 1) + 3) * iters;
+    h->ctr.kernel_launches += (uint64_t)((h->cfg.nlevels - 1) + 3) * iters;
+    h->ctr.frames += (uint64_t)n * iters;
+    return YGZ_OK;
+}
+
+int ygz_orb_device_outputs(ygz_orb* h, void** d_kps, void** d_desc, void** d_counts, int* cap) {
+    YGZ_ARG_CHECK(h);
+    if (d_kps) *d_kps = h->d_kps;
+    if (d_desc) *d_desc = h->d_desc;
+    if (d_counts) *d_counts = h->d_counts;
+    if (cap) *cap = h->P.out_cap;
+    return YGZ_OK;
+}
+
+int ygz_orb_device_level(ygz_orb* h, int level, void** d_ptr, int* pitch, size_t* frame_stride) {
+    YGZ_ARG_CHECK(h && level >= 0 && level < h->cfg.nlevels);
+    if (d_ptr) *d_ptr = h->lv[level].d_base;
+    if (pitch) *pitch = h->lv[level].pitch;
+    if (frame_stride) *frame_stride = h->lv[level].frame_stride;
+    return YGZ_OK;
+}
+
+int ygz_orb_counters(ygz_orb* h, ygz_counters* out, int reset) {
+    YGZ_ARG_CHECK(h && out);
+    *out = h->ctr;
+    if (reset) h->ctr = ygz_counters{};
+    return YGZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+"""GPU parity of the ORB extractor (through the C ABI) against the oracle: bit-exact pyramid levels,
+FAST candidates (order + response), keypoints (all 7 fields) and 32-byte descriptors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KP_FIELDS = ("x", "y", "size", "angle", "response", "octave", "class_id")
+
+
+def assert_kps_equal(a, b, what=""):
+    assert len(a) == len(b), "%s: count %d vs %d" % (what, len(a), len(b))
+    for f in KP_FIELDS:
+        bad = np.nonzero(a[f] != b[f])[0]
+        assert bad.size == 0, "%s: field %s differs at %s: %s vs %s" % (what, f, bad[:5], a[f][bad[:5]], b[f][bad[:5]])
+
+
+CONFIGS = [
+    # (w, h, nfeatures, scale, nlevels, seeds)
+    (752, 480, 1000, 1.2, 8, [1, 2]),       # C1
+    (1242, 375, 2000, 1.2, 8, [5]),          # C5 (KITTI shape)
+    (752, 480, 1000, 2.0, 4, [7]),           # C3 pyramid (EuRoC.yaml): level 3 has no FAST cells
+    (320, 240, 500, 1.2, 8, [3, 4]),
+    (200, 150, 300, 1.5, 5, [9]),
+]
+
+
+@pytest.mark.parametrize("w,h,nf,sf,nl,seeds", CONFIGS)
+def test_extract_stages_bit_exact(gpu, oracle, synth, w, h, nf, sf, nl, seeds):
+    imgs = np.stack([synth.synth_frame(s, w, h) for s in seeds])
+    ex = gpu.ORBextractor(nf, sf, nl, 20, 7, width=w, height=h, max_batch=len(seeds))
+    res = ex.extract_batch(imgs)
+    ox = oracle.Extractor(nf, sf, nl, 20, 7)
+    t = ex.tables()
+    ot = ox.tables()
+    for k in ("scale", "inv_scale", "sigma2", "inv_sigma2", "features_per_level"):
+        assert (t[k] == ot[k]).all(), k
+    for f, seed in enumerate(seeds):
+        okps, odesc = ox.extract(imgs[f])
+        for l in range(nl):
+            assert ex.level_size(l) == ox.level_size(l)
+            assert (ex.level(f, l) == ox.level(l)).all(), "pyramid level %d" % l
+            gc = ex.candidates(f, l)
+            oc = ox.candidates(l)
+            assert_kps_equal(gc, oc, "candidates level %d" % l)
+        kps, desc = res[f]
+        assert_kps_equal(kps, okps, "keypoints seed %d" % seed)
+        assert (desc == odesc).all(), "descriptors: %d rows differ" % (desc != odesc).any(1).sum()
+
+
+def test_flat_and_noise_images(gpu, oracle):
+    w, h = 320, 240
+    rng = np.random.default_rng(0)
+    imgs = np.stack([np.full((h, w), 128, np.uint8),                        # no corners at all
+                     rng.integers(0, 256, (h, w), dtype=np.uint8),          # corners everywhere
+                     np.zeros((h, w), np.uint8)])
+    imgs[2, ::2, ::2] = 255                                                 # checker dots: many equal scores
+    ex = gpu.ORBextractor(500, 1.2, 8, 20, 7, width=w, height=h, max_batch=3)
+    res = ex.extract_batch(imgs)
+    ox = oracle.Extractor(500, 1.2, 8, 20, 7)
+    for f in range(3):
+        okps, odesc = ox.extract(imgs[f])
+        assert_kps_equal(res[f][0], okps, "image %d" % f)
+        assert (res[f][1] == odesc).all()
+    assert len(res[0][0]) == 0
+
+
+def test_border_pyramid(gpu, oracle, synth):
+    w, h = 320, 240
+    img = synth.synth_frame(11, w, h)
+    ex = gpu.ORBextractor(500, 1.2, 8, 20, 7, width=w, height=h)
+    ex.ComputePyramid(img)
+    ox = oracle.Extractor(500, 1.2, 8, 20, 7)
+    ox.extract(img)
+    for l in (0, 3, 7):
+        assert (ex.level(0, l, border=19) == oracle.border101(ox.level(l), 19)).all()
+
+
+def test_extract_frame_existing_keys(gpu, oracle, synth):
+    w, h = 752, 480
+    img = synth.synth_frame(21, w, h)
+    ex = gpu.ORBextractor(1000, 1.2, 8, 20, 7, width=w, height=h)
+    ox = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    base, _ = ox.extract(img)
+    existing = base[::7].copy()          # pretend these were direct-tracked from the last frame
+    okps, odesc = ox.extract_frame(img, existing)
+    kps, desc = ex.extract_frame(img, existing)
+    assert_kps_equal(kps, okps, "extract_frame")
+    assert (desc == odesc).all()
