@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py — front-end frames/sec of the B200-native ORB-YGZ-SLAM image front end.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B]
+
+Workload (BASELINE.json configs[1], "C2"): synthetic EuRoC-shape mono stream, 752x480 u8 frames,
+ORBextractor(1000, 1.2, 8, 20, 7) + ORBmatcher(0.7, checkOri).SearchByBoW of every frame against the previous
+one (synthetic bench vocabulary node = descriptor byte0 >> 2; DBoW2 transform is a "next" row).
+One "step" = one batch of B frames through the whole hot path (7 pyramid launches, FAST cells, octree,
+orientation+rBRIEF, batched SearchByBoW).  Inputs are B distinct frames (B*361 KB = 92 MB at B=256; pyramid working
+set 286 MB > the 126 MB L2, so no L2 flush is needed between steps).
+
+  value  whole-job frames/s with inputs already resident in HBM (CUDA events on the launching stream)
+  e2e    the same through the public C-ABI calls with HOST (pinned) buffers: H2D of the frames, D2H of
+         keypoints + descriptors + match arrays inside the timed region
+  roofline  for the dominant kernel (by device time) against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the oracle port (host-tuned build, all host threads) on a bounded sample of the same workload
+
+Multi-GPU (torchrun, one rank per GPU): frames are independent units, every rank runs its own batch (weak
+scaling, no data-path collective); the only exchange is one NCCL all-gather of throughput counters.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 752, 480
+ORB = dict(nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7)
+NNRATIO, CHECK_ORI = 0.7, True
+# algorithmic bytes per frame (SURVEY.md §8d, C1 geometry)
+LEVELS = [(752, 480), (627, 400), (522, 333), (435, 278), (363, 231), (302, 193), (252, 161), (210, 134)]
+SUM_P = sum(w * h for w, h in LEVELS)                      # 1 117 367 : read every level once (FAST) / strict pyramid+FAST
+PYR_CHAIN = sum(w * h for w, h in LEVELS[:-1]) + sum(w * h for w, h in LEVELS[1:])   # 1 845 634 : per-level resize chain
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                p = [x.strip() for x in line.split(",")]
+                if len(p) >= 7:
+                    self.samples.append(p)
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_frames(seed, n):
+    import __graft_entry__ as g
+    g.load_package()
+    import importlib
+    synth = importlib.import_module("orb_ygz_slam_b200.synth")
+    return synth.synth_stream(seed, n, W, H)
+
+
+def cpu_arm(frames, threads, min_seconds=8.0, max_frames=None):
+    """Oracle port (host-tuned build) on all host threads over a bounded sample; returns (fps, n_frames, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    try:
+        O.lib(native=True)
+        native = True
+    except Exception:
+        native = False
+    n = len(frames) if max_frames is None else min(len(frames), max_frames)
+    O.frontend_batch(frames[:min(n, max(threads, 8))], threads, nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, **_orb_kw())  # warm
+    done, t0 = 0, time.perf_counter()
+    while True:
+        O.frontend_batch(frames[:n], threads, nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, **_orb_kw())
+        done += n
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return done / dt, done, dt, native
+
+
+def _orb_kw():
+    return dict(nfeatures=ORB["nfeatures"], scale=ORB["scaleFactor"], nlevels=ORB["nlevels"], ini_th=ORB["iniThFAST"],
+                min_th=ORB["minThFAST"])
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the reference itself cannot be
+    compiled here — no OpenCV/Eigen headers) on all host threads.  Rank 0 only."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = max(threads, 64)
+    frames = make_frames(1234, min(sample, 256))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    try:
+        O.lib(native=True); native = True
+    except Exception:
+        native = False
+    kw = dict(nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, **_orb_kw())
+    for _ in range(max(args.warmup, 1)):
+        O.frontend_batch(frames, threads, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.frontend_batch(frames, threads, **kw)
+    dt = time.perf_counter() - t0
+    fps = args.steps * len(frames) / dt
+    out = {
+        "impl": "reference", "metric": "front-end frames/sec (752x480, 1000 feat, 8-lvl pyr)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(len(frames)),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d frames/step x %d steps, oracle port (%s build), %d threads" %
+                                   (len(frames), args.steps, "-march=native" if native else "portable", threads)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+def workload_config(batch):
+    return {"workload": "C2 synthetic EuRoC-shape mono stream 752x480 u8: ORBextractor(1000,1.2,8,20,7) + "
+                        "ORBmatcher(0.7,checkOri).SearchByBoW vs previous frame (synthetic vocabulary byte0>>2)",
+            "frames_per_step": batch, "l2_policy": "inputs larger than L2 (%d distinct frames/step, pyramid working set %.0f MB)"
+                                                   % (batch, batch * (SUM_P + 361e3 * 0) / 1e6),
+            "parallelism": "replicas: one independent batch per GPU"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    g.build_cuda()
+    m = g.load_package()
+    if m.device_count() <= local:
+        raise SystemExit("bench.py needs a CUDA device (product path has no CPU fallback)")
+    B = args.batch
+    frames = make_frames(1000 + rank, B)
+
+    ex = m.ORBextractor(width=W, height=H, max_batch=B, device=local, **ORB)
+    mt = m.ORBmatcher(NNRATIO, CHECK_ORI, device=local)
+    cap = ex.cap
+    kf_idx = np.array([(i - 1) % B for i in range(B)], np.int32)
+    f_idx = np.arange(B, dtype=np.int32)
+
+    # pinned host buffers (torch is plumbing: pinned memory + the one collective)
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+    h_img = pin((B, H, W), torch.uint8)
+    h_img.numpy()[:] = frames
+    h_kps = pin((B, cap, 7), torch.float32)
+    h_desc = pin((B, cap, 32), torch.uint8)
+    h_cnt = pin((B,), torch.int32)
+    h_match = pin((B, cap), torch.int32)
+    h_nm = pin((B,), torch.int32)
+    import ctypes as C
+
+    def e2e_step():
+        m._check(m.lib().ygz_orb_extract(ex.h, h_img.data_ptr(), B, W * H, W, h_kps.data_ptr(), h_desc.data_ptr(),
+                                         h_cnt.data_ptr(), cap), "ygz_orb_extract")
+        m._check(m.lib().ygz_search_by_bow_batch(mt.h, ex.h, NNRATIO, int(CHECK_ORI), kf_idx.ctypes.data_as(m.i32p),
+                                                 f_idx.ctypes.data_as(m.i32p), B, None, C.cast(h_match.data_ptr(), m.i32p),
+                                                 C.cast(h_nm.data_ptr(), m.i32p)), "ygz_search_by_bow_batch")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also makes inputs resident and sets up the pair lists)
+    for _ in range(args.warmup):
+        e2e_step()
+    n_kp = int(h_cnt.numpy().sum())
+    n_match = int(h_nm.numpy().sum())
+    for _ in range(args.warmup):
+        mt.time_frontend(ex, B, 1)
+
+    # ---- device-resident timing: K steps, CUDA events on the launching stream
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    ms_dev = mt.time_frontend(ex, B, args.steps)
+    barrier()
+    # ---- end-to-end timing through the public C-ABI calls with host buffers (copies inside)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.finish()
+
+    # per-stage device times (same launches, separately timed) for the roofline of the dominant kernel
+    it = max(3, min(args.steps, 10))
+    st = ex.time(B, it)
+    bow_ms = mt.time_bow_batch(ex, B, it) / it
+    stages = {"pyramid(7 launches)": st["pyramid"] / it, "fast_cells": st["fast_cells"] / it, "octree": st["octree"] / it,
+              "orient_describe": st["describe"] / it, "bow_match": bow_ms}
+
+    # ---- max over ranks; the ONE collective: all-gather of throughput counters
+    t_dev, t_e = ms_dev / 1e3, t_e2e
+    ctr = ex.counters()
+    if dist is not None:
+        tt = torch.tensor([t_dev, t_e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e = float(tt[0]), float(tt[1])
+        mine = torch.tensor([ctr["frames"], ctr["keypoints"], n_match, 0, ctr["bytes_in"], ctr["bytes_out"],
+                             ctr["kernel_launches"], int(t_dev * 1e9)], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        gathered = torch.stack(allc).cpu().numpy()
+    else:
+        gathered = np.array([[ctr["frames"], ctr["keypoints"], n_match, 0, ctr["bytes_in"], ctr["bytes_out"],
+                              ctr["kernel_launches"], int(t_dev * 1e9)]])
+
+    if rank == 0:
+        total_frames = world * B * args.steps
+        value = total_frames / t_dev
+        e2e_v = total_frames / t_e
+        peak, peak_src = measured_peak_gbs()
+        dom = max(stages, key=stages.get)
+        alg = {"pyramid(7 launches)": PYR_CHAIN, "fast_cells": SUM_P, "octree": 0, "orient_describe": 0, "bow_match": 0}
+        # algorithmic bytes of gather-type kernels: keypoints * (43x43 raw patch + 60 B out) ; BoW: descriptors of both frames
+        kp_per_frame = n_kp / B
+        alg["orient_describe"] = int(kp_per_frame * (43 * 43 + 28 + 32))
+        alg["octree"] = int(4 * 16139 / 16)     # ~4 B per FAST candidate (read once); informative only
+        alg["bow_match"] = int(2 * kp_per_frame * (32 + 28) + 4 * cap)
+        dom_bytes = alg[dom] * B
+        achieved = dom_bytes / (stages[dom] / 1e3) / 1e9
+        pf_bytes = (SUM_P) * B
+        pf_ms = stages["pyramid(7 launches)"] + stages["fast_cells"]
+        out = {
+            "metric": "front-end frames/sec (752x480, 1000 feat, 8-lvl pyr)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(B),
+            "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(h_img.numel()),
+                    "d2h_bytes_per_step": int(h_kps.numel() * 4 + h_desc.numel() + h_cnt.numel() * 4 + h_match.numel() * 4 + h_nm.numel() * 4),
+                    "ms_per_step": t_e / args.steps * 1e3},
+            "gpu_launches": int(args.steps * ((ORB["nlevels"] - 1) + 3 + 1)),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                         "kernel_ms_per_launch": stages[dom],
+                         "pyramid_plus_fast": {"strict_bytes_per_step": pf_bytes, "ms_per_step": pf_ms,
+                                               "achieved": pf_bytes / (pf_ms / 1e3) / 1e9,
+                                               "frac": pf_bytes / (pf_ms / 1e3) / 1e9 / peak}},
+            "stages_ms_per_step": stages,
+            "keypoints_per_frame": kp_per_frame, "matches_per_frame": n_match / B,
+            "counters_all_ranks": {"columns": ["frames", "keypoints", "matches", "sia_iters", "bytes_in", "bytes_out",
+                                               "kernel_launches", "elapsed_ns"], "rows": gathered.tolist()},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            fps, done, dt, native = cpu_arm(frames, threads, min_seconds=8.0)
+            out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                   "sample": "%d frames of the same stream in %.1f s, oracle port (%s build), %d threads" %
+                                             (done, dt, "-march=native" if native else "portable", threads)}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

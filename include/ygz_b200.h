@@ -176,7 +176,9 @@ int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_orien
 /* Batched device-resident SearchByBoW over n independent (KF, F) pairs whose keypoints/descriptors are
  * extractor outputs already in HBM (stream front end, BASELINE C2): pair p matches frame kf_idx[p]
  * against frame f_idx[p] of the extractor batch; FeatureVectors are given per frame as node ids per
- * feature (node_of_feature[frame][cap], 0xFFFFFFFF = none).  All KF features carry a map point.
+ * feature (node_of_feature[frame][cap], 0xFFFFFFFF = none; NULL selects the synthetic bench vocabulary
+ * node = descriptor byte 0 >> 2, a stand-in for DBoW2 transform which is a "next" row).  All KF features
+ * carry a map point.
  * out_matches: n x cap ints (host), out_nmatches: n ints. */
 int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
                             const int* kf_idx, const int* f_idx, int n_pairs, const uint32_t* node_of_feature,
@@ -184,6 +186,12 @@ int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int che
 /* same, results left on the device; timing variant for bench.py (ms over `iters` repeats) */
 int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
                                  int n_pairs, int iters, float* ms);
+
+/* One whole front-end step (extractor kernels + batched SearchByBoW) on the extractor's stream, repeated
+ * `iters` times and timed with CUDA events; inputs resident in HBM.  Requires a prior
+ * ygz_search_by_bow_batch call on the same handles (pair lists resident). */
+int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, float nnratio, int check_orientation,
+                      float* ms);
 
 /* ------------------------------------------------------------------ SparseImgAlign
  * replaces ygz::SparseImgAlign (include/SparseImageAlign.h:14-113, src/SparseImageAlign.cc) and its

@@ -138,4 +138,75 @@ long orc_extract_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t*
     return total.load();
 }
 
+
+// CPU front-end baseline (bench.py cpu_baseline / --impl reference): per frame ORBextractor::operator() and
+// SearchByBoW against the previous frame of the same thread's chunk (chunk wrap-around for the first frame), with the
+// synthetic bench vocabulary node = descriptor byte0 >> 2 (same stand-in as the device path).  Returns total matches.
+long orc_frontend_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t* imgs, int n_frames, int w, int hh,
+                        int threads, float nnratio, int check_ori, long* total_keypoints) {
+    if (threads < 1) threads = 1;
+    if (threads > n_frames) threads = n_frames;
+    std::atomic<long> matches(0), keys(0);
+    auto work = [&](int t) {
+        const int c0 = (int)((long)n_frames * t / threads), c1 = (int)((long)n_frames * (t + 1) / threads);
+        if (c1 <= c0) return;
+        Extractor ex(nf, sf, nl, ini, mn);
+        struct FrameData { std::vector<KeyPoint> k; std::vector<uint8_t> d; std::vector<uint32_t> node_id, index; std::vector<int> off, mp; };
+        std::vector<FrameData> fr(c1 - c0);
+        auto build = [&](FrameData& F) {
+            const int n = (int)F.k.size();
+            std::vector<std::vector<uint32_t>> buckets(64);
+            for (int i = 0; i < n; i++) buckets[F.d[(size_t)i * 32] >> 2].push_back((uint32_t)i);
+            F.off.assign(1, 0);
+            for (uint32_t b = 0; b < 64; b++) {
+                if (buckets[b].empty()) continue;
+                F.node_id.push_back(b);
+                F.index.insert(F.index.end(), buckets[b].begin(), buckets[b].end());
+                F.off.push_back((int)F.index.size());
+            }
+            F.mp.resize(n);
+            for (int i = 0; i < n; i++) F.mp[i] = i;
+        };
+        auto view = [&](FrameData& F) {
+            orc_frame_view v;
+            std::memset(&v, 0, sizeof(v));
+            v.n = (int)F.k.size();
+            v.keys = (const orc_keypoint*)F.k.data();
+            v.desc = F.d.data();
+            v.map_point = F.mp.data();
+            v.fv_nodes = (int)F.node_id.size();
+            v.fv_node_id = F.node_id.data();
+            v.fv_offset = F.off.data();
+            v.fv_index = F.index.data();
+            return v;
+        };
+        long km = 0, mm = 0;
+        for (int i = c0; i < c1; i++) {
+            FrameData& F = fr[i - c0];
+            ex.extract(imgs + (size_t)i * w * hh, w, hh, w, F.k, F.d);
+            build(F);
+            km += (long)F.k.size();
+        }
+        std::vector<int> out;
+        for (int i = c0; i < c1; i++) {
+            FrameData& F = fr[i - c0];
+            FrameData& KF = fr[(i - c0 + (c1 - c0) - 1) % (c1 - c0)];
+            orc_frame_view vf = view(F), vk = view(KF);
+            orc_map_points mps;
+            std::memset(&mps, 0, sizeof(mps));
+            mps.m = vk.n;
+            out.resize(vf.n + 1);
+            mm += orc_search_by_bow(nnratio, check_ori, &vk, &mps, &vf, out.data());
+        }
+        keys += km;
+        matches += mm;
+    };
+    std::vector<std::thread> ts;
+    for (int t = 1; t < threads; t++) ts.emplace_back(work, t);
+    work(0);
+    for (auto& t : ts) t.join();
+    if (total_keypoints) *total_keypoints = keys.load();
+    return matches.load();
+}
+
 }  // extern "C"

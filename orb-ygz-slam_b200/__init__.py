@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
     "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
-    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_time",
+    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_time", "ygz_frontend_time",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
 ]
 
@@ -137,6 +137,7 @@ def lib():
     sigs.setdefault('ygz_sia_destroy', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_sia_run', {})['argtypes'] = [C.c_void_p, C.POINTER(SiaProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, i32p]
     sigs.setdefault('ygz_sia_time', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
+    sigs.setdefault('ygz_frontend_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
     sigs.setdefault('ygz_sia_last_trace', {})['argtypes'] = [C.c_void_p, C.c_int, f32p, C.c_int, i32p]
     for name, sig in sigs.items():
         if hasattr(L, name):          # tests/test_abi.py asserts that nothing is missing
@@ -431,8 +432,8 @@ class ORBmatcher:
 
     @staticmethod
     def DescriptorDistance(a, b):
-        a = np.ascontiguousarray(a, np.uint8)
-        b = np.ascontiguousarray(b, np.uint8)
+        a = np.frombuffer(bytes(a), np.uint8) if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a, np.uint8)
+        b = np.frombuffer(bytes(b), np.uint8) if isinstance(b, (bytes, bytearray)) else np.ascontiguousarray(b, np.uint8)
         return lib().ygz_descriptor_distance(a.ctypes.data, b.ctypes.data)
 
     def bf_top2(self, q, t):
@@ -485,15 +486,23 @@ class ORBmatcher:
         """Device-resident SearchByBoW over frame pairs of an extractor batch (outputs already in HBM)."""
         kf_idx = np.ascontiguousarray(kf_idx, np.int32)
         f_idx = np.ascontiguousarray(f_idx, np.int32)
-        nof = np.ascontiguousarray(node_of_feature, np.uint32)
         cap = extractor.cap
-        assert nof.ndim == 2 and nof.shape[1] == cap
+        nof = None
+        if node_of_feature is not None:
+            nof = np.ascontiguousarray(node_of_feature, np.uint32)
+            assert nof.ndim == 2 and nof.shape[1] == cap
         out = np.zeros((len(kf_idx), cap), np.int32)
         nm = np.zeros(len(kf_idx), np.int32)
         _check(self.L.ygz_search_by_bow_batch(self.h, extractor.h, self.nnratio, int(self.checkOri), _ptr(kf_idx, i32p),
                                               _ptr(f_idx, i32p), len(kf_idx), _ptr(nof, u32p), _ptr(out, i32p),
                                               _ptr(nm, i32p)), "ygz_search_by_bow_batch")
         return nm, out
+
+    def time_frontend(self, extractor, n_frames, iters):
+        ms = C.c_float()
+        _check(self.L.ygz_frontend_time(extractor.h, self.h, n_frames, iters, self.nnratio, int(self.checkOri),
+                                        C.byref(ms)), "ygz_frontend_time")
+        return ms.value
 
     def time_bow_batch(self, extractor, n_pairs, iters):
         ms = C.c_float()

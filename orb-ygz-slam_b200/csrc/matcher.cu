@@ -161,10 +161,15 @@ __global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A)
     const uint4* fd = A.desc + (size_t)fr * A.cap * 2;
     int pk = 1; while (pk < nk) pk <<= 1;
     int pf = 1; while (pf < nf) pf <<= 1;
+    // A.node == nullptr: synthetic vocabulary (bench stand-in for DBoW2 transform): node = top 6 bits of byte 0
+    auto node_of = [&](int frame, const uint4* d, int i) -> unsigned long long {
+        return A.node ? (unsigned long long)A.node[(size_t)frame * A.cap + i]
+                      : (unsigned long long)((reinterpret_cast<const uint8_t*>(d + (size_t)i * 2)[0]) >> 2);
+    };
     for (int i = threadIdx.x; i < pk; i += BOW_THREADS)
-        skf[i] = i < nk ? (((unsigned long long)A.node[(size_t)kf * A.cap + i] << 32) | (unsigned)i) : ~0ull;
+        skf[i] = i < nk ? ((node_of(kf, kd, i) << 32) | (unsigned)i) : ~0ull;
     for (int i = threadIdx.x; i < pf; i += BOW_THREADS)
-        sf[i] = i < nf ? (((unsigned long long)A.node[(size_t)fr * A.cap + i] << 32) | (unsigned)i) : ~0ull;
+        sf[i] = i < nf ? ((node_of(fr, fd, i) << 32) | (unsigned)i) : ~0ull;
     for (int i = threadIdx.x; i < BOW_MAX_FEATS; i += BOW_THREADS) { match_of_f[i] = -1; bin_of_f[i] = -1; }
     if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_n = 0;
@@ -757,14 +762,14 @@ static int bow_batch_prepare(ygz_matcher* h, ygz_orb* orb, int n_pairs, int* cap
 
 int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, const int* kf_idx, const int* f_idx,
                             int n_pairs, const uint32_t* node_of_feature, int* out_matches, int* out_nmatches) {
-    YGZ_ARG_CHECK(h && orb && kf_idx && f_idx && n_pairs >= 1 && node_of_feature && out_matches && out_nmatches);
+    YGZ_ARG_CHECK(h && orb && kf_idx && f_idx && n_pairs >= 1 && out_matches && out_nmatches);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
     int cap = 0, rc;
     if ((rc = bow_batch_prepare(h, orb, n_pairs, &cap, nullptr))) return rc;
     int max_frame = 0;
     for (int i = 0; i < n_pairs; i++) max_frame = std::max(max_frame, std::max(kf_idx[i], f_idx[i]));
     const int frames = max_frame + 1;
-    if (frames > h->bow_frames) {
+    if (node_of_feature && frames > h->bow_frames) {
         cudaFree(h->d_node); h->d_node = nullptr;
         YGZ_CUDA_TRY(cudaMalloc(&h->d_node, (size_t)frames * cap * 4));
         h->bow_frames = frames;
@@ -773,12 +778,13 @@ int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int che
     ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, nullptr);
     // the extractor's stream produced the inputs: order our stream after it
     YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
-    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_node, node_of_feature, (size_t)frames * cap * 4, cudaMemcpyHostToDevice, h->stream));
+    if (node_of_feature)
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_node, node_of_feature, (size_t)frames * cap * 4, cudaMemcpyHostToDevice, h->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_kf_idx, kf_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_f_idx, f_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     BowBatchArgs A;
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
-    A.node = h->d_node; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
+    A.node = node_of_feature ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
     k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, h->stream>>>(A);
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -799,6 +805,29 @@ int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, in
     YGZ_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < iters; i++) k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, h->stream>>>(A);
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
+    YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return YGZ_OK;
+}
+
+
+// whole front-end step on ONE stream (the extractor's): pyramid + FAST + octree + describe + batched SearchByBoW.
+// Needs a prior ygz_search_by_bow_batch call (pair lists / node ids resident).  CUDA-event timed.
+int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, float nnratio, int check_ori, float* ms) {
+    YGZ_ARG_CHECK(orb && h && ms && iters >= 1 && h->last_pairs >= 1);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)ygz_orb_stream(orb);
+    BowBatchArgs A = h->last_args;
+    A.nnratio = nnratio; A.check_ori = check_ori;
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev0, st));
+    for (int i = 0; i < iters; i++) {
+        int rc = ygz_orb_run(orb, n_frames);
+        if (rc) return rc;
+        k_bow_match_batch<<<h->last_pairs, BOW_THREADS, 0, st>>>(A);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev1, st));
     YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
     YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return YGZ_OK;

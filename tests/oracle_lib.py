@@ -105,6 +105,9 @@ def lib(native=False):
     L.orc_bf_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p]
     L.orc_sia_run.argtypes = [C.POINTER(SiaProblem), C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p,
                               f32p, C.c_int, i32p]
+    L.orc_frontend_batch.restype = C.c_long
+    L.orc_frontend_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_float, C.c_int, C.POINTER(C.c_long)]
     L.orc_se3_exp.argtypes = [f32p, f32p, f32p]
     L.orc_se3_mul.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p]
     L.orc_se3_inv.argtypes = [f32p, f32p, f32p, f32p]
@@ -244,3 +247,34 @@ def bf_top2(q, t):
     sd = np.zeros(len(q), np.int32)
     lib().orc_bf_top2(_ptr(q, u8p), len(q), _ptr(t, u8p), len(t), _ptr(bi, i32p), _ptr(bd, i32p), _ptr(sd, i32p))
     return bi, bd, sd
+
+
+def sia_run(problem, max_level, min_level, n_iter=10, eps=1e-6, trace_cap=192):
+    """problem: _Keep(SiaProblem) built with cls=oracle_lib.SiaProblem.  Returns (n_tracked, q, t, H, trace)."""
+    q = np.zeros(4, np.float32)
+    t = np.zeros(3, np.float32)
+    H = np.zeros(36, np.float32)
+    tr = np.zeros((trace_cap, 8), np.float32)
+    tn = C.c_int()
+    n = lib().orc_sia_run(problem.ptr(), max_level, min_level, n_iter, eps, _ptr(q, f32p), _ptr(t, f32p), _ptr(H, f32p),
+                          _ptr(tr, f32p), trace_cap, C.byref(tn))
+    return n, q, t, H.reshape(6, 6), tr[:tn.value]
+
+
+def se3_exp(x6):
+    x6 = np.ascontiguousarray(x6, np.float32)
+    q = np.zeros(4, np.float32)
+    t = np.zeros(3, np.float32)
+    lib().orc_se3_exp(_ptr(x6, f32p), _ptr(q, f32p), _ptr(t, f32p))
+    return q, t
+
+
+def frontend_batch(imgs, threads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, nnratio=0.7, check_ori=True,
+                   native=True):
+    """CPU baseline: extract + SearchByBoW(prev frame) over imgs[n,h,w]; returns (matches, keypoints)."""
+    imgs = np.ascontiguousarray(imgs, np.uint8)
+    n, h, w = imgs.shape
+    kp = C.c_long()
+    m = lib(native).orc_frontend_batch(nfeatures, scale, nlevels, ini_th, min_th, _ptr(imgs, u8p), n, w, h, threads,
+                                       nnratio, int(check_ori), C.byref(kp))
+    return m, kp.value
