@@ -272,21 +272,14 @@ def main():
     stages = {"pyramid(7 launches)": st["pyramid"] / it, "fast_cells": st["fast_cells"] / it, "octree": st["octree"] / it,
               "orient_describe": st["describe"] / it, "bow_match": bow_ms}
 
-    # ---- max over ranks; the ONE collective: all-gather of throughput counters
-    t_dev, t_e = ms_dev / 1e3, t_e2e
+    # ---- max over ranks; the ONE collective: all-gather of throughput counters (orb-ygz-slam_b200/shard.py)
+    import importlib
+    shard = importlib.import_module("orb_ygz_slam_b200.shard")
     ctr = ex.counters()
-    if dist is not None:
-        tt = torch.tensor([t_dev, t_e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_e = float(tt[0]), float(tt[1])
-        mine = torch.tensor([ctr["frames"], ctr["keypoints"], n_match, 0, ctr["bytes_in"], ctr["bytes_out"],
-                             ctr["kernel_launches"], int(t_dev * 1e9)], dtype=torch.int64, device="cuda")
-        allc = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allc, mine)
-        gathered = torch.stack(allc).cpu().numpy()
-    else:
-        gathered = np.array([[ctr["frames"], ctr["keypoints"], n_match, 0, ctr["bytes_in"], ctr["bytes_out"],
-                              ctr["kernel_launches"], int(t_dev * 1e9)]])
+    ctr["matches"] = n_match
+    t_dev, t_e = shard.max_over_ranks(dist, [ms_dev / 1e3, t_e2e], device="cuda" if dist is not None else None)
+    ctr["elapsed_ns"] = int(t_dev * 1e9)
+    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None)
 
     if rank == 0:
         total_frames = world * B * args.steps

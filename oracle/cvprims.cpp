@@ -40,7 +40,8 @@ void resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride,
     resize_linear_tables(sw, dw, xofs, ialpha);
     // vertical: cv keeps the fractional weights and clips the row indices instead
     const double scale_y = 1.0 / ((double)dh / sh);
-    std::vector<int> r0(dw), r1(dw);
+    static thread_local std::vector<int> r0, r1;
+    if (r0.size() < (size_t)dw) { r0.resize(dw); r1.resize(dw); }
     int prev0 = -1, prev1 = -1;
     auto hrow = [&](int sy, std::vector<int>& out) {
         const uint8_t* S = src + (size_t)sy * sstride;
@@ -91,8 +92,11 @@ static const int G7[7] = {18, 34, 48, 56, 48, 34, 18};
 
 void gauss7_sigma2_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
     // horizontal pass into 8.8 fixed point (u16), rows padded by reflect-101 so the inner loop is branch-free
-    std::vector<uint16_t> hbuf((size_t)w * h);
-    std::vector<uint8_t> prow((size_t)w + 6);
+    // scratch reused per thread: fresh multi-100KB vectors per call go through mmap and serialise many-thread runs
+    static thread_local std::vector<uint16_t> hbuf;
+    static thread_local std::vector<uint8_t> prow;
+    if (hbuf.size() < (size_t)w * h) hbuf.resize((size_t)w * h);
+    if (prow.size() < (size_t)w + 6) prow.resize((size_t)w + 6);
     for (int y = 0; y < h; y++) {
         const uint8_t* S = src + (size_t)y * sstride;
         for (int x = -3; x < w + 3; x++) prow[x + 3] = S[reflect101(x, w)];
@@ -195,8 +199,10 @@ void fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, bool 
     for (int k = 0; k < 25; k++) pixel[k] = RING[k & 15][0] + RING[k & 15][1] * stride;
     uint8_t tab0[512];
     for (int i = -255; i <= 255; i++) tab0[i + 255] = (uint8_t)(i < -threshold ? 1 : i > threshold ? 2 : 0);
-    std::vector<uint8_t> sbuf((size_t)3 * w, 0);
-    std::vector<int> cbuf((size_t)3 * (w + 1), 0);
+    static thread_local std::vector<uint8_t> sbuf;
+    static thread_local std::vector<int> cbuf;
+    sbuf.assign((size_t)3 * w, 0);
+    cbuf.assign((size_t)3 * (w + 1), 0);
     uint8_t* buf[3] = {sbuf.data(), sbuf.data() + w, sbuf.data() + 2 * w};
     int* cpbuf[3] = {cbuf.data() + 1, cbuf.data() + (w + 1) + 1, cbuf.data() + 2 * (w + 1) + 1};
     for (int i = 3; i < h - 2; i++) {

@@ -1,0 +1,61 @@
+"""CPU tests (no GPU): the C-ABI shared library loads, exports every symbol include/ygz_b200.h declares, and fails
+loudly (no CPU fallback) when asked to compute without a CUDA device."""
+import os
+import re
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "ygz_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ygz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.lib()
+    names = header_functions()
+    assert len(names) >= 35
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sorted(pkg.ABI_SYMBOLS) == names, set(pkg.ABI_SYMBOLS) ^ set(names)
+    assert pkg.missing_symbols() == []
+
+
+def test_struct_layouts(pkg):
+    import ctypes as C
+    assert pkg.KP_DTYPE.itemsize == 28                         # == sizeof(cv::KeyPoint)
+    assert C.sizeof(pkg.OrbConfig) == 36
+    assert C.sizeof(pkg.Counters) == 64
+
+
+def test_host_only_entry_points(pkg):
+    a = np.arange(32, dtype=np.uint8)
+    b = a[::-1].copy()
+    assert pkg.ORBmatcher.DescriptorDistance(a, b) == int(np.unpackbits(a ^ b).sum())
+    assert pkg.ORBmatcher.DescriptorDistance(a, a) == 0
+
+
+def test_no_cpu_fallback(pkg):
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.YgzError):
+        pkg.ORBextractor(1000, 1.2, 8, 20, 7)
+    with pytest.raises(pkg.YgzError):
+        pkg.ORBmatcher()
+    with pytest.raises(pkg.YgzError):
+        pkg.SparseImgAlign(3, 1)
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    import subprocess
+    so = os.path.join(ROOT, "orb-ygz-slam_b200", "libygz_b200.so")
+    out = subprocess.run(["ldd", so], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "orb-ygz-slam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "libygz_oracle" not in txt and "ygz_oracle.h" not in txt, f
