@@ -59,3 +59,19 @@ def test_product_does_not_link_or_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "libygz_oracle" not in txt and "ygz_oracle.h" not in txt, f
+
+
+def test_cpp_class_mirror_compiles_and_links(tmp_path):
+    """include/ygz/*.h (the reference-named C++ classes) compile against the C ABI and link with the library."""
+    import subprocess
+    src = tmp_path / "shim.cpp"
+    src.write_text('#include "ygz/ORBextractor.h"\n#include "ygz/ORBmatcher.h"\n#include "ygz/SparseImageAlign.h"\n'
+                   'int main() { unsigned char a[32] = {1}, b[32] = {0};\n'
+                   '  ygz::ORBextractor ex(1000, 1.2f, 8, 20, 7);\n'
+                   '  return ygz::ORBmatcher::DescriptorDistance(a, b) == 1 && ex.GetLevels() == 8 ? 0 : 1; }\n')
+    exe = tmp_path / "shim"
+    libdir = os.path.join(ROOT, "orb-ygz-slam_b200")
+    r = subprocess.run(["g++", "-std=c++11", "-Wall", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L" + libdir, "-lygz_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
