@@ -67,6 +67,12 @@ int ygz_orb_max_keypoints(ygz_orb* h);    /* upper bound of keypoints per frame 
 int ygz_orb_extract(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride,
                     ygz_keypoint* kps, uint8_t* desc, int* counts, int cap);
 
+/* Asynchronous form of ygz_orb_extract: enqueues H2D + kernels + D2H on the handle's stream and returns; the host
+ * buffers must be pinned and stay valid until ygz_orb_wait(h).  Alternating two handles overlaps copies and kernels. */
+int ygz_orb_extract_async(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride,
+                          ygz_keypoint* kps, uint8_t* desc, int* counts, int cap);
+int ygz_orb_wait(ygz_orb* h);
+
 /* ORBextractor::operator()(Frame*, keypoints, descriptors, ORBSLAM_KEYPOINT, leftEye),
  * src/ORBextractor.cc:1031-1127, single frame: kps[0..n_existing) are the frame's pre-existing
  * (direct-tracked) keys whose descriptors are recomputed first (:1088-1099); new keys are appended.
@@ -96,6 +102,10 @@ int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches);
 int ygz_orb_device_outputs(ygz_orb* h, void** d_kps, void** d_desc, void** d_counts, int* cap);
 int ygz_orb_device_level(ygz_orb* h, int level, void** d_ptr, int* pitch, size_t* frame_stride);
 void* ygz_orb_stream(ygz_orb* h);
+
+/* Parity instrumentation: (cos, sin) of computeOrbDescriptor (src/ORBextractor.cc:108-109) as the device evaluates
+ * them, for the n consecutive float bit patterns starting at first_bits taken as kpt.angle in degrees. */
+int ygz_debug_cos_sin(int device, unsigned first_bits, unsigned n, float* cos_out, float* sin_out);
 
 /* ------------------------------------------------------------------ ORBmatcher
  * replaces the Hamming search core of ygz::ORBmatcher (include/ORBmatcher.h:38-220, src/ORBmatcher.cc). */
@@ -183,6 +193,9 @@ int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_orien
 int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
                             const int* kf_idx, const int* f_idx, int n_pairs, const uint32_t* node_of_feature,
                             int* out_matches, int* out_nmatches);
+/* asynchronous form on the extractor's stream (synthetic vocabulary); results valid after ygz_orb_wait(orb) */
+int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
+                                  const int* kf_idx, const int* f_idx, int n_pairs, int* out_matches, int* out_nmatches);
 /* same, results left on the device; timing variant for bench.py (ms over `iters` repeats) */
 int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
                                  int n_pairs, int iters, float* ms);

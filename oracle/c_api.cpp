@@ -143,7 +143,8 @@ long orc_extract_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t*
 // SearchByBoW against the previous frame of the same thread's chunk (chunk wrap-around for the first frame), with the
 // synthetic bench vocabulary node = descriptor byte0 >> 2 (same stand-in as the device path).  Returns total matches.
 long orc_frontend_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t* imgs, int n_frames, int w, int hh,
-                        int threads, float nnratio, int check_ori, long* total_keypoints) {
+                        int threads, float nnratio, int check_ori, long* total_keypoints, int repeat) {
+    if (repeat < 1) repeat = 1;
     if (threads < 1) threads = 1;
     if (threads > n_frames) threads = n_frames;
     std::atomic<long> matches(0), keys(0);
@@ -181,13 +182,15 @@ long orc_frontend_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t
             return v;
         };
         long km = 0, mm = 0;
+        std::vector<int> out;
+        for (int rep = 0; rep < repeat; rep++) {      // the chunk is re-processed `repeat` times (buffers stay warm)
         for (int i = c0; i < c1; i++) {
             FrameData& F = fr[i - c0];
+            F.node_id.clear(); F.index.clear();
             ex.extract(imgs + (size_t)i * w * hh, w, hh, w, F.k, F.d);
             build(F);
             km += (long)F.k.size();
         }
-        std::vector<int> out;
         for (int i = c0; i < c1; i++) {
             FrameData& F = fr[i - c0];
             FrameData& KF = fr[(i - c0 + (c1 - c0) - 1) % (c1 - c0)];
@@ -197,6 +200,7 @@ long orc_frontend_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t
             mps.m = vk.n;
             out.resize(vf.n + 1);
             mm += orc_search_by_bow(nnratio, check_ori, &vk, &mps, &vf, out.data());
+        }
         }
         keys += km;
         matches += mm;

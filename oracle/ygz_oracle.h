@@ -127,7 +127,8 @@ int orc_sia_run(const orc_sia_problem* p, int max_level, int min_level, int n_it
                 float* out_q, float* out_t, float* H_out, float* trace, int trace_cap, int* trace_n);
 /* CPU front-end baseline: extractor + SearchByBoW vs previous frame, `threads` std::threads (bench.py) */
 long orc_frontend_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs,
-                        int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints);
+                        int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints,
+                        int repeat);
 /* Sophus pieces exposed for unit tests */
 void orc_se3_exp(const float* x6, float* q, float* t);
 void orc_se3_mul(const float* qa, const float* ta, const float* qb, const float* tb, float* q, float* t);

@@ -70,13 +70,13 @@ class Counters(C.Structure):
 ABI_SYMBOLS = [
     "ygz_last_error", "ygz_device_count", "ygz_device_info",
     "ygz_orb_create", "ygz_orb_destroy", "ygz_orb_tables", "ygz_orb_level_size", "ygz_orb_max_keypoints",
-    "ygz_orb_extract", "ygz_orb_extract_frame", "ygz_orb_compute_pyramid", "ygz_orb_get_level",
+    "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_compute_pyramid", "ygz_orb_get_level",
     "ygz_orb_upload", "ygz_orb_run", "ygz_orb_download", "ygz_orb_sync", "ygz_orb_get_candidates",
-    "ygz_orb_time", "ygz_orb_device_outputs", "ygz_orb_device_level", "ygz_orb_stream", "ygz_orb_counters",
+    "ygz_orb_time", "ygz_debug_cos_sin", "ygz_orb_device_outputs", "ygz_orb_device_level", "ygz_orb_stream", "ygz_orb_counters",
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
     "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
-    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_time", "ygz_frontend_time",
+    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
 ]
 
@@ -137,6 +137,10 @@ def lib():
     sigs.setdefault('ygz_sia_destroy', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_sia_run', {})['argtypes'] = [C.c_void_p, C.POINTER(SiaProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, i32p]
     sigs.setdefault('ygz_sia_time', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
+    sigs.setdefault('ygz_orb_extract_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    sigs.setdefault('ygz_orb_wait', {})['argtypes'] = [C.c_void_p]
+    sigs.setdefault('ygz_search_by_bow_batch_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, C.c_void_p, C.c_void_p]
+    sigs.setdefault('ygz_debug_cos_sin', {})['argtypes'] = [C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
     sigs.setdefault('ygz_frontend_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
     sigs.setdefault('ygz_sia_last_trace', {})['argtypes'] = [C.c_void_p, C.c_int, f32p, C.c_int, i32p]
     for name, sig in sigs.items():

@@ -796,6 +796,32 @@ int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int che
     return YGZ_OK;
 }
 
+// Asynchronous variant on the EXTRACTOR's stream (stream order gives the dependency on the descriptors): synthetic
+// vocabulary only (node_of_feature == NULL path); results land in the (pinned) host arrays after ygz_orb_wait(orb).
+int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, const int* kf_idx, const int* f_idx,
+                                  int n_pairs, int* out_matches, int* out_nmatches) {
+    YGZ_ARG_CHECK(h && orb && kf_idx && f_idx && n_pairs >= 1 && out_matches && out_nmatches);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    int cap = 0, rc;
+    if ((rc = bow_batch_prepare(h, orb, n_pairs, &cap, nullptr))) return rc;
+    cudaStream_t st = (cudaStream_t)ygz_orb_stream(orb);
+    void *d_kps, *d_desc, *d_counts;
+    ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, nullptr);
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_kf_idx, kf_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_f_idx, f_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+    BowBatchArgs A;
+    A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
+    A.node = nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
+    A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
+    k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, st>>>(A);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    h->last_args = A;
+    h->last_pairs = n_pairs;
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_matches, h->d_matches, (size_t)n_pairs * cap * 4, cudaMemcpyDeviceToHost, st));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_nmatches, h->d_nmatches, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    return YGZ_OK;
+}
+
 int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, int n_pairs, int iters, float* ms) {
     YGZ_ARG_CHECK(h && orb && ms && iters >= 1 && h->last_pairs >= 1 && n_pairs == h->last_pairs);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));

@@ -52,7 +52,9 @@ struct ygz_orb {
     int* d_counts = nullptr;
     ExistingKey* d_existing = nullptr;
     int existing_cap = 0;
+    char4* d_pattern = nullptr;
     size_t fast_smem = 0, oct_smem = 0;
+    int fast_warp_smem = 0;
     int launches_per_run = 0;
     ygz_counters ctr = {};
     int last_n = 0;
@@ -91,7 +93,7 @@ static int orb_free(ygz_orb* h) {
     for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_tx); cudaFree(L.d_ty); }
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
-    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing);
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing); cudaFree(h->d_pattern);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -179,7 +181,7 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         L.w = host_cv_round((float)cfg->width * h->inv_scale[l]);
         L.h = host_cv_round((float)cfg->height * h->inv_scale[l]);
         if (L.w < 1 || L.h < 1) { orb_free(h); set_last_error("pyramid level vanishes"); return YGZ_ERR_ARG; }
-        L.pitch = round_up(L.w, 32);
+        L.pitch = round_up(L.w, 16);     // 16-byte vector access; 752 stays 752 so contiguous host frames upload as one 1-D copy
         L.frame_stride = (size_t)L.pitch * L.h;
         LevelDev& D = h->P.lv[l];
         D.w = L.w; D.h = L.h; D.pitch = L.pitch; D.frame_stride = L.frame_stride;
@@ -215,10 +217,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
                     pool += c.cap;
                     key_cap += c.cap;
                     h->cells.push_back(c);
-                    if (dw > 0 && dh > 0) {
-                        size_t sm = round4(c.cw * c.ch) + round4((dw + 2) * (dh + 2)) + round4(dw * dh) + 2 * (size_t)(dw * dh + 160);
-                        fast_smem = std::max(fast_smem, sm);
-                    }
+                    if (dw > 63 || dh > 63) { orb_free(h); set_last_error("FAST cell larger than 63x63 detection window"); return YGZ_ERR_ARG; }
+                    if (dw > 0 && dh > 0) fast_smem = std::max(fast_smem, (size_t)fast_warp_smem(c.cw, c.ch));
                 }
             }
         }
@@ -251,6 +251,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
     h->P.key_total = std::max(key_total, 1);
     h->P.sel_total = sel_total;
     h->P.out_cap = sel_total;
+    h->fast_warp_smem = (int)round_up((int)fast_smem, 16);
+    fast_smem = (size_t)h->fast_warp_smem * FAST_WARPS;
     h->fast_smem = fast_smem;
     h->oct_smem = oct_smem;
     if (fast_smem > 200 * 1024 || oct_smem > 200 * 1024) { orb_free(h); set_last_error("shared memory budget exceeded"); return YGZ_ERR_ARG; }
@@ -291,7 +293,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
     TRY_OR_FREE(cudaMalloc(&h->d_counts, (size_t)B * 4));
     TRY_OR_FREE(cudaMemset(h->d_counts, 0, (size_t)B * 4));
     TRY_OR_FREE(cudaMemset(h->d_nsel, 0, (size_t)nl * B * 4));
-    TRY_OR_FREE(cudaMemcpyToSymbol(c_pattern, h_pattern, sizeof(h_pattern)));
+    TRY_OR_FREE(cudaMalloc(&h->d_pattern, sizeof(h_pattern)));
+    TRY_OR_FREE(cudaMemcpy(h->d_pattern, h_pattern, sizeof(h_pattern), cudaMemcpyHostToDevice));
     TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
     TRY_OR_FREE(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
     TRY_OR_FREE(cudaDeviceSynchronize());
@@ -328,7 +331,10 @@ int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride
     YGZ_ARG_CHECK(h && images && n >= 1 && n <= h->cfg.max_batch && row_stride >= h->cfg.width);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
     const LevelHost& L0 = h->lv[0];
-    if (frame_stride == (size_t)row_stride * L0.h) {
+    if (frame_stride == (size_t)row_stride * L0.h && row_stride == L0.pitch) {
+        // contiguous frames and no row padding on the device (w % 16 == 0): one 1-D copy
+        YGZ_CUDA_TRY(cudaMemcpyAsync(L0.d_base, images, L0.frame_stride * n, cudaMemcpyHostToDevice, h->stream));
+    } else if (frame_stride == (size_t)row_stride * L0.h) {
         YGZ_CUDA_TRY(cudaMemcpy2DAsync(L0.d_base, L0.pitch, images, row_stride, L0.w, (size_t)L0.h * n,
                                        cudaMemcpyHostToDevice, h->stream));
     } else {
@@ -345,8 +351,8 @@ static int launch_pyramid(ygz_orb* h, int n) {
     for (int l = 1; l < h->cfg.nlevels; l++) {
         const LevelHost& S = h->lv[l - 1];
         const LevelHost& D = h->lv[l];
-        dim3 block(64, 4);
-        dim3 grid(ceil_div(ceil_div(D.w, 4), 64), ceil_div(D.h, 4), n);
+        dim3 block(PYR_THREADS);
+        dim3 grid(ceil_div(ceil_div(D.w, 4), PYR_THREADS), ceil_div(D.h, PYR_ROWS), n);
         k_pyr_resize<<<grid, block, 0, h->stream>>>(S.d_base, S.pitch, S.frame_stride, S.w, D.d_base, D.pitch, D.frame_stride,
                                                     D.w, D.h, D.d_tx, D.d_ty);
     }
@@ -356,8 +362,8 @@ static int launch_pyramid(ygz_orb* h, int n) {
 
 static int launch_detect(ygz_orb* h, int n) {
     if (h->P.n_cells > 0) {
-        dim3 grid(h->P.n_cells, n);
-        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count);
+        dim3 grid(ceil_div(h->P.n_cells, FAST_WARPS), n);
+        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->fast_warp_smem);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     return YGZ_OK;
@@ -372,12 +378,12 @@ static int launch_octree(ygz_orb* h, int n) {
 }
 
 static int launch_describe(ygz_orb* h, int n, int n_existing) {
-    dim3 grid(h->P.sel_total, n);
-    k_orient_describe<<<grid, DESC_THREADS, 0, h->stream>>>(h->P, 0, n_existing, h->d_sel, h->d_nsel, nullptr, h->d_kps,
-                                                           h->d_desc, h->d_counts);
+    dim3 grid(ceil_div(h->P.sel_total, DESC_WARPS), n);
+    k_orient_describe<<<grid, DESC_THREADS, 0, h->stream>>>(h->P, 0, n_existing, h->P.sel_total, h->d_pattern, h->d_sel, h->d_nsel, nullptr,
+                                                           h->d_kps, h->d_desc, h->d_counts);
     if (n_existing > 0) {
-        dim3 g2(n_existing, n);
-        k_orient_describe<<<g2, DESC_THREADS, 0, h->stream>>>(h->P, 1, n_existing, h->d_sel, h->d_nsel, h->d_existing,
+        dim3 g2(ceil_div(n_existing, DESC_WARPS), n);
+        k_orient_describe<<<g2, DESC_THREADS, 0, h->stream>>>(h->P, 1, n_existing, n_existing, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing,
                                                              h->d_kps, h->d_desc, h->d_counts);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -440,6 +446,33 @@ int ygz_orb_extract(ygz_orb* h, const uint8_t* images, int n, size_t frame_strid
     if ((rc = ygz_orb_upload(h, images, n, frame_stride, row_stride))) return rc;
     if ((rc = ygz_orb_run(h, n))) return rc;
     return ygz_orb_download(h, n, kps, desc, counts, cap);
+}
+
+// Asynchronous variant of ygz_orb_extract: enqueues H2D, all kernels and the D2H of the results on the handle's stream
+// and returns; the (pinned) host buffers must stay valid until ygz_orb_wait.  Two handles used alternately overlap
+// one batch's copies with the other's kernels.
+int ygz_orb_extract_async(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride, ygz_keypoint* kps,
+                          uint8_t* desc, int* counts, int cap) {
+    int rc;
+    YGZ_ARG_CHECK(h && images && n >= 1 && kps && desc && counts);
+    if ((rc = ygz_orb_upload(h, images, n, frame_stride, row_stride))) return rc;
+    if ((rc = ygz_orb_run(h, n))) return rc;
+    const int oc = h->P.out_cap, m = std::min(cap, oc);
+    YGZ_CUDA_TRY(cudaMemcpyAsync(counts, h->d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (m > 0) {
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(ygz_keypoint), h->d_kps, (size_t)oc * sizeof(ygz_keypoint),
+                                       (size_t)m * sizeof(ygz_keypoint), n, cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)oc * 32, (size_t)m * 32, n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    h->ctr.bytes_out += (uint64_t)n * 4 + (uint64_t)n * m * (sizeof(ygz_keypoint) + 32);
+    return YGZ_OK;
+}
+
+int ygz_orb_wait(ygz_orb* h) {
+    YGZ_ARG_CHECK(h);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return YGZ_OK;
 }
 
 int ygz_orb_compute_pyramid(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride) {
@@ -594,6 +627,32 @@ int ygz_orb_device_level(ygz_orb* h, int level, void** d_ptr, int* pitch, size_t
     if (d_ptr) *d_ptr = h->lv[level].d_base;
     if (pitch) *pitch = h->lv[level].pitch;
     if (frame_stride) *frame_stride = h->lv[level].frame_stride;
+    return YGZ_OK;
+}
+
+namespace ygz_b200 {
+__global__ void k_debug_cos_sin(unsigned first_bits, unsigned n, float* __restrict__ c, float* __restrict__ s) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float deg = __uint_as_float(first_bits + i);
+    const float factorPI = (float)(3.141592653589793238462643383279502884197169399375 / 180.0);
+    ref_cos_sin(__fmul_rn(deg, factorPI), &c[i], &s[i]);
+}
+}  // namespace ygz_b200
+
+// (a, b) = (cos, sin) of computeOrbDescriptor (src/ORBextractor.cc:108-109) for the n consecutive float bit patterns
+// starting at first_bits, interpreted as kpt.angle in degrees.  Parity instrumentation for tests/test_trig_gpu.py.
+int ygz_debug_cos_sin(int device, unsigned first_bits, unsigned n, float* cos_out, float* sin_out) {
+    YGZ_ARG_CHECK(cos_out && sin_out && n >= 1 && n <= (1u << 26));
+    YGZ_CUDA_TRY(cudaSetDevice(device));
+    float *dc = nullptr, *ds = nullptr;
+    YGZ_CUDA_TRY(cudaMalloc(&dc, (size_t)n * 4));
+    if (cudaMalloc(&ds, (size_t)n * 4) != cudaSuccess) { cudaFree(dc); set_last_error("cudaMalloc"); return YGZ_ERR_CUDA; }
+    k_debug_cos_sin<<<(n + 255) / 256, 256>>>(first_bits, n, dc, ds);
+    cudaError_t e = cudaMemcpy(cos_out, dc, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(sin_out, ds, (size_t)n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dc); cudaFree(ds);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return YGZ_ERR_CUDA; }
     return YGZ_OK;
 }
 

@@ -70,34 +70,59 @@ __device__ __forceinline__ int cand_s(uint32_t c) { return c >> 24; }
 // K1  pyramid level from the previous level: cv::resize(INTER_LINEAR) on CV_8UC1, 11-bit fixed point
 //     (src/ORBextractor.cc:1139).  4 output pixels per thread, one 32-bit store.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pyr_resize(const uint8_t* __restrict__ src, int spitch, size_t sframe,
-                                                    int sw, uint8_t* __restrict__ dst, int dpitch, size_t dframe,
-                                                    int dw, int dh, const ResizeTabX* __restrict__ tx,
-                                                    const ResizeTabY* __restrict__ ty) {
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x4 >= dw || dy >= dh) return;
+constexpr int PYR_ROWS = 8;          // output rows per thread (column tables stay in registers, source rows are reused)
+constexpr int PYR_THREADS = 64;      // 4 output columns per thread -> 256 columns per CTA
+
+__global__ void __launch_bounds__(PYR_THREADS) k_pyr_resize(const uint8_t* __restrict__ src, int spitch, size_t sframe,
+                                                            int sw, uint8_t* __restrict__ dst, int dpitch, size_t dframe,
+                                                            int dw, int dh, const ResizeTabX* __restrict__ tx,
+                                                            const ResizeTabY* __restrict__ ty) {
+    const int x4 = (blockIdx.x * PYR_THREADS + threadIdx.x) * 4;
+    if (x4 >= dw) return;
+    const int dy0 = blockIdx.y * PYR_ROWS;
     const uint8_t* S = src + (size_t)blockIdx.z * sframe;
-    uint8_t* D = dst + (size_t)blockIdx.z * dframe + (size_t)dy * dpitch;
-    const ResizeTabY yy = ty[dy];
-    const uint8_t* S0 = S + (size_t)yy.y0 * spitch;
-    const uint8_t* S1 = S + (size_t)yy.y1 * spitch;
-    uint32_t outw = 0;
+    uint8_t* D = dst + (size_t)blockIdx.z * dframe;
+    // horizontal tables of this thread's four columns (xofs / ialpha of cv::resize), kept in registers
+    int ofs0[4], ofs1[4], a0[4], a1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int dx = x4 + i;
-        int v = 0;
-        if (dx < dw) {
-            const int2 tv = __ldg(reinterpret_cast<const int2*>(tx) + dx);
-            ResizeTabX t; t.ofs = tv.x; t.a0 = (short)(tv.y & 0xFFFF); t.a1 = (short)(tv.y >> 16);
-            const int sx1 = min(t.ofs + 1, sw - 1);
-            const int r0 = S0[t.ofs] * t.a0 + S0[sx1] * t.a1;
-            const int r1 = S1[t.ofs] * t.a0 + S1[sx1] * t.a1;
-            v = (((yy.b0 * (r0 >> 4)) >> 16) + ((yy.b1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        }
-        outw |= (uint32_t)(v & 0xFF) << (8 * i);
+        const int dx = min(x4 + i, dw - 1);
+        const int2 tv = __ldg(reinterpret_cast<const int2*>(tx) + dx);
+        ofs0[i] = tv.x;
+        ofs1[i] = min(tv.x + 1, sw - 1);
+        a0[i] = (short)(tv.y & 0xFFFF);
+        a1[i] = (short)(tv.y >> 16);
     }
-    if (x4 + 3 < dpitch) *reinterpret_cast<uint32_t*>(D + x4) = outw;   // pitch is a multiple of 4; pad bytes are scratch
+    int hA[4], hB[4];                // horizontally interpolated source rows yA (= y0 of the current row) and yB (= y1)
+    int yA = -1, yB = -1;
+    auto hrow = [&](int y, int* h) {
+        const uint8_t* R = S + (size_t)y * spitch;
+#pragma unroll
+        for (int i = 0; i < 4; i++) h[i] = R[ofs0[i]] * a0[i] + R[ofs1[i]] * a1[i];
+    };
+#pragma unroll 1
+    for (int r = 0; r < PYR_ROWS; r++) {
+        const int dy = dy0 + r;
+        if (dy >= dh) break;
+        const ResizeTabY yy = ty[dy];
+        if (yy.y0 == yB) {           // the usual case when downscaling: this row's upper source row is the previous lower one
+#pragma unroll
+            for (int i = 0; i < 4; i++) hA[i] = hB[i];
+            yA = yB;
+        } else if (yy.y0 != yA) { hrow(yy.y0, hA); yA = yy.y0; }
+        if (yy.y1 == yA) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) hB[i] = hA[i];
+            yB = yA;
+        } else if (yy.y1 != yB) { hrow(yy.y1, hB); yB = yy.y1; }
+        uint32_t outw = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int v = (((yy.b0 * (hA[i] >> 4)) >> 16) + ((yy.b1 * (hB[i] >> 4)) >> 16) + 2) >> 2;
+            outw |= (uint32_t)(v & 0xFF) << (8 * i);
+        }
+        *reinterpret_cast<uint32_t*>(D + (size_t)dy * dpitch + x4) = outw;   // pitch is a multiple of 16; pad bytes are scratch
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -130,114 +155,157 @@ __device__ __forceinline__ int fast9_best(int c, const int* r) {
     return best;
 }
 
-constexpr int FAST_THREADS = 128;
+constexpr int FAST_WARPS = 8;                       // one warp per cell, FAST_WARPS cells per CTA, no block barrier
+constexpr int FAST_THREADS = FAST_WARPS * 32;
+
+// FAST-9 score of one pixel, both polarities at once in the two 16-bit halves of a register (VIMNMX3.S16x2):
+//   low  half: c - r_k + 256  (darker ring),   high half: r_k - c + 255  (brighter ring), all values in [0, 511].
+// min over 9 contiguous = min3 of three min3 (32 instructions for all 16 arcs), then a max3 tree.
+// No negated operand feeds a min/max (ptxas 12.9 drops the negation when fusing into VIMNMX3).
+__device__ __forceinline__ int fast9_best_packed(int c, const int* r) {
+    const unsigned K = (unsigned)(c + 256) * 0x00010001u;
+    unsigned E[16], e3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) E[k] = (K - (unsigned)r[k] * 0x00010001u) ^ 0x01FF0000u;
+#pragma unroll
+    for (int k = 0; k < 16; k++) e3[k] = __vimin3_s16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+    unsigned m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m[k] = __vimin3_s16x2(e3[k], e3[(k + 3) & 15], e3[(k + 6) & 15]);
+    const unsigned a0 = __vimax3_s16x2(m[0], m[1], m[2]), a1 = __vimax3_s16x2(m[3], m[4], m[5]);
+    const unsigned a2 = __vimax3_s16x2(m[6], m[7], m[8]), a3 = __vimax3_s16x2(m[9], m[10], m[11]);
+    const unsigned a4 = __vimax3_s16x2(m[12], m[13], m[14]);
+    const unsigned b0 = __vimax3_s16x2(a0, a1, a2), b1 = __vimax3_s16x2(a3, a4, m[15]);
+    const unsigned bb = __vmaxs2(b0, b1);
+    const int dark = (int)(bb & 0xFFFFu) - 256, bright = (int)(bb >> 16) - 255;
+    return max(dark, bright);
+}
+
+// shared-memory bytes one warp needs for a cell image of cw x ch (x0 & 3 = worst-case 3 extra columns)
+__host__ __device__ inline int fast_warp_smem(int cw, int ch) {
+    const int dw = cw - 6, dh = ch - 6;
+    const int tp = round4(cw + 3);
+    return round4(ch * tp) + round4((dw + 2) * (dh + 2)) + round4(dw * dh) + round4(2 * dw * dh);
+}
 
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const CellDesc* __restrict__ cells,
                                                              uint32_t* __restrict__ pool,
-                                                             uint16_t* __restrict__ cell_count) {
-    extern __shared__ uint8_t smem_raw[];
-    const CellDesc cd = cells[blockIdx.x];
+                                                             uint16_t* __restrict__ cell_count, int warp_smem) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * FAST_WARPS + warp;
+    if (cell >= P.n_cells) return;
     const int frame = blockIdx.y;
+    const CellDesc cd = cells[cell];
     const LevelDev& L = P.lv[cd.level];
     const int cw = cd.cw, ch = cd.ch;
     const int dw = cw - 6, dh = ch - 6;               // detection window [3, cw-3) x [3, ch-3)
-    uint16_t* cnt_out = cell_count + (size_t)frame * P.n_cells + blockIdx.x;
-    if (dw <= 0 || dh <= 0) { if (threadIdx.x == 0) *cnt_out = 0; return; }
+    uint16_t* cnt_out = cell_count + (size_t)frame * P.n_cells + cell;
+    if (dw <= 0 || dh <= 0) { if (lane == 0) *cnt_out = 0; return; }
     const int npx = dw * dh;
     const int sw2 = dw + 2;
-    // shared layout
-    uint8_t* raw = smem_raw;                                      // ch x cw
-    uint8_t* sc = raw + round4(cw * ch);                          // (dh+2) x (dw+2) scores, zero border
-    uint8_t* flag = sc + round4((dw + 2) * (dh + 2));             // per item: score if NMS survivor else 0
-    uint16_t* items = reinterpret_cast<uint16_t*>(flag + round4(npx));   // pre-test survivors, raster order
-    __shared__ int warp_cnt[FAST_THREADS / 32];
-    __shared__ int warp_off[FAST_THREADS / 32 + 1];
+    const int xa = cd.x0 & ~3, shift = cd.x0 - xa;    // tile is loaded as aligned 32-bit words
+    const int TP = round4(cw + shift);
+    uint8_t* tile = smem_raw + (size_t)warp * warp_smem;               // ch x TP
+    uint8_t* sc = tile + round4(ch * TP);                              // (dh+2) x (dw+2) scores, zero border
+    uint8_t* flag = sc + round4(sw2 * (dh + 2));                       // per item: score if NMS survivor else 0
+    uint16_t* items = reinterpret_cast<uint16_t*>(flag + round4(npx)); // pre-test survivors: x | y<<6 | polarity<<12
 
-    const uint8_t* img = L.base + (size_t)frame * L.frame_stride + (size_t)cd.y0 * L.pitch + cd.x0;
-    for (int i = threadIdx.x; i < cw * ch; i += FAST_THREADS) {
-        const int y = i / cw, x = i - y * cw;
-        raw[i] = img[(size_t)y * L.pitch + x];
+    {   // ---- tile load (coalesced words) + score tile clear
+        const int wpr = TP >> 2;
+        const uint8_t* g0 = L.base + (size_t)frame * L.frame_stride + (size_t)cd.y0 * L.pitch + xa;
+        int r = 0, c = lane;
+        while (c >= wpr) { c -= wpr; r++; }
+        while (r < ch) {
+            reinterpret_cast<uint32_t*>(tile + r * TP)[c] = __ldg(reinterpret_cast<const uint32_t*>(g0 + (size_t)r * L.pitch) + c);
+            c += 32;
+            while (c >= wpr) { c -= wpr; r++; }
+        }
+        const int nsw = round4(sw2 * (dh + 2)) >> 2;
+        for (int i = lane; i < nsw; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0u;
     }
-    for (int i = threadIdx.x; i < (dw + 2) * (dh + 2); i += FAST_THREADS) sc[i] = 0;
-    __syncthreads();
+    __syncwarp();
 
     const int tmin = P.min_th;
-    // ring offsets in the raw tile (cv::FAST offsets16)
-    const int o0 = 3 * cw, o1 = 3 * cw + 1, o2 = 2 * cw + 2, o3 = cw + 3, o4 = 3, o5 = -cw + 3, o6 = -2 * cw + 2,
-              o7 = -3 * cw + 1, o8 = -3 * cw, o9 = -3 * cw - 1, o10 = -2 * cw - 2, o11 = -cw - 3, o12 = -3,
-              o13 = cw - 3, o14 = 2 * cw - 2, o15 = 3 * cw - 1;
+    // ring offsets in the tile (cv::FAST offsets16)
+    const int o0 = 3 * TP, o1 = 3 * TP + 1, o2 = 2 * TP + 2, o3 = TP + 3, o4 = 3, o5 = -TP + 3, o6 = -2 * TP + 2,
+              o7 = -3 * TP + 1, o8 = -3 * TP, o9 = -3 * TP - 1, o10 = -2 * TP - 2, o11 = -TP - 3, o12 = -3,
+              o13 = TP - 3, o14 = 2 * TP - 2, o15 = 3 * TP - 1;
+    const uint8_t* t0 = tile + 3 * TP + shift + 3;     // pixel (0,0) of the detection window
 
-    // ---- phase A: opposite-pair pre-test at minTh (necessary for 9 contiguous), ordered per-warp compaction
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = FAST_THREADS / 32;
-    const int chunk = ((npx + nwarps - 1) / nwarps + 31) & ~31;
-    {
-        const int start = warp * chunk, end = min(npx, start + chunk);
-        int cnt = 0;
-        for (int base = start; base < end; base += 32) {
-            const int idx = base + lane;
+    // ---- phase A: opposite-pair pre-test at minTh (necessary for 9 contiguous): with da = a-c, db = b-c of an
+    //      opposite pair, a brighter arc needs max(da,db) > t for every pair and a darker arc min(da,db) < -t.
+    //      Straight-line (no early exits: a warp almost always has a surviving lane), one detection row per step;
+    //      ordered compaction keeps raster order.
+    int total = 0;
+    if (dw <= 32) {
+        // two detection rows per step, packed in the 16-bit halves of a register (VIMNMX.U16x2): lo = row y, hi = row y+1.
+        // D = r - c + 256 per half (always in [1, 511], so plain 32-bit adds never carry between the halves).
+        const int x = lane;
+        const unsigned thi = 256u + (unsigned)tmin, tlo = 256u - (unsigned)tmin;
+        for (int y = 0; y < dh; y += 2) {
+            bool pass0 = false, pass1 = false;
+            if (x < dw) {
+                const uint8_t* p = t0 + y * TP + x;
+#define LD2(o) ((unsigned)p[(o)] | ((unsigned)p[(o) + TP] << 16))
+                const unsigned KB = 0x01000100u - LD2(0);
+                const unsigned D0 = LD2(o0) + KB, D8 = LD2(o8) + KB, D4 = LD2(o4) + KB, D12 = LD2(o12) + KB;
+                const unsigned D2 = LD2(o2) + KB, D10 = LD2(o10) + KB, D6 = LD2(o6) + KB, D14 = LD2(o14) + KB;
+#undef LD2
+                const unsigned bmin = __vminu2(__vminu2(__vmaxu2(D0, D8), __vmaxu2(D4, D12)), __vminu2(__vmaxu2(D2, D10), __vmaxu2(D6, D14)));
+                const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(D0, D8), __vminu2(D4, D12)), __vmaxu2(__vminu2(D2, D10), __vminu2(D6, D14)));
+                pass0 = ((bmin & 0xFFFFu) > thi) | ((dmax & 0xFFFFu) < tlo);
+                pass1 = (y + 1 < dh) & (((bmin >> 16) > thi) | ((dmax >> 16) < tlo));
+            }
+            const unsigned bal0 = __ballot_sync(0xffffffffu, pass0);
+            const unsigned bal1 = __ballot_sync(0xffffffffu, pass1);
+            if (pass0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)(x | (y << 6));
+            total += __popc(bal0);
+            if (pass1) items[total + __popc(bal1 & lanemask_lt())] = (uint16_t)(x | ((y + 1) << 6));
+            total += __popc(bal1);
+        }
+    } else {
+    for (int y = 0; y < dh; y++) {
+        for (int xb = 0; xb < dw; xb += 32) {
+            const int x = xb + lane;
             bool pass = false;
-            if (idx < end) {
-                const int y = idx / dw, x = idx - y * dw;
-                const uint8_t* p = raw + (y + 3) * cw + x + 3;
+            if (x < dw) {
+                const uint8_t* p = t0 + y * TP + x;
                 const int c = p[0];
-                const int hi = c + tmin, lo = c - tmin;
-                int a = p[o0], b = p[o8];
-                int m = ((a > hi) | (b > hi)) * 2 + ((a < lo) | (b < lo));
-                if (m) {
-                    a = p[o4]; b = p[o12];
-                    m &= ((a > hi) | (b > hi)) * 2 + ((a < lo) | (b < lo));
-                    if (m) {
-                        a = p[o2]; b = p[o10];
-                        m &= ((a > hi) | (b > hi)) * 2 + ((a < lo) | (b < lo));
-                        a = p[o6]; b = p[o14];
-                        m &= ((a > hi) | (b > hi)) * 2 + ((a < lo) | (b < lo));
-                    }
-                }
-                pass = m != 0;
+                const int d0 = p[o0] - c, d8 = p[o8] - c, d4 = p[o4] - c, d12 = p[o12] - c;
+                const int d2 = p[o2] - c, d10 = p[o10] - c, d6 = p[o6] - c, d14 = p[o14] - c;
+                const int bmin = min(min(max(d0, d8), max(d4, d12)), min(max(d2, d10), max(d6, d14)));
+                const int dmax = max(max(min(d0, d8), min(d4, d12)), max(min(d2, d10), min(d6, d14)));
+                pass = (bmin > tmin) | (dmax + tmin < 0);
             }
             const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (pass) items[start + cnt + __popc(bal & lanemask_lt())] = (uint16_t)idx;
-            cnt += __popc(bal);
+            if (pass) items[total + __popc(bal & lanemask_lt())] = (uint16_t)(x | (y << 6));
+            total += __popc(bal);
         }
-        if (lane == 0) warp_cnt[warp] = cnt;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int w = 0; w < nwarps; w++) { warp_off[w] = s; s += warp_cnt[w]; }
-        warp_off[nwarps] = s;
     }
-    __syncthreads();
-    const int total = warp_off[nwarps];
-    auto item_at = [&](int g) -> int {
-        int w = 0;
-#pragma unroll
-        for (int k = 1; k < nwarps; k++) w += (g >= warp_off[k]);
-        return items[w * chunk + (g - warp_off[w])];
-    };
+    __syncwarp();
 
-    // ---- phase B: full FAST-9 score of the pre-test survivors
-    for (int g = threadIdx.x; g < total; g += FAST_THREADS) {
-        const int idx = item_at(g);
-        const int y = idx / dw, x = idx - y * dw;
-        const uint8_t* p = raw + (y + 3) * cw + x + 3;
-        int r[16] = {p[o0], p[o1], p[o2], p[o3], p[o4], p[o5], p[o6], p[o7],
-                     p[o8], p[o9], p[o10], p[o11], p[o12], p[o13], p[o14], p[o15]};
-        const int best = fast9_best(p[0], r);
+    // ---- phase B: FAST-9 score of the survivors (both polarities packed, fast9_best_packed)
+    for (int g = lane; g < total; g += 32) {
+        const int it = items[g];
+        const int x = it & 63, y = (it >> 6) & 63;
+        const uint8_t* p = t0 + y * TP + x;
+        const int r[16] = {p[o0], p[o1], p[o2], p[o3], p[o4], p[o5], p[o6], p[o7],
+                           p[o8], p[o9], p[o10], p[o11], p[o12], p[o13], p[o14], p[o15]};
+        const int best = fast9_best_packed(p[0], r);
         if (best > tmin) sc[(y + 1) * sw2 + x + 1] = (uint8_t)(best - 1);   // corner at minTh; response = best-1
     }
-    __syncthreads();
+    __syncwarp();
 
     // ---- phase C: 3x3 non-max suppression inside the detection window (strict >, zeros outside)
     int any_hi = 0;
-    for (int g = threadIdx.x; g < total; g += FAST_THREADS) {
-        const int idx = item_at(g);
-        const int y = idx / dw, x = idx - y * dw;
+    for (int g = lane; g < total; g += 32) {
+        const int it = items[g];
+        const int x = it & 63, y = (it >> 6) & 63;
         const uint8_t* q = sc + (y + 1) * sw2 + x + 1;
         const int s = q[0];
         int keep = 0;
-        // a corner at minTh has s >= minTh; s == 0 can only be a corner when minTh == 0 and is never kept by cv either
         if (s > 0 && s >= tmin) {
             keep = (s > q[-1]) & (s > q[1]) & (s > q[-sw2 - 1]) & (s > q[-sw2]) & (s > q[-sw2 + 1]) &
                    (s > q[sw2 - 1]) & (s > q[sw2]) & (s > q[sw2 + 1]);
@@ -246,31 +314,25 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         any_hi |= keep && (s >= P.ini_th);
     }
     // vKeysCell.empty() after the iniTh call decides the fallback (src/ORBextractor.cc:767)
-    const int use_hi = __syncthreads_or(any_hi);
-    const int T = use_hi ? P.ini_th : tmin;
+    const int T = __any_sync(0xffffffffu, any_hi) ? P.ini_th : tmin;
+    __syncwarp();
 
     // ---- phase D: ordered emission (raster order inside the cell), coordinates relative to (16,16)
     uint32_t* out = pool + (size_t)frame * P.pool_size + cd.out_off;
     int base = 0;
-    for (int g0 = 0; g0 < total; g0 += FAST_THREADS) {
-        const int g = g0 + threadIdx.x;
-        int s = 0, idx = 0;
-        if (g < total) { s = flag[g]; idx = item_at(g); }
+    for (int g0 = 0; g0 < total; g0 += 32) {
+        const int g = g0 + lane;
+        int s = 0, it = 0;
+        if (g < total) { s = flag[g]; it = items[g]; }
         const bool keep = s > 0 && s >= T;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
-        __syncthreads();
-        int off = base;
-        for (int w = 0; w < warp; w++) off += warp_cnt[w];
         if (keep) {
-            const int y = idx / dw, x = idx - y * dw;
-            const int pos = off + __popc(bal & lanemask_lt());
-            if (pos < cd.cap) out[pos] = pack_cand(x + 3 + cd.offx, y + 3 + cd.offy, s);
+            const int pos = base + __popc(bal & lanemask_lt());
+            if (pos < cd.cap) out[pos] = pack_cand((it & 63) + 3 + cd.offx, ((it >> 6) & 63) + 3 + cd.offy, s);
         }
-        for (int w = 0; w < nwarps; w++) base += warp_cnt[w];
-        __syncthreads();
+        base += __popc(bal);
     }
-    if (threadIdx.x == 0) *cnt_out = (uint16_t)min(base, (int)cd.cap);
+    if (lane == 0) *cnt_out = (uint16_t)min(base, (int)cd.cap);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,14 +652,17 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
 //       GaussianBlur 7x7 s2   src/ORBextractor.cc:1010,1083 (8.8 fixed point [18,34,48,56,48,34,18], REFLECT_101)
 //       computeOrbDescriptor  src/ORBextractor.cc:105-149 (float, no fma, round-half-even)
 // ------------------------------------------------------------------------------------------------
-constexpr int DESC_THREADS = 256;
+constexpr int DESC_WARPS = 8;           // one warp per keypoint, DESC_WARPS keypoints per CTA, no block barrier
+constexpr int DESC_THREADS = DESC_WARPS * 32;
 constexpr int PR = 21;                 // patch radius: 18 (pattern reach) + 3 (blur)
 constexpr int PW = 2 * PR + 1;         // 43
-constexpr int RAWP = 44;               // raw pitch
+constexpr int RAWP = 48;               // raw pitch: 12 aligned words cover 43 columns + up to 3 columns of misalignment
 constexpr int HW = 37;                 // horizontally blurred columns (-18..18)
 constexpr int HP = 38;                 // pitch of H
+constexpr int DESC_WARP_SMEM = PW * RAWP + PW * HP * 2;     // 2064 + 3268 = 5332 B per warp
 
-__constant__ int8_t c_pattern[256 * 4];     // bit_pattern_31_ (data), src/ORBextractor.cc:152-410
+// bit_pattern_31_ (data, src/ORBextractor.cc:152-410) lives in GLOBAL memory as 256 x char4: every lane reads its own
+// eight tests, and lane-divergent addresses serialise on the constant cache.
 
 __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
     // cv::fastAtan2 (degrees), evaluated without fma contraction
@@ -629,31 +694,34 @@ __device__ void ref_cos_sin(float angle_rad, float* c, float* s);
 struct ExistingKey { float x, y, angle; int octave; };   // pt * mvInvScaleFactor[octave], :1094-1095
 
 // mode 0: keys selected by k_octree (angle computed);  mode 1: pre-existing keys (angle kept, :1088-1099)
-__global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, int mode, int n_existing,
+// One WARP per keypoint: raw 43x43 patch -> shared (aligned word loads), IC moments by warp shuffle, horizontal
+// blur pass into H, then every lane evaluates 8 binary tests = one descriptor byte.
+__global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, int mode, int n_existing, int n_items,
+                                                                  const char4* __restrict__ pattern,
                                                                   const uint32_t* __restrict__ sel_all,
                                                                   const int* __restrict__ nsel_all,
                                                                   const ExistingKey* __restrict__ existing,
                                                                   ygz_keypoint* __restrict__ kps_out,
                                                                   uint8_t* __restrict__ desc_out,
                                                                   int* __restrict__ counts_out) {
-    __shared__ uint8_t raw[PW * RAWP];
-    __shared__ uint16_t H[PW * HP];
-    __shared__ int s_m[2][DESC_THREADS / 32];
-    __shared__ float s_ab[3];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) uint8_t smem[DESC_WARPS * DESC_WARP_SMEM + 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * DESC_WARPS + warp;          // (level, slot) index or existing-key index
     const int frame = blockIdx.y;
+    if (item >= n_items) return;
+    uint8_t* raw = smem + warp * DESC_WARP_SMEM;               // PW x RAWP
+    uint16_t* H = reinterpret_cast<uint16_t*>(raw + PW * RAWP);
     int level, cx, cy, out_idx, score = 0;
     float angle = 0.f;
     if (mode == 0) {
-        // blockIdx.x enumerates (level, slot) over the per-frame sel array
-        const int s = blockIdx.x;
+        const int s = item;
         level = 0;
         while (level + 1 < P.nlevels && s >= P.lv[level + 1].sel_off) level++;
         const int slot = s - P.lv[level].sel_off;
         const int* nsel = nsel_all + (size_t)frame * P.nlevels;
         int before = n_existing;
         for (int l = 0; l < level; l++) before += nsel[l];
-        if (s == 0 && tid == 0) {
+        if (s == 0 && lane == 0) {
             int tot = n_existing;
             for (int l = 0; l < P.nlevels; l++) tot += nsel[l];
             counts_out[frame] = tot;
@@ -665,33 +733,50 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
         score = cand_s(c);
         out_idx = before + slot;
     } else {
-        const ExistingKey ek = existing[(size_t)frame * n_existing + blockIdx.x];
+        const ExistingKey ek = existing[(size_t)frame * n_existing + item];
         level = ek.octave;
         cx = __float2int_rn(ek.x);             // cvRound(kpt.pt.x), :111
         cy = __float2int_rn(ek.y);
         angle = ek.angle;
-        out_idx = blockIdx.x;
+        out_idx = item;
     }
     const LevelDev& L = P.lv[level];
     cx = min(max(cx, 0), L.w - 1);
     cy = min(max(cy, 0), L.h - 1);
     const uint8_t* img = L.base + (size_t)frame * L.frame_stride;
-    // ---- raw patch with REFLECT_101 at the level border
-    for (int i = tid; i < PW * PW; i += DESC_THREADS) {
-        const int r = i / PW, c = i - r * PW;
-        const int yy = reflect101(cy - PR + r, L.h), xx = reflect101(cx - PR + c, L.w);
-        raw[r * RAWP + c] = img[(size_t)yy * L.pitch + xx];
+    // ---- raw patch rows cy-21..cy+21, columns cx-21..cx+21 (REFLECT_101 at the level border)
+    const int x0 = cx - PR, y0 = cy - PR;
+    int shift;                                                  // column of x0 inside the shared row
+    const int xa = x0 & ~3;
+    if (x0 >= 0 && y0 >= 0 && xa + RAWP <= L.pitch && y0 + PW <= L.h && x0 + PW <= L.w) {
+        shift = x0 - xa;
+        for (int i = lane; i < PW * (RAWP / 4); i += 32) {     // 43 rows x 12 aligned words
+            const int r = i / (RAWP / 4), c = i - r * (RAWP / 4);
+            reinterpret_cast<uint32_t*>(raw + r * RAWP)[c] =
+                __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y0 + r) * L.pitch + xa) + c);
+        }
+    } else {                                                    // patch touches the border: byte path with reflection
+        shift = 0;
+        for (int i = lane; i < PW * PW; i += 32) {
+            const int r = i / PW, c = i - r * PW;
+            raw[r * RAWP + c] = img[(size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w)];
+        }
     }
-    __syncthreads();
-    // ---- IC_Angle on the raw patch
+    __syncwarp();
+    const uint8_t* rp = raw + shift;                            // rp[r * RAWP + c], c in [0, 43)
+    // ---- IC_Angle on the raw patch: lane = column u, loop over rows v
     if (mode == 0) {
         int m10 = 0, m01 = 0;
-        for (int i = tid; i < 31 * 31; i += DESC_THREADS) {
-            const int v = i / 31 - HALF_PATCH, u = i - (i / 31) * 31 - HALF_PATCH;
-            if (abs(u) <= P.umax[abs(v)]) {
-                const int I = raw[(PR + v) * RAWP + PR + u];
-                m10 += u * I;
-                m01 += v * I;
+        const int u = lane - HALF_PATCH;                        // lanes 0..30 <-> u = -15..15
+        if (lane < 31) {
+            const int au = abs(u);
+#pragma unroll 1
+            for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
+                if (au <= P.umax[abs(v)]) {
+                    const int I = rp[(PR + v) * RAWP + PR + u];
+                    m10 += u * I;
+                    m01 += v * I;
+                }
             }
         }
 #pragma unroll
@@ -699,46 +784,84 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
             m10 += __shfl_xor_sync(0xffffffffu, m10, o);
             m01 += __shfl_xor_sync(0xffffffffu, m01, o);
         }
-        if ((tid & 31) == 0) { s_m[0][tid >> 5] = m10; s_m[1][tid >> 5] = m01; }
+        angle = fast_atan2_dev((float)m01, (float)m10);        // every lane computes the same value
     }
-    // ---- horizontal 7-tap pass (8.8 fixed point), columns -18..18 of all 43 rows
-    for (int i = tid; i < PW * HW; i += DESC_THREADS) {
-        const int r = i / HW, c = i - r * HW;            // output column c <-> raw columns c .. c+6
-        const uint8_t* p = raw + r * RAWP + c;
-        H[r * HP + c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (mode == 0) {
-            int m10 = 0, m01 = 0;
-            for (int w = 0; w < DESC_THREADS / 32; w++) { m10 += s_m[0][w]; m01 += s_m[1][w]; }
-            angle = fast_atan2_dev((float)m01, (float)m10);
-        }
-        const float factorPI = (float)(3.141592653589793238462643383279502884197169399375 / 180.0);   // (float)(CV_PI/180.f)
-        float a, b;
-        ref_cos_sin(__fmul_rn(angle, factorPI), &a, &b);
-        s_ab[0] = a; s_ab[1] = b; s_ab[2] = angle;
-    }
-    __syncthreads();
-    const float a = s_ab[0], b = s_ab[1];
-    // ---- 256 binary tests, one per thread; vertical 7-tap evaluated at the two sample points
+    // ---- horizontal 7-tap pass (8.8 fixed point), columns -18..18 of all 43 rows.
+    //      Each lane produces 4 adjacent outputs from 3 aligned words of the row (10 source bytes).
     {
-        const int px0 = c_pattern[tid * 4 + 0], py0 = c_pattern[tid * 4 + 1];
-        const int px1 = c_pattern[tid * 4 + 2], py1 = c_pattern[tid * 4 + 3];
+        const int base4 = shift & ~3, sh = shift & 3;          // shift in 0..3 -> base4 == 0
+        (void)base4;
+        for (int i = lane; i < PW * 10; i += 32) {             // 10 groups of 4 outputs cover 37 (+3 spare) columns
+            const int r = i / 10, g4 = i - r * 10;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + r * RAWP) + g4;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = (g4 < 9) ? w[3] : 0u;     // 12 words per row
+            // bytes b[j] = raw[r][4*g4 + sh + j], j = 0..9
+            const uint32_t q0 = __funnelshift_r(w0, w1, 8 * sh), q1 = __funnelshift_r(w1, w2, 8 * sh),
+                           q2 = __funnelshift_r(w2, w3, 8 * sh);
+            int bt[10];
+            bt[0] = q0 & 255; bt[1] = (q0 >> 8) & 255; bt[2] = (q0 >> 16) & 255; bt[3] = q0 >> 24;
+            bt[4] = q1 & 255; bt[5] = (q1 >> 8) & 255; bt[6] = (q1 >> 16) & 255; bt[7] = q1 >> 24;
+            bt[8] = q2 & 255; bt[9] = (q2 >> 8) & 255;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = 4 * g4 + j;
+                if (c < HW)
+                    H[r * HP + c] = (uint16_t)(18 * (bt[j] + bt[j + 6]) + 34 * (bt[j + 1] + bt[j + 5]) + 48 * (bt[j + 2] + bt[j + 4]) + 56 * bt[j + 3]);
+            }
+        }
+    }
+    float a, b;
+    {
+        const float factorPI = (float)(3.141592653589793238462643383279502884197169399375 / 180.0);   // (float)(CV_PI/180.f)
+        float ca = 0.f, sb = 0.f;
+        if (lane == 0) ref_cos_sin(__fmul_rn(angle, factorPI), &ca, &sb);
+        a = __shfl_sync(0xffffffffu, ca, 0);
+        b = __shfl_sync(0xffffffffu, sb, 0);
+    }
+    __syncwarp();
+    // ---- vertical 7-tap pass: lane = column, sliding 7-row window in registers -> blurred 37x37 patch (u8) that
+    //      overwrites the raw patch (no longer needed); one shared load per sample afterwards
+    uint8_t* G = raw;                                           // G[(dy+18) * GP + (dx+18)]
+    constexpr int GP = 40;
+    {   // columns 0..31: one lane per column, 7-row sliding window
+        const int c = lane;
+        uint32_t w0 = H[0 * HP + c], w1 = H[1 * HP + c], w2 = H[2 * HP + c], w3 = H[3 * HP + c], w4 = H[4 * HP + c],
+                 w5 = H[5 * HP + c];
+#pragma unroll 4
+        for (int r = 0; r < HW; r++) {
+            const uint32_t w6 = H[(r + 6) * HP + c];
+            const uint32_t acc = 18u * (w0 + w6) + 34u * (w1 + w5) + 48u * (w2 + w4) + 56u * w3;
+            G[r * GP + c] = (uint8_t)((acc + (1u << 15)) >> 16);
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+        }
+        // columns 32..36: 5 x 37 outputs spread over the warp, direct 7-tap
+        for (int i = lane; i < 5 * HW; i += 32) {
+            const int r = i / 5, cc = 32 + (i - r * 5);
+            const uint16_t* h = H + r * HP + cc;
+            const uint32_t acc = 18u * (h[0] + h[6 * HP]) + 34u * (h[HP] + h[5 * HP]) + 48u * (h[2 * HP] + h[4 * HP]) + 56u * h[3 * HP];
+            G[r * GP + cc] = (uint8_t)((acc + (1u << 15)) >> 16);
+        }
+    }
+    __syncwarp();
+    // ---- lane j evaluates tests 8j..8j+7 = descriptor byte j (:118-145)
+    {
         auto sample = [&](int px, int py) -> int {
             const float xf = (float)px, yf = (float)py;
             const int dy = __float2int_rn(__fadd_rn(__fmul_rn(xf, b), __fmul_rn(yf, a)));   // cvRound(x*b + y*a)
             const int dx = __float2int_rn(__fsub_rn(__fmul_rn(xf, a), __fmul_rn(yf, b)));   // cvRound(x*a - y*b)
-            const uint16_t* h = H + (PR + dy - 3) * HP + (dx + 18);
-            const uint32_t acc = 18u * (h[0] + h[6 * HP]) + 34u * (h[HP] + h[5 * HP]) + 48u * (h[2 * HP] + h[4 * HP]) + 56u * h[3 * HP];
-            return (int)((acc + (1u << 15)) >> 16);
+            return G[(dy + 18) * GP + (dx + 18)];
         };
-        const int t0 = sample(px0, py0), t1 = sample(px1, py1);
-        const unsigned bal = __ballot_sync(0xffffffffu, t0 < t1);      // bit j of byte i = test 8i+j (:118-145)
-        if ((tid & 31) == 0)
-            *reinterpret_cast<uint32_t*>(desc_out + ((size_t)frame * P.out_cap + out_idx) * 32 + (tid >> 5) * 4) = bal;
+        int byte = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const char4 pt = __ldg(pattern + lane * 8 + j);
+            const int t0 = sample(pt.x, pt.y);
+            const int t1 = sample(pt.z, pt.w);
+            byte |= (t0 < t1) << j;
+        }
+        desc_out[((size_t)frame * P.out_cap + out_idx) * 32 + lane] = (uint8_t)byte;
     }
-    if (tid == 0 && mode == 0) {
+    if (lane == 0 && mode == 0) {
         ygz_keypoint kp;
         if (level != 0) {            // keypoint->pt *= scale, :1019-1024
             kp.x = __fmul_rn((float)cx, L.scale);
@@ -747,7 +870,7 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
             kp.x = (float)cx; kp.y = (float)cy;
         }
         kp.size = L.size;
-        kp.angle = s_ab[2];
+        kp.angle = angle;
         kp.response = (float)score;
         kp.octave = level;
         kp.class_id = -1;

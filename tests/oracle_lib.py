@@ -107,7 +107,7 @@ def lib(native=False):
                               f32p, C.c_int, i32p]
     L.orc_frontend_batch.restype = C.c_long
     L.orc_frontend_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_float, C.c_int, C.POINTER(C.c_long)]
+                                     C.c_float, C.c_int, C.POINTER(C.c_long), C.c_int]
     L.orc_se3_exp.argtypes = [f32p, f32p, f32p]
     L.orc_se3_mul.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p]
     L.orc_se3_inv.argtypes = [f32p, f32p, f32p, f32p]
@@ -270,11 +270,11 @@ def se3_exp(x6):
 
 
 def frontend_batch(imgs, threads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, nnratio=0.7, check_ori=True,
-                   native=True):
+                   native=True, repeat=1):
     """CPU baseline: extract + SearchByBoW(prev frame) over imgs[n,h,w]; returns (matches, keypoints)."""
     imgs = np.ascontiguousarray(imgs, np.uint8)
     n, h, w = imgs.shape
     kp = C.c_long()
     m = lib(native).orc_frontend_batch(nfeatures, scale, nlevels, ini_th, min_th, _ptr(imgs, u8p), n, w, h, threads,
-                                       nnratio, int(check_ori), C.byref(kp))
+                                       nnratio, int(check_ori), C.byref(kp), repeat)
     return m, kp.value
