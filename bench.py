@@ -197,6 +197,47 @@ def run_reference(args):
     return 0
 
 
+def aux_metrics(m, device):
+    """Secondary configurations of BASELINE.json (not part of `value`): C3 SparseImgAlign batch and C5 brute-force
+    stereo-size matcher, device-timed with CUDA events."""
+    import importlib
+    synth = importlib.import_module("orb_ygz_slam_b200.synth")
+    aux = {}
+    try:
+        # C3: 4-level x2.0 pyramid (built by the device extractor), 200 patches, levels 3..1, 10 GN iterations
+        px = m.ORBextractor(1000, 2.0, 4, 20, 7, width=W, height=H, max_batch=1, device=device)
+        inv = px.tables()["inv_scale"]
+        probs = []
+        for seed in range(4):
+            s = synth.synth_sia_pair(seed, n_pts=200, w=W, h=H)
+            px.ComputePyramid(s["ref"]); ref = [px.level(0, l) for l in range(4)]
+            px.ComputePyramid(s["cur"]); cur = [px.level(0, l) for l in range(4)]
+            probs.append(m.make_sia_problem(ref, cur, inv, s["K"], s["px"], s["xyz"]))
+        P = 64
+        sia = m.SparseImgAlign(3, 1, 10, device=device, max_problems=P, max_features=256, max_level_pixels=2 * W * H)
+        batch = [probs[i % 4] for i in range(P)]
+        sia.run_batch(batch)
+        it = 20
+        ms = sia.time(P, it) / it
+        aux["sia_c3"] = {"problems_per_launch": P, "patches": 200, "levels": "3..1", "gn_iters_per_level": 10,
+                         "ms_per_launch": ms, "alignments_per_s": P / (ms / 1e3)}
+    except Exception as e:        # aux numbers never break the headline line
+        aux["sia_c3"] = {"error": str(e)[:200]}
+    try:
+        q, t, _ = synth.synth_descriptors(5, 2000, 2000)
+        mt = m.ORBmatcher(0.7, True, device=device)
+        import time as _t
+        mt.bf_top2(q, t)
+        t0 = _t.perf_counter()
+        for _ in range(20):
+            mt.bf_top2(q, t)
+        dt = (_t.perf_counter() - t0) / 20
+        aux["bf_top2_c5"] = {"nq": 2000, "nt": 2000, "ms_per_call_host_buffers": dt * 1e3, "comparisons_per_s": 4e6 / dt}
+    except Exception as e:
+        aux["bf_top2_c5"] = {"error": str(e)[:200]}
+    return aux
+
+
 def workload_config(batch):
     return {"workload": "C2 synthetic EuRoC-shape mono stream 752x480 u8: ORBextractor(1000,1.2,8,20,7) + "
                         "ORBmatcher(0.7,checkOri).SearchByBoW vs previous frame (synthetic vocabulary byte0>>2)",
@@ -213,6 +254,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -368,6 +410,8 @@ def main():
             "counters_all_ranks": {"columns": ["frames", "keypoints", "matches", "sia_iters", "bytes_in", "bytes_out",
                                                "kernel_launches", "elapsed_ns"], "rows": gathered.tolist()},
         }
+        if world == 1 and not args.no_aux:
+            out["aux"] = aux_metrics(m, local)
         if not args.no_cpu_baseline and world == 1:
             threads, cpu_note = host_threads()
             fps, done, dt, native = cpu_arm(frames, threads, min_seconds=8.0)

@@ -353,7 +353,7 @@ static int launch_pyramid(ygz_orb* h, int n) {
         const LevelHost& D = h->lv[l];
         dim3 block(PYR_THREADS);
         dim3 grid(ceil_div(ceil_div(D.w, 4), PYR_THREADS), ceil_div(D.h, PYR_ROWS), n);
-        k_pyr_resize<<<grid, block, 0, h->stream>>>(S.d_base, S.pitch, S.frame_stride, S.w, D.d_base, D.pitch, D.frame_stride,
+        k_pyr_resize<<<grid, block, 0, h->stream>>>(S.d_base, S.pitch, S.frame_stride, S.w, S.h, D.d_base, D.pitch, D.frame_stride,
                                                     D.w, D.h, D.d_tx, D.d_ty);
     }
     YGZ_CUDA_TRY(cudaGetLastError());

@@ -70,19 +70,44 @@ __device__ __forceinline__ int cand_s(uint32_t c) { return c >> 24; }
 // K1  pyramid level from the previous level: cv::resize(INTER_LINEAR) on CV_8UC1, 11-bit fixed point
 //     (src/ORBextractor.cc:1139).  4 output pixels per thread, one 32-bit store.
 // ------------------------------------------------------------------------------------------------
-constexpr int PYR_ROWS = 8;          // output rows per thread (column tables stay in registers, source rows are reused)
+constexpr int PYR_ROWS = 8;          // output rows per CTA / thread
 constexpr int PYR_THREADS = 64;      // 4 output columns per thread -> 256 columns per CTA
+constexpr int PYR_SROWS = 12;        // source rows staged per CTA (8 output rows at scale 1.2 span <= 11 source rows)
+constexpr int PYR_SPITCH = 352;      // staged bytes per source row (256 * 1.2 + slack, multiple of 16)
 
+// The CTA stages the source window of its 256 x 8 output tile in shared memory with coalesced 16-byte streaming loads
+// (every source byte is read from HBM/L2 once per CTA), then each thread produces a 4 x 8 block: horizontal taps from
+// shared memory with the column tables (xofs / ialpha of cv::resize) held in registers, source rows reused between
+// consecutive output rows, one aligned 32-bit store per row.  Falls back to direct global reads when the window does
+// not fit the staging buffer (level-to-level scale outside ~[1.0, 1.35]).
 __global__ void __launch_bounds__(PYR_THREADS) k_pyr_resize(const uint8_t* __restrict__ src, int spitch, size_t sframe,
-                                                            int sw, uint8_t* __restrict__ dst, int dpitch, size_t dframe,
+                                                            int sw, int sh, uint8_t* __restrict__ dst, int dpitch, size_t dframe,
                                                             int dw, int dh, const ResizeTabX* __restrict__ tx,
                                                             const ResizeTabY* __restrict__ ty) {
-    const int x4 = (blockIdx.x * PYR_THREADS + threadIdx.x) * 4;
-    if (x4 >= dw) return;
+    __shared__ __align__(16) uint8_t stage[PYR_SROWS * PYR_SPITCH];
+    const int xg0 = blockIdx.x * PYR_THREADS * 4;              // first output column of the CTA
+    const int x4 = xg0 + threadIdx.x * 4;
     const int dy0 = blockIdx.y * PYR_ROWS;
+    const int dy1 = min(dy0 + PYR_ROWS, dh) - 1;
     const uint8_t* S = src + (size_t)blockIdx.z * sframe;
     uint8_t* D = dst + (size_t)blockIdx.z * dframe;
-    // horizontal tables of this thread's four columns (xofs / ialpha of cv::resize), kept in registers
+    // source window of the tile
+    const int xlast = min(xg0 + PYR_THREADS * 4, dw) - 1;
+    const int sx_lo = __ldg(reinterpret_cast<const int2*>(tx) + xg0).x & ~15;
+    const int sx_hi = min(__ldg(reinterpret_cast<const int2*>(tx) + xlast).x + 1, sw - 1);
+    const int sy_lo = ty[dy0].y0, sy_hi = ty[dy1].y1;
+    const int nrows = sy_hi - sy_lo + 1;
+    const int nvec = (sx_hi - sx_lo) / 16 + 1;                 // 16-byte vectors per staged row (reads stay inside the pitch)
+    const bool staged = (nrows <= PYR_SROWS) && (nvec * 16 <= PYR_SPITCH) && (sx_lo + nvec * 16 <= spitch);
+    if (staged) {
+        for (int i = threadIdx.x; i < nrows * nvec; i += PYR_THREADS) {
+            const int r = i / nvec, c = i - r * nvec;
+            const uint4 v = ld_nc_u4(S + (size_t)(sy_lo + r) * spitch + sx_lo + c * 16);
+            *reinterpret_cast<uint4*>(stage + r * PYR_SPITCH + c * 16) = v;
+        }
+    }
+    __syncthreads();
+    if (x4 >= dw) return;
     int ofs0[4], ofs1[4], a0[4], a1[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -96,14 +121,18 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_resize(const uint8_t* __res
     int hA[4], hB[4];                // horizontally interpolated source rows yA (= y0 of the current row) and yB (= y1)
     int yA = -1, yB = -1;
     auto hrow = [&](int y, int* h) {
-        const uint8_t* R = S + (size_t)y * spitch;
+        if (staged) {
+            const uint8_t* R = stage + (y - sy_lo) * PYR_SPITCH - sx_lo;
 #pragma unroll
-        for (int i = 0; i < 4; i++) h[i] = R[ofs0[i]] * a0[i] + R[ofs1[i]] * a1[i];
+            for (int i = 0; i < 4; i++) h[i] = R[ofs0[i]] * a0[i] + R[ofs1[i]] * a1[i];
+        } else {
+            const uint8_t* R = S + (size_t)y * spitch;
+#pragma unroll
+            for (int i = 0; i < 4; i++) h[i] = R[ofs0[i]] * a0[i] + R[ofs1[i]] * a1[i];
+        }
     };
 #pragma unroll 1
-    for (int r = 0; r < PYR_ROWS; r++) {
-        const int dy = dy0 + r;
-        if (dy >= dh) break;
+    for (int dy = dy0; dy <= dy1; dy++) {
         const ResizeTabY yy = ty[dy];
         if (yy.y0 == yB) {           // the usual case when downscaling: this row's upper source row is the previous lower one
 #pragma unroll
