@@ -144,89 +144,121 @@ struct BowBatchArgs {
     int* nmatches;               // [pairs]
 };
 
+// dynamic shared memory of k_bow_match_batch for a per-frame capacity `cap` (features), cap2 = next power of two
+__host__ __device__ inline size_t bow_smem_bytes(int cap) {
+    int p2 = 1; while (p2 < cap) p2 <<= 1;
+    return (size_t)p2 * 8 * 2        // sorted (node, index) keys of both frames
+         + (size_t)cap * 32 * 2      // descriptors of both frames
+         + (size_t)cap * 2 * 2       // match_of_f (short) + seg_start (short)
+         + (size_t)cap               // bin_of_f
+         + 64;
+}
+
 __global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A) {
-    __shared__ unsigned long long skf[BOW_MAX_FEATS];    // (node << 32) | feature index, sorted
-    __shared__ unsigned long long sf[BOW_MAX_FEATS];
-    __shared__ short match_of_f[BOW_MAX_FEATS];          // KF feature matched to F feature (or -1)
-    __shared__ signed char bin_of_f[BOW_MAX_FEATS];
+    extern __shared__ __align__(16) uint8_t bow_smem[];
     __shared__ int hist[HISTO_LENGTH];
     __shared__ int s_keep[3];
     __shared__ int s_n;
+    __shared__ int s_wcnt[BOW_THREADS / 32];
+    __shared__ int s_nseg;
+    const int cap = A.cap;
+    int p2 = 1; while (p2 < cap) p2 <<= 1;
+    unsigned long long* skf = reinterpret_cast<unsigned long long*>(bow_smem);   // (node << 32) | feature index, sorted
+    unsigned long long* sf = skf + p2;
+    uint4* kds = reinterpret_cast<uint4*>(sf + p2);                                // KF descriptors
+    uint4* fds = kds + (size_t)cap * 2;                                            // F descriptors
+    short* match_of_f = reinterpret_cast<short*>(fds + (size_t)cap * 2);           // KF feature matched to F feature (or -1)
+    short* seg_start = match_of_f + cap;                                           // first sorted position of every KF node
+    signed char* bin_of_f = reinterpret_cast<signed char*>(seg_start + cap);
     const int pair = blockIdx.x;
     const int kf = A.kf_idx[pair], fr = A.f_idx[pair];
-    const int nk = min(A.counts[kf], BOW_MAX_FEATS), nf = min(A.counts[fr], BOW_MAX_FEATS);
+    const int nk = min(A.counts[kf], cap), nf = min(A.counts[fr], cap);
     const ygz_keypoint* kkp = A.kps + (size_t)kf * A.cap;
     const ygz_keypoint* fkp = A.kps + (size_t)fr * A.cap;
     const uint4* kd = A.desc + (size_t)kf * A.cap * 2;
     const uint4* fd = A.desc + (size_t)fr * A.cap * 2;
     int pk = 1; while (pk < nk) pk <<= 1;
     int pf = 1; while (pf < nf) pf <<= 1;
+    // stage both descriptor sets (coalesced 16-byte loads); every later access is a shared-memory read
+    for (int i = threadIdx.x; i < nk * 2; i += BOW_THREADS) kds[i] = __ldg(kd + i);
+    for (int i = threadIdx.x; i < nf * 2; i += BOW_THREADS) fds[i] = __ldg(fd + i);
+    __syncthreads();
     // A.node == nullptr: synthetic vocabulary (bench stand-in for DBoW2 transform): node = top 6 bits of byte 0
     auto node_of = [&](int frame, const uint4* d, int i) -> unsigned long long {
         return A.node ? (unsigned long long)A.node[(size_t)frame * A.cap + i]
                       : (unsigned long long)((reinterpret_cast<const uint8_t*>(d + (size_t)i * 2)[0]) >> 2);
     };
     for (int i = threadIdx.x; i < pk; i += BOW_THREADS)
-        skf[i] = i < nk ? ((node_of(kf, kd, i) << 32) | (unsigned)i) : ~0ull;
+        skf[i] = i < nk ? ((node_of(kf, kds, i) << 32) | (unsigned)i) : ~0ull;
     for (int i = threadIdx.x; i < pf; i += BOW_THREADS)
-        sf[i] = i < nf ? ((node_of(fr, fd, i) << 32) | (unsigned)i) : ~0ull;
-    for (int i = threadIdx.x; i < BOW_MAX_FEATS; i += BOW_THREADS) { match_of_f[i] = -1; bin_of_f[i] = -1; }
+        sf[i] = i < nf ? ((node_of(fr, fds, i) << 32) | (unsigned)i) : ~0ull;
+    for (int i = threadIdx.x; i < cap; i += BOW_THREADS) { match_of_f[i] = -1; bin_of_f[i] = -1; }
     if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x == 0) { s_n = 0; s_nseg = 0; }
     __syncthreads();
     bitonic_sort_u64(skf, pk);
     bitonic_sort_u64(sf, pf);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = BOW_THREADS / 32;
-    // each warp scans the KF segment starts; segment s is handled by warp (s % nwarps)
-    int seg = 0;
-    for (int i0 = 0; i0 < nk;) {
+    // ---- KF node segments: ordered compaction of the positions where the node id changes
+    for (int base = 0; base < nk; base += BOW_THREADS) {
+        const int i = base + threadIdx.x;
+        const bool st = i < nk && (uint32_t)(skf[i] >> 32) != 0xFFFFFFFFu && (i == 0 || (uint32_t)(skf[i] >> 32) != (uint32_t)(skf[i - 1] >> 32));
+        const unsigned bal = __ballot_sync(0xffffffffu, st);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = s_nseg;
+        for (int w = 0; w < warp; w++) off += s_wcnt[w];
+        if (st) seg_start[off + __popc(bal & lanemask_lt())] = (short)i;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < nwarps; w++) t += s_wcnt[w]; s_nseg += t; }
+        __syncthreads();
+    }
+    const int nseg = s_nseg;
+    // ---- one warp per common node: the reference's sequential loop over that node's KF features (:180-234)
+    for (int sgm = warp; sgm < nseg; sgm += nwarps) {
+        const int i0 = seg_start[sgm];
         const uint32_t node = (uint32_t)(skf[i0] >> 32);
-        int i1 = i0 + 1;
-        while (i1 < nk && (uint32_t)(skf[i1] >> 32) == node) i1++;
-        if (node != 0xFFFFFFFFu && (seg % nwarps) == warp) {
-            // F segment with the same node (lower_bound)
-            int lo = 0, hi = nf;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(sf[mid] >> 32) < node) lo = mid + 1; else hi = mid; }
-            int j1 = lo;
-            while (j1 < nf && (uint32_t)(sf[j1] >> 32) == node) j1++;
-            const int j0 = lo;
-            for (int i = i0; i < i1 && j1 > j0; i++) {
-                const int realIdxKF = (int)(skf[i] & 0xFFFFFFFFu);
-                const uint4 a0 = __ldg(kd + realIdxKF * 2), a1 = __ldg(kd + realIdxKF * 2 + 1);
-                int b = 256, bi = INT_MAX, s = 256;
-                for (int j = j0 + lane; j < j1; j += 32) {
-                    const int realIdxF = (int)(sf[j] & 0xFFFFFFFFu);
-                    if (match_of_f[realIdxF] >= 0) continue;                      // :200-201
-                    const int d = hamming256(a0, a1, __ldg(fd + realIdxF * 2), __ldg(fd + realIdxF * 2 + 1));
-                    // order inside the bucket = position j (ascending); keep position for the tie-break
-                    if (d < b) { s = b; b = d; bi = j; }
-                    else if (d < s) s = d;
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    const int ob = __shfl_xor_sync(0xffffffffu, b, o);
-                    const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    const int os = __shfl_xor_sync(0xffffffffu, s, o);
-                    merge_top2(b, bi, s, ob, obi, os);
-                }
-                if (lane == 0 && b <= TH_LOW && (float)b < A.nnratio * (float)s) {    // :216-217
-                    const int bestIdxF = (int)(sf[bi] & 0xFFFFFFFFu);
-                    match_of_f[bestIdxF] = (short)realIdxKF;
-                    if (A.check_ori) {
-                        float rot = kkp[realIdxKF].angle - fkp[bestIdxF].angle;        // :221-226
-                        if (rot < 0.0f) rot += 360.0f;
-                        int bin = (int)roundf(rot * (1.0f / HISTO_LENGTH));
-                        if (bin == HISTO_LENGTH) bin = 0;
-                        bin_of_f[bestIdxF] = (signed char)bin;
-                        atomicAdd(&hist[bin], 1);
-                    }
-                    atomicAdd(&s_n, 1);
-                }
-                __syncwarp();
+        int i1 = (sgm + 1 < nseg) ? (int)seg_start[sgm + 1] : nk;
+        while (i1 > i0 && (uint32_t)(skf[i1 - 1] >> 32) != node) i1--;      // trailing 0xFFFFFFFF (no node) entries
+        int lo = 0, hi = nf;                                                 // F segment with the same node (lower_bound)
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint32_t)(sf[mid] >> 32) < node) lo = mid + 1; else hi = mid; }
+        int j1 = lo;
+        while (j1 < nf && (uint32_t)(sf[j1] >> 32) == node) j1++;
+        const int j0 = lo;
+        for (int i = i0; i < i1 && j1 > j0; i++) {
+            const int realIdxKF = (int)(skf[i] & 0xFFFFFFFFu);
+            const uint4 a0 = kds[realIdxKF * 2], a1 = kds[realIdxKF * 2 + 1];
+            int b = 256, bi = INT_MAX, s = 256;
+            for (int j = j0 + lane; j < j1; j += 32) {
+                const int realIdxF = (int)(sf[j] & 0xFFFFFFFFu);
+                if (match_of_f[realIdxF] >= 0) continue;                      // :200-201
+                const int d = hamming256(a0, a1, fds[realIdxF * 2], fds[realIdxF * 2 + 1]);
+                // order inside the bucket = position j (ascending); keep position for the tie-break
+                if (d < b) { s = b; b = d; bi = j; }
+                else if (d < s) s = d;
             }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const int ob = __shfl_xor_sync(0xffffffffu, b, o);
+                const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int os = __shfl_xor_sync(0xffffffffu, s, o);
+                merge_top2(b, bi, s, ob, obi, os);
+            }
+            if (lane == 0 && b <= TH_LOW && (float)b < A.nnratio * (float)s) {    // :216-217
+                const int bestIdxF = (int)(sf[bi] & 0xFFFFFFFFu);
+                match_of_f[bestIdxF] = (short)realIdxKF;
+                if (A.check_ori) {
+                    float rot = kkp[realIdxKF].angle - fkp[bestIdxF].angle;        // :221-226
+                    if (rot < 0.0f) rot += 360.0f;
+                    int bin = (int)roundf(rot * (1.0f / HISTO_LENGTH));
+                    if (bin == HISTO_LENGTH) bin = 0;
+                    bin_of_f[bestIdxF] = (signed char)bin;
+                    atomicAdd(&hist[bin], 1);
+                }
+                atomicAdd(&s_n, 1);
+            }
+            __syncwarp();
         }
-        seg++;
-        i0 = i1;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -754,6 +786,7 @@ static int bow_batch_prepare(ygz_matcher* h, ygz_orb* orb, int n_pairs, int* cap
         YGZ_CUDA_TRY(cudaMalloc(&h->d_nmatches, (size_t)n_pairs * 4));
         h->bow_pairs_cap = n_pairs;
         h->bow_cap = cap;
+        YGZ_CUDA_TRY(cudaFuncSetAttribute(k_bow_match_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bow_smem_bytes(cap)));
     }
     *cap_out = cap;
     (void)frames_out;
@@ -786,7 +819,7 @@ int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int che
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
     A.node = node_of_feature ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
-    k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, h->stream>>>(A);
+    k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
     YGZ_CUDA_TRY(cudaGetLastError());
     h->last_args = A;
     h->last_pairs = n_pairs;
@@ -813,7 +846,7 @@ int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, i
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
     A.node = nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
-    k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, st>>>(A);
+    k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), st>>>(A);
     YGZ_CUDA_TRY(cudaGetLastError());
     h->last_args = A;
     h->last_pairs = n_pairs;
@@ -829,7 +862,7 @@ int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, in
     A.nnratio = nnratio; A.check_ori = check_ori;
     YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
     YGZ_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    for (int i = 0; i < iters; i++) k_bow_match_batch<<<n_pairs, BOW_THREADS, 0, h->stream>>>(A);
+    for (int i = 0; i < iters; i++) k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
     YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
@@ -850,7 +883,7 @@ int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, flo
     for (int i = 0; i < iters; i++) {
         int rc = ygz_orb_run(orb, n_frames);
         if (rc) return rc;
-        k_bow_match_batch<<<h->last_pairs, BOW_THREADS, 0, st>>>(A);
+        k_bow_match_batch<<<h->last_pairs, BOW_THREADS, bow_smem_bytes(A.cap), st>>>(A);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, st));

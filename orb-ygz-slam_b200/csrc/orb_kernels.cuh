@@ -95,7 +95,15 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_resize(const uint8_t* __res
     const int xlast = min(xg0 + PYR_THREADS * 4, dw) - 1;
     const int sx_lo = __ldg(reinterpret_cast<const int2*>(tx) + xg0).x & ~15;
     const int sx_hi = min(__ldg(reinterpret_cast<const int2*>(tx) + xlast).x + 1, sw - 1);
-    const int sy_lo = ty[dy0].y0, sy_hi = ty[dy1].y1;
+    // the row tables of the tile are fetched up front (independent loads) instead of one dependent load per row
+    ResizeTabY yt[PYR_ROWS];
+#pragma unroll
+    for (int r = 0; r < PYR_ROWS; r++) {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(ty) + min(dy0 + r, dh - 1));
+        yt[r].y0 = (short)(v.x & 0xFFFF); yt[r].y1 = (short)(v.x >> 16);
+        yt[r].b0 = (short)(v.y & 0xFFFF); yt[r].b1 = (short)(v.y >> 16);
+    }
+    const int sy_lo = yt[0].y0, sy_hi = ty[dy1].y1;
     const int nrows = sy_hi - sy_lo + 1;
     const int nvec = (sx_hi - sx_lo) / 16 + 1;                 // 16-byte vectors per staged row (reads stay inside the pitch)
     const bool staged = (nrows <= PYR_SROWS) && (nvec * 16 <= PYR_SPITCH) && (sx_lo + nvec * 16 <= spitch);
@@ -131,9 +139,11 @@ __global__ void __launch_bounds__(PYR_THREADS) k_pyr_resize(const uint8_t* __res
             for (int i = 0; i < 4; i++) h[i] = R[ofs0[i]] * a0[i] + R[ofs1[i]] * a1[i];
         }
     };
-#pragma unroll 1
-    for (int dy = dy0; dy <= dy1; dy++) {
-        const ResizeTabY yy = ty[dy];
+#pragma unroll
+    for (int r = 0; r < PYR_ROWS; r++) {
+        const int dy = dy0 + r;
+        if (dy > dy1) break;
+        const ResizeTabY yy = yt[r];
         if (yy.y0 == yB) {           // the usual case when downscaling: this row's upper source row is the previous lower one
 #pragma unroll
             for (int i = 0; i < 4; i++) hA[i] = hB[i];
@@ -543,6 +553,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
         for (int i = tid; i < Lsz; i += OCT_THREADS) S.processed[i] = 0;
         __syncthreads();
         // P2: keys of expandable nodes vote for their quadrant
+#pragma unroll 4
         for (int k = tid; k < n; k += OCT_THREADS) {
             const int nid = keynode[k];
             if (CNT[nid] > 1) {
@@ -644,6 +655,7 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
         }
         __syncthreads();
         // P6: relabel keys
+#pragma unroll 4
         for (int k = tid; k < n; k += OCT_THREADS) {
             const int nid = keynode[k];
             if (S.processed[nid]) {
