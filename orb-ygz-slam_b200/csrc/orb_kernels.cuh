@@ -442,9 +442,10 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
                                                         const uint16_t* __restrict__ cell_count,
                                                         uint32_t* __restrict__ keys_all, uint16_t* __restrict__ keynode_all,
                                                         int* __restrict__ nkeys_all, uint32_t* __restrict__ sel_all,
-                                                        int* __restrict__ nsel_all) {
+                                                        int* __restrict__ nsel_all, int node_smem_bytes, int key_cache) {
     extern __shared__ __align__(16) uint8_t smem_oct[];
-    const int level = blockIdx.x, frame = blockIdx.y;
+    // grid = (frames, levels): the heavy level-0 problems of ALL frames are scheduled first, the cheap coarse levels fill the tail
+    const int level = blockIdx.y, frame = blockIdx.x;
     const LevelDev& L = P.lv[level];
     const int NC = L.node_cap;
     const int N = L.n_target;
@@ -474,6 +475,10 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
 
     uint32_t* keys = keys_all + (size_t)frame * P.key_total + L.key_off;
     uint16_t* keynode = keynode_all + (size_t)frame * P.key_total + L.key_off;
+    // shared-memory cache of the key list (packed candidates + node labels): the refinement passes re-read every key
+    // ~20 times with no reuse distance an L1 would catch; levels whose key count exceeds the cache stay in global memory
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(smem_oct + node_smem_bytes);
+    uint16_t* snode = reinterpret_cast<uint16_t*>(skeys + key_cache);
     uint32_t* sel = sel_all + (size_t)frame * P.sel_total + L.sel_off;
 
     // ---- step 0: compact this level's per-cell candidate slots into one ordered key list
@@ -504,6 +509,12 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
     }
     if (tid == 0) nkeys_all[(size_t)frame * P.nlevels + level] = n;
     __syncthreads();     // keys[] written by this CTA are visible to it after the barrier
+    if (n <= key_cache) {
+        for (int k = tid; k < n; k += OCT_THREADS) skeys[k] = keys[k];
+        keys = skeys;
+        keynode = snode;
+        __syncthreads();
+    }
 
     int cur = 0;
     int Lsz = 0;
@@ -839,15 +850,18 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
             // bytes b[j] = raw[r][4*g4 + sh + j], j = 0..9
             const uint32_t q0 = __funnelshift_r(w0, w1, 8 * sh), q1 = __funnelshift_r(w1, w2, 8 * sh),
                            q2 = __funnelshift_r(w2, w3, 8 * sh);
-            int bt[10];
-            bt[0] = q0 & 255; bt[1] = (q0 >> 8) & 255; bt[2] = (q0 >> 16) & 255; bt[3] = q0 >> 24;
-            bt[4] = q1 & 255; bt[5] = (q1 >> 8) & 255; bt[6] = (q1 >> 16) & 255; bt[7] = q1 >> 24;
-            bt[8] = q2 & 255; bt[9] = (q2 >> 8) & 255;
+            // adjacent byte pairs packed as 16x2: P[j] = b[j] | b[j+1] << 16.  Every partial sum stays below 2^16
+            // (H <= 255 * 256), so ordinary 32-bit adds / multiplies act on both halves independently:
+            // one instruction stream yields two neighbouring H values.
+            unsigned Pk[9];
+            Pk[0] = __byte_perm(q0, 0, 0x4140); Pk[1] = __byte_perm(q0, 0, 0x4241); Pk[2] = __byte_perm(q0, 0, 0x4342);
+            Pk[3] = __byte_perm(q0, q1, 0x7473) & 0x00FF00FFu; Pk[4] = __byte_perm(q1, 0, 0x4140); Pk[5] = __byte_perm(q1, 0, 0x4241);
+            Pk[6] = __byte_perm(q1, 0, 0x4342); Pk[7] = __byte_perm(q1, q2, 0x7473) & 0x00FF00FFu; Pk[8] = __byte_perm(q2, 0, 0x4140);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 4; j += 2) {
                 const int c = 4 * g4 + j;
-                if (c < HW)
-                    H[r * HP + c] = (uint16_t)(18 * (bt[j] + bt[j + 6]) + 34 * (bt[j + 1] + bt[j + 5]) + 48 * (bt[j + 2] + bt[j + 4]) + 56 * bt[j + 3]);
+                const unsigned hp = 18u * (Pk[j] + Pk[j + 6]) + 34u * (Pk[j + 1] + Pk[j + 5]) + 48u * (Pk[j + 2] + Pk[j + 4]) + 56u * Pk[j + 3];
+                if (c + 1 < HP) *reinterpret_cast<uint32_t*>(&H[r * HP + c]) = hp;      // columns c, c+1 (c even; column 37 is padding)
             }
         }
     }
