@@ -54,6 +54,8 @@ struct ygz_orb {
     ExistingKey* d_existing = nullptr;
     int existing_cap = 0;
     char4* d_pattern = nullptr;
+    TmaMaps tma;
+    int use_tma = 0;
     size_t fast_smem = 0, oct_smem = 0;
     int fast_warp_smem = 0;
     int oct_node_smem = 0, oct_key_cache = 0;
@@ -305,9 +307,20 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
     TRY_OR_FREE(cudaMalloc(&h->d_counts, (size_t)B * 4));
     TRY_OR_FREE(cudaMemset(h->d_counts, 0, (size_t)B * 4));
     TRY_OR_FREE(cudaMemset(h->d_nsel, 0, (size_t)nl * B * 4));
+    // TMA descriptors of the pyramid levels (box 48 x 43 for the descriptor patch); a failed encode only disables the
+    // TMA path (the aligned-word loader is kept), YGZ_NO_TMA=1 forces that for A/B measurements
+    h->use_tma = getenv("YGZ_NO_TMA") ? 0 : 1;
+    std::memset(&h->tma, 0, sizeof(h->tma));
+    for (int l = 0; l < nl && h->use_tma; l++) {
+        const LevelHost& L = h->lv[l];
+        if (L.w < RAWP || L.h < PW ||
+            make_tensor_map_u8_3d(&h->tma.patch[l], L.d_base, L.w, L.h, B, L.pitch, L.frame_stride, RAWP, PW) != 0)
+            h->use_tma = 0;
+    }
     TRY_OR_FREE(cudaMalloc(&h->d_pattern, sizeof(h_pattern)));
     TRY_OR_FREE(cudaMemcpy(h->d_pattern, h_pattern, sizeof(h_pattern), cudaMemcpyHostToDevice));
     TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_orient_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_WARPS * DESC_WARP_SMEM));
     TRY_OR_FREE(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
     TRY_OR_FREE(cudaDeviceSynchronize());
 #undef TRY_OR_FREE
@@ -391,11 +404,11 @@ static int launch_octree(ygz_orb* h, int n) {
 
 static int launch_describe(ygz_orb* h, int n, int n_existing) {
     dim3 grid(ceil_div(h->P.sel_total, DESC_WARPS), n);
-    k_orient_describe<<<grid, DESC_THREADS, 0, h->stream>>>(h->P, 0, n_existing, h->P.sel_total, h->d_pattern, h->d_sel, h->d_nsel, nullptr,
+    k_orient_describe<<<grid, DESC_THREADS, DESC_WARPS * DESC_WARP_SMEM, h->stream>>>(h->P, h->tma, h->use_tma, 0, n_existing, h->P.sel_total, h->d_pattern, h->d_sel, h->d_nsel, nullptr,
                                                            h->d_kps, h->d_desc, h->d_counts);
     if (n_existing > 0) {
         dim3 g2(ceil_div(n_existing, DESC_WARPS), n);
-        k_orient_describe<<<g2, DESC_THREADS, 0, h->stream>>>(h->P, 1, n_existing, n_existing, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing,
+        k_orient_describe<<<g2, DESC_THREADS, DESC_WARPS * DESC_WARP_SMEM, h->stream>>>(h->P, h->tma, h->use_tma, 1, n_existing, n_existing, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing,
                                                              h->d_kps, h->d_desc, h->d_counts);
     }
     YGZ_CUDA_TRY(cudaGetLastError());

@@ -708,10 +708,12 @@ constexpr int DESC_WARPS = 8;           // one warp per keypoint, DESC_WARPS key
 constexpr int DESC_THREADS = DESC_WARPS * 32;
 constexpr int PR = 21;                 // patch radius: 18 (pattern reach) + 3 (blur)
 constexpr int PW = 2 * PR + 1;         // 43
-constexpr int RAWP = 48;               // raw pitch: 12 aligned words cover 43 columns + up to 3 columns of misalignment
+constexpr int RAWP = 64;               // raw pitch = TMA box width: the box must start 16-byte aligned, 43 + 15 columns round up to 64
 constexpr int HW = 37;                 // horizontally blurred columns (-18..18)
 constexpr int HP = 38;                 // pitch of H
-constexpr int DESC_WARP_SMEM = PW * RAWP + PW * HP * 2;     // 2064 + 3268 = 5332 B per warp
+constexpr int DESC_WARP_SMEM = 6144;   // 43*64 raw + 43*38*2 H = 6020 B, rounded to 128 B (TMA destination alignment)
+
+struct TmaMaps { CUtensorMap patch[MAX_LEVELS]; };   // per level: u8 [frames][h][pitch], box 64 x 43 x 1 (rBRIEF / IC patch)
 
 // bit_pattern_31_ (data, src/ORBextractor.cc:152-410) lives in GLOBAL memory as 256 x char4: every lane reads its own
 // eight tests, and lane-divergent addresses serialise on the constant cache.
@@ -748,7 +750,9 @@ struct ExistingKey { float x, y, angle; int octave; };   // pt * mvInvScaleFacto
 // mode 0: keys selected by k_octree (angle computed);  mode 1: pre-existing keys (angle kept, :1088-1099)
 // One WARP per keypoint: raw 43x43 patch -> shared (aligned word loads), IC moments by warp shuffle, horizontal
 // blur pass into H, then every lane evaluates 8 binary tests = one descriptor byte.
-__global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, int mode, int n_existing, int n_items,
+__global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(const __grid_constant__ OrbParams P,
+                                                                  const __grid_constant__ TmaMaps maps, int use_tma,
+                                                                  int mode, int n_existing, int n_items,
                                                                   const char4* __restrict__ pattern,
                                                                   const uint32_t* __restrict__ sel_all,
                                                                   const int* __restrict__ nsel_all,
@@ -756,7 +760,8 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
                                                                   ygz_keypoint* __restrict__ kps_out,
                                                                   uint8_t* __restrict__ desc_out,
                                                                   int* __restrict__ counts_out) {
-    __shared__ __align__(16) uint8_t smem[DESC_WARPS * DESC_WARP_SMEM + 16];
+    extern __shared__ __align__(128) uint8_t smem[];            // DESC_WARPS * DESC_WARP_SMEM (dynamic: 48 KB)
+    __shared__ __align__(8) unsigned long long tma_bar[DESC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * DESC_WARPS + warp;          // (level, slot) index or existing-key index
     const int frame = blockIdx.y;
@@ -799,8 +804,24 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
     // ---- raw patch rows cy-21..cy+21, columns cx-21..cx+21 (REFLECT_101 at the level border)
     const int x0 = cx - PR, y0 = cy - PR;
     int shift;                                                  // column of x0 inside the shared row
+    const bool inside = x0 >= 0 && y0 >= 0 && y0 + PW <= L.h && x0 + PW <= L.w;
+    if (use_tma && inside) {
+        // TMA: one elected lane issues a single bulk tensor copy of the 64 x 43 box (the box start must be 16-byte
+        // aligned in global memory: x is rounded down, `shift` keeps the offset), the warp waits on its mbarrier.
+        // SASS: UTMALDG.3D.  Columns past the level width are zero-filled by the TMA unit and never read.
+        const int xa16 = x0 & ~15;
+        shift = x0 - xa16;
+        __syncwarp();
+        if (elect_one()) {
+            mbar_init(&tma_bar[warp], 1);
+            mbar_expect_tx(&tma_bar[warp], PW * RAWP);
+            tma_load_3d(raw, &maps.patch[level], xa16, y0, frame, &tma_bar[warp]);
+        }
+        __syncwarp();
+        mbar_wait(&tma_bar[warp], 0);
+    } else {
     const int xa = x0 & ~3;
-    if (x0 >= 0 && y0 >= 0 && xa + RAWP <= L.pitch && y0 + PW <= L.h && x0 + PW <= L.w) {
+    if (inside && xa + RAWP <= L.pitch) {
         shift = x0 - xa;
         for (int i = lane; i < PW * (RAWP / 4); i += 32) {     // 43 rows x 12 aligned words
             const int r = i / (RAWP / 4), c = i - r * (RAWP / 4);
@@ -813,6 +834,7 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
             const int r = i / PW, c = i - r * PW;
             raw[r * RAWP + c] = img[(size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w)];
         }
+    }
     }
     __syncwarp();
     const uint8_t* rp = raw + shift;                            // rp[r * RAWP + c], c in [0, 43)
@@ -841,12 +863,11 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(OrbParams P, i
     // ---- horizontal 7-tap pass (8.8 fixed point), columns -18..18 of all 43 rows.
     //      Each lane produces 4 adjacent outputs from 3 aligned words of the row (10 source bytes).
     {
-        const int base4 = shift & ~3, sh = shift & 3;          // shift in 0..3 -> base4 == 0
-        (void)base4;
+        const int wofs = shift >> 2, sh = shift & 3;           // shift in 0..15 (TMA path) or 0..3 (word loader)
         for (int i = lane; i < PW * 10; i += 32) {             // 10 groups of 4 outputs cover 37 (+3 spare) columns
             const int r = i / 10, g4 = i - r * 10;
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + r * RAWP) + g4;
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = (g4 < 9) ? w[3] : 0u;     // 12 words per row
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + r * RAWP) + g4 + wofs;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];                   // g4 + wofs + 3 <= 15 < RAWP / 4
             // bytes b[j] = raw[r][4*g4 + sh + j], j = 0..9
             const uint32_t q0 = __funnelshift_r(w0, w1, 8 * sh), q1 = __funnelshift_r(w1, w2, 8 * sh),
                            q2 = __funnelshift_r(w2, w3, 8 * sh);
