@@ -388,6 +388,11 @@ def main():
         achieved = dom_bytes / (stages[dom] / 1e3) / 1e9
         pf_bytes = (SUM_P) * B
         pf_ms = stages["pyramid(7 launches)"] + stages["fast_cells"]
+        # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the ncu --set full capture of this very
+        # command shape (B=256), profiles/r1_full_B256_raw.csv; None for other shapes
+        NCU_TRAFFIC_B256 = {"fast_cells": 271869696 + 32466688, "orient_describe": 270863616 + 16201472,
+                            "octree": 70613504 + 52721408}
+        traffic = NCU_TRAFFIC_B256.get(dom) if B == 256 else None
         out = {
             "metric": "front-end frames/sec (752x480, 1000 feat, 8-lvl pyr)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
@@ -400,7 +405,8 @@ def main():
             "gpu_launches": int(args.steps * ((ORB["nlevels"] - 1) + 3 + 1)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                         "limiter": "issue slots, not bytes: ncu smsp__issue_active 78 % (fast_cells), 78 % (orient_describe); see DESIGN.md §4",
                          "kernel_ms_per_launch": stages[dom],
                          "pyramid_plus_fast": {"strict_bytes_per_step": pf_bytes, "ms_per_step": pf_ms,
                                                "achieved": pf_bytes / (pf_ms / 1e3) / 1e9,
