@@ -206,6 +206,11 @@ int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, in
 int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, float nnratio, int check_orientation,
                       float* ms);
 
+/* Two batches in flight on two streams (handle pairs A and B, inputs resident, pair lists prepared): steps alternate
+ * A, B, A, ...; CUDA-event timed from the start on A's stream until both streams have drained. */
+int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matcher* hB, int n_frames, int iters,
+                       float nnratio, int check_orientation, float* ms);
+
 /* ------------------------------------------------------------------ SparseImgAlign
  * replaces ygz::SparseImgAlign (include/SparseImageAlign.h:14-113, src/SparseImageAlign.cc) and its
  * Gauss-Newton driver (include/NLSSolver_impl.hpp:17-91). */

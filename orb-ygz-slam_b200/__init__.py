@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
     "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
-    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time",
+    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
 ]
 
@@ -141,6 +141,7 @@ def lib():
     sigs.setdefault('ygz_orb_wait', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_search_by_bow_batch_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, C.c_void_p, C.c_void_p]
     sigs.setdefault('ygz_debug_cos_sin', {})['argtypes'] = [C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+    sigs.setdefault('ygz_frontend_time2', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
     sigs.setdefault('ygz_frontend_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
     sigs.setdefault('ygz_sia_last_trace', {})['argtypes'] = [C.c_void_p, C.c_int, f32p, C.c_int, i32p]
     for name, sig in sigs.items():
@@ -501,6 +502,12 @@ class ORBmatcher:
                                               _ptr(f_idx, i32p), len(kf_idx), _ptr(nof, u32p), _ptr(out, i32p),
                                               _ptr(nm, i32p)), "ygz_search_by_bow_batch")
         return nm, out
+
+    def time_frontend2(self, extractor, other_matcher, other_extractor, n_frames, iters):
+        ms = C.c_float()
+        _check(self.L.ygz_frontend_time2(extractor.h, self.h, other_extractor.h, other_matcher.h, n_frames, iters,
+                                         self.nnratio, int(self.checkOri), C.byref(ms)), "ygz_frontend_time2")
+        return ms.value
 
     def time_frontend(self, extractor, n_frames, iters):
         ms = C.c_float()

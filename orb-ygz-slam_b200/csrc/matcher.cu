@@ -892,4 +892,39 @@ int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, flo
     return YGZ_OK;
 }
 
+
+// Same as ygz_frontend_time with TWO independent batches in flight on two streams (handle pairs A and B, both with
+// resident inputs and prepared pair lists): steps alternate A, B, A, ... so the latency-bound kernels of one batch
+// (octree, BoW, small pyramid levels) fill the issue slots the other batch's FAST / describe kernels leave idle.
+// Timed with CUDA events: start on A's stream (B waits on it), end after both streams have drained.
+int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matcher* hB, int n_frames, int iters,
+                       float nnratio, int check_ori, float* ms) {
+    YGZ_ARG_CHECK(orbA && hA && orbB && hB && ms && iters >= 1 && hA->last_pairs >= 1 && hB->last_pairs >= 1);
+    YGZ_CUDA_TRY(cudaSetDevice(hA->device));
+    cudaStream_t sA = (cudaStream_t)ygz_orb_stream(orbA), sB = (cudaStream_t)ygz_orb_stream(orbB);
+    BowBatchArgs A = hA->last_args, B = hB->last_args;
+    A.nnratio = B.nnratio = nnratio; A.check_ori = B.check_ori = check_ori;
+    YGZ_CUDA_TRY(cudaStreamSynchronize(hA->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(hB->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(sA));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(sB));
+    YGZ_CUDA_TRY(cudaEventRecord(hA->ev0, sA));
+    YGZ_CUDA_TRY(cudaStreamWaitEvent(sB, hA->ev0, 0));
+    for (int i = 0; i < iters; i++) {
+        ygz_orb* orb = (i & 1) ? orbB : orbA;
+        ygz_matcher* h = (i & 1) ? hB : hA;
+        cudaStream_t st = (i & 1) ? sB : sA;
+        int rc = ygz_orb_run(orb, n_frames);
+        if (rc) return rc;
+        k_bow_match_batch<<<h->last_pairs, BOW_THREADS, bow_smem_bytes((i & 1) ? B.cap : A.cap), st>>>((i & 1) ? B : A);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    YGZ_CUDA_TRY(cudaEventRecord(hB->ev1, sB));
+    YGZ_CUDA_TRY(cudaStreamWaitEvent(sA, hB->ev1, 0));
+    YGZ_CUDA_TRY(cudaEventRecord(hA->ev1, sA));
+    YGZ_CUDA_TRY(cudaEventSynchronize(hA->ev1));
+    YGZ_CUDA_TRY(cudaEventElapsedTime(ms, hA->ev0, hA->ev1));
+    return YGZ_OK;
+}
+
 }  // extern "C"

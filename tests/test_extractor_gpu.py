@@ -87,3 +87,31 @@ def test_extract_frame_existing_keys(gpu, oracle, synth):
     kps, desc = ex.extract_frame(img, existing)
     assert_kps_equal(kps, okps, "extract_frame")
     assert (desc == odesc).all()
+
+
+def test_async_two_handles_equals_sync(gpu, synth):
+    """ygz_orb_extract_async / ygz_orb_wait with two handles in flight returns what the blocking call returns."""
+    import ctypes as C
+    import numpy as np
+    w, h, B = 320, 240, 3
+    imgs = np.stack([synth.synth_frame(40 + i, w, h) for i in range(2 * B)])
+    exs = [gpu.ORBextractor(500, 1.2, 8, 20, 7, width=w, height=h, max_batch=B) for _ in range(2)]
+    ref = exs[0].extract_batch(imgs[:B]) + exs[0].extract_batch(imgs[B:])
+    cap = exs[0].cap
+    bufs = []
+    for k, ex in enumerate(exs):
+        kps = np.zeros((B, cap), gpu.KP_DTYPE)
+        desc = np.zeros((B, cap, 32), np.uint8)
+        cnt = np.zeros(B, np.int32)
+        part = np.ascontiguousarray(imgs[k * B:(k + 1) * B])
+        gpu._check(gpu.lib().ygz_orb_extract_async(ex.h, part.ctypes.data, B, w * h, w, kps.ctypes.data, desc.ctypes.data,
+                                                   cnt.ctypes.data, cap), "ygz_orb_extract_async")
+        bufs.append((kps, desc, cnt, part))
+    for ex in exs:
+        gpu._check(gpu.lib().ygz_orb_wait(ex.h), "ygz_orb_wait")
+    got = []
+    for kps, desc, cnt, _ in bufs:
+        got += [(kps[f, :cnt[f]], desc[f, :cnt[f]]) for f in range(B)]
+    for (k0, d0), (k1, d1) in zip(ref, got):
+        assert_kps_equal(k0, k1, "async")
+        assert (d0 == d1).all()
