@@ -42,8 +42,8 @@ typedef struct {
     int nfeatures;        /* ORBextractor ctor args, include/ORBextractor.h:59-60 */
     float scale_factor;
     int nlevels;
-    int ini_th_fast;
-    int min_th_fast;
+    int ini_th_fast;      /* 1..255: threshold of the first cv::FAST call per cell */
+    int min_th_fast;      /* 1..255: threshold of the second call, made only for cells the first left empty */
     int width, height;    /* frame geometry the handle is sized for */
     int max_batch;        /* frames per launch (1 for the per-frame drop-in path) */
     int device;           /* CUDA device ordinal */

@@ -128,7 +128,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
     YGZ_ARG_CHECK(cfg->nlevels >= 1 && cfg->nlevels <= MAX_LEVELS);
     YGZ_ARG_CHECK(cfg->width >= 64 && cfg->height >= 64 && cfg->width <= 4096 && cfg->height <= 4096);
     YGZ_ARG_CHECK(cfg->max_batch >= 1 && cfg->nfeatures >= 1 && cfg->scale_factor > 1.0f);
-    YGZ_ARG_CHECK(cfg->ini_th_fast >= cfg->min_th_fast && cfg->min_th_fast >= 0 && cfg->ini_th_fast <= 255);
+    // any order of the two thresholds is legal in the reference (FAST(iniTh), then FAST(minTh) for empty cells)
+    YGZ_ARG_CHECK(cfg->ini_th_fast >= 1 && cfg->ini_th_fast <= 255 && cfg->min_th_fast >= 1 && cfg->min_th_fast <= 255);
     if (ygz_device_count() <= cfg->device) { set_last_error("no such CUDA device"); return YGZ_ERR_NO_DEVICE; }
     YGZ_CUDA_TRY(cudaSetDevice(cfg->device));
     ygz_orb* h = new ygz_orb();

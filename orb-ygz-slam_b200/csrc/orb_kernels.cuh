@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
     uint8_t* tile = smem_raw + (size_t)warp * warp_smem;               // ch x TP
     uint8_t* sc = tile + round4(ch * TP);                              // (dh+2) x (dw+2) scores, zero border
     uint8_t* flag = sc + round4(sw2 * (dh + 2));                       // per item: score if NMS survivor else 0
-    uint16_t* items = reinterpret_cast<uint16_t*>(flag + round4(npx)); // pre-test survivors: x | y<<6 | polarity<<12
+    uint16_t* items = reinterpret_cast<uint16_t*>(flag + round4(npx)); // pre-test survivors: x | y<<6
 
     {   // ---- tile load (coalesced words) + score tile clear
         const int wpr = TP >> 2;
@@ -241,101 +241,106 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
     }
     __syncwarp();
 
-    const int tmin = P.min_th;
     // ring offsets in the tile (cv::FAST offsets16)
     const int o0 = 3 * TP, o1 = 3 * TP + 1, o2 = 2 * TP + 2, o3 = TP + 3, o4 = 3, o5 = -TP + 3, o6 = -2 * TP + 2,
               o7 = -3 * TP + 1, o8 = -3 * TP, o9 = -3 * TP - 1, o10 = -2 * TP - 2, o11 = -TP - 3, o12 = -3,
               o13 = TP - 3, o14 = 2 * TP - 2, o15 = 3 * TP - 1;
     const uint8_t* t0 = tile + 3 * TP + shift + 3;     // pixel (0,0) of the detection window
 
-    // ---- phase A: opposite-pair pre-test at minTh (necessary for 9 contiguous): with da = a-c, db = b-c of an
-    //      opposite pair, a brighter arc needs max(da,db) > t for every pair and a darker arc min(da,db) < -t.
-    //      Straight-line (no early exits: a warp almost always has a surviving lane), one detection row per step;
-    //      ordered compaction keeps raster order.
+    // The reference runs cv::FAST at iniTh and, only when that returns nothing, again at minTh.  The score of a pixel
+    // (largest threshold at which it is still a corner) does not depend on the call's threshold, and a pixel that is not
+    // a corner at t can never suppress one that is (its score is < t), so pass 0 below restricted to the iniTh
+    // pre-test survivors equals the iniTh call; pass 1 (rare: flat cells) equals the minTh call.
     int total = 0;
-    if (dw <= 32) {
-        // two detection rows per step, packed in the 16-bit halves of a register (VIMNMX.U16x2): lo = row y, hi = row y+1.
-        // D = r - c + 256 per half (always in [1, 511], so plain 32-bit adds never carry between the halves).
-        const int x = lane;
-        const unsigned thi = 256u + (unsigned)tmin, tlo = 256u - (unsigned)tmin;
-        for (int y = 0; y < dh; y += 2) {
-            int m0 = 0, m1 = 0;
-            if (x < dw) {
-                const uint8_t* p = t0 + y * TP + x;
-#define LD2(o) ((unsigned)p[(o)] | ((unsigned)p[(o) + TP] << 16))
-                const unsigned KB = 0x01000100u - LD2(0);
-                const unsigned D0 = LD2(o0) + KB, D8 = LD2(o8) + KB, D4 = LD2(o4) + KB, D12 = LD2(o12) + KB;
-                const unsigned D2 = LD2(o2) + KB, D10 = LD2(o10) + KB, D6 = LD2(o6) + KB, D14 = LD2(o14) + KB;
-#undef LD2
-                const unsigned bmin = __vminu2(__vminu2(__vmaxu2(D0, D8), __vmaxu2(D4, D12)), __vminu2(__vmaxu2(D2, D10), __vmaxu2(D6, D14)));
-                const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(D0, D8), __vminu2(D4, D12)), __vmaxu2(__vminu2(D2, D10), __vminu2(D6, D14)));
-                // polarity bits of the survivors: 1 = a darker arc is still possible, 2 = a brighter arc is
-                m0 = (int)((dmax & 0xFFFFu) < tlo) | ((int)((bmin & 0xFFFFu) > thi) << 1);
-                m1 = (y + 1 < dh) ? ((int)((dmax >> 16) < tlo) | ((int)((bmin >> 16) > thi) << 1)) : 0;
+    for (int pass = 0; pass < 2; pass++) {
+        const int tmin = pass ? P.min_th : P.ini_th;          // threshold of this cv::FAST call
+        // ---- phase A: opposite-pair pre-test at the call's threshold (necessary for 9 contiguous): with da = a-c, db = b-c of an
+        //      opposite pair, a brighter arc needs max(da,db) > t for every pair and a darker arc min(da,db) < -t.
+        //      Straight-line (no early exits: a warp almost always has a surviving lane), one detection row per step;
+        //      ordered compaction keeps raster order.
+        total = 0;
+        if (dw <= 32) {
+            // two detection rows per step, packed in the 16-bit halves of a register (VIMNMX.U16x2): lo = row y, hi = row y+1.
+            // D = r - c + 256 per half (always in [1, 511], so plain 32-bit adds never carry between the halves).
+            const int x = lane;
+            const unsigned thi = 256u + (unsigned)tmin, tlo = 256u - (unsigned)tmin;
+            for (int y = 0; y < dh; y += 2) {
+                bool pass0 = false, pass1 = false;
+                if (x < dw) {
+                    const uint8_t* p = t0 + y * TP + x;
+    #define LD2(o) ((unsigned)p[(o)] | ((unsigned)p[(o) + TP] << 16))
+                    const unsigned KB = 0x01000100u - LD2(0);
+                    const unsigned D0 = LD2(o0) + KB, D8 = LD2(o8) + KB, D4 = LD2(o4) + KB, D12 = LD2(o12) + KB;
+                    const unsigned D2 = LD2(o2) + KB, D10 = LD2(o10) + KB, D6 = LD2(o6) + KB, D14 = LD2(o14) + KB;
+    #undef LD2
+                    const unsigned bmin = __vminu2(__vminu2(__vmaxu2(D0, D8), __vmaxu2(D4, D12)), __vminu2(__vmaxu2(D2, D10), __vmaxu2(D6, D14)));
+                    const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(D0, D8), __vminu2(D4, D12)), __vmaxu2(__vminu2(D2, D10), __vminu2(D6, D14)));
+                    pass0 = ((bmin & 0xFFFFu) > thi) | ((dmax & 0xFFFFu) < tlo);
+                    pass1 = (y + 1 < dh) & (((bmin >> 16) > thi) | ((dmax >> 16) < tlo));
+                }
+                const unsigned bal0 = __ballot_sync(0xffffffffu, pass0);
+                const unsigned bal1 = __ballot_sync(0xffffffffu, pass1);
+                if (pass0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)(x | (y << 6));
+                total += __popc(bal0);
+                if (pass1) items[total + __popc(bal1 & lanemask_lt())] = (uint16_t)(x | ((y + 1) << 6));
+                total += __popc(bal1);
             }
-            const unsigned bal0 = __ballot_sync(0xffffffffu, m0 != 0);
-            const unsigned bal1 = __ballot_sync(0xffffffffu, m1 != 0);
-            if (m0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)(x | (y << 6) | (m0 << 12));
-            total += __popc(bal0);
-            if (m1) items[total + __popc(bal1 & lanemask_lt())] = (uint16_t)(x | ((y + 1) << 6) | (m1 << 12));
-            total += __popc(bal1);
-        }
-    } else {
-    for (int y = 0; y < dh; y++) {
-        for (int xb = 0; xb < dw; xb += 32) {
-            const int x = xb + lane;
-            bool pass = false;
-            int mm = 0;
-            if (x < dw) {
-                const uint8_t* p = t0 + y * TP + x;
-                const int c = p[0];
-                const int d0 = p[o0] - c, d8 = p[o8] - c, d4 = p[o4] - c, d12 = p[o12] - c;
-                const int d2 = p[o2] - c, d10 = p[o10] - c, d6 = p[o6] - c, d14 = p[o14] - c;
-                const int bmin = min(min(max(d0, d8), max(d4, d12)), min(max(d2, d10), max(d6, d14)));
-                const int dmax = max(max(min(d0, d8), min(d4, d12)), max(min(d2, d10), min(d6, d14)));
-                pass = (bmin > tmin) | (dmax + tmin < 0);
-                mm = (int)(dmax + tmin < 0) | ((int)(bmin > tmin) << 1);
+        } else {
+        for (int y = 0; y < dh; y++) {
+            for (int xb = 0; xb < dw; xb += 32) {
+                const int x = xb + lane;
+                bool pass = false;
+                if (x < dw) {
+                    const uint8_t* p = t0 + y * TP + x;
+                    const int c = p[0];
+                    const int d0 = p[o0] - c, d8 = p[o8] - c, d4 = p[o4] - c, d12 = p[o12] - c;
+                    const int d2 = p[o2] - c, d10 = p[o10] - c, d6 = p[o6] - c, d14 = p[o14] - c;
+                    const int bmin = min(min(max(d0, d8), max(d4, d12)), min(max(d2, d10), max(d6, d14)));
+                    const int dmax = max(max(min(d0, d8), min(d4, d12)), max(min(d2, d10), min(d6, d14)));
+                    pass = (bmin > tmin) | (dmax + tmin < 0);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) items[total + __popc(bal & lanemask_lt())] = (uint16_t)(x | (y << 6));
+                total += __popc(bal);
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (pass) items[total + __popc(bal & lanemask_lt())] = (uint16_t)(x | (y << 6) | (mm << 12));
-            total += __popc(bal);
         }
-    }
-    }
-    __syncwarp();
-
-    // ---- phase B: FAST-9 score of the survivors (both polarities packed in the 16-bit halves, fast9_best_packed).
-    //      Measured alternative (two single-polarity items per lane, one per half): 1.55 ms vs 1.45 ms — the extra packing
-    //      and the halved lane utilisation of the last iteration cost more than the shared min/max network saves.
-    for (int g = lane; g < total; g += 32) {
-        const int it = items[g];
-        const int x = it & 63, y = (it >> 6) & 63;
-        const uint8_t* p = t0 + y * TP + x;
-        const int r[16] = {p[o0], p[o1], p[o2], p[o3], p[o4], p[o5], p[o6], p[o7],
-                           p[o8], p[o9], p[o10], p[o11], p[o12], p[o13], p[o14], p[o15]};
-        const int best = fast9_best_packed(p[0], r);
-        if (best > tmin) sc[(y + 1) * sw2 + x + 1] = (uint8_t)(best - 1);   // corner at minTh; response = best-1
-    }
-    __syncwarp();
-
-    // ---- phase C: 3x3 non-max suppression inside the detection window (strict >, zeros outside)
-    int any_hi = 0;
-    for (int g = lane; g < total; g += 32) {
-        const int it = items[g];
-        const int x = it & 63, y = (it >> 6) & 63;
-        const uint8_t* q = sc + (y + 1) * sw2 + x + 1;
-        const int s = q[0];
-        int keep = 0;
-        if (s > 0 && s >= tmin) {
-            keep = (s > q[-1]) & (s > q[1]) & (s > q[-sw2 - 1]) & (s > q[-sw2]) & (s > q[-sw2 + 1]) &
-                   (s > q[sw2 - 1]) & (s > q[sw2]) & (s > q[sw2 + 1]);
         }
-        flag[g] = keep ? (uint8_t)s : 0;
-        any_hi |= keep && (s >= P.ini_th);
+        __syncwarp();
+
+        // ---- phase B: FAST-9 score of the survivors (both polarities packed in the 16-bit halves, fast9_best_packed).
+        //      Measured alternative (two single-polarity items per lane, one per half): 1.55 ms vs 1.45 ms — the extra packing
+        //      and the halved lane utilisation of the last iteration cost more than the shared min/max network saves.
+        for (int g = lane; g < total; g += 32) {
+            const int it = items[g];
+            const int x = it & 63, y = (it >> 6) & 63;
+            const uint8_t* p = t0 + y * TP + x;
+            const int r[16] = {p[o0], p[o1], p[o2], p[o3], p[o4], p[o5], p[o6], p[o7],
+                               p[o8], p[o9], p[o10], p[o11], p[o12], p[o13], p[o14], p[o15]};
+            const int best = fast9_best_packed(p[0], r);
+            if (best > tmin) sc[(y + 1) * sw2 + x + 1] = (uint8_t)(best - 1);   // corner at minTh; response = best-1
+        }
+        __syncwarp();
+
+        // ---- phase C: 3x3 non-max suppression inside the detection window (strict >, zeros outside)
+        int any_keep = 0;
+        for (int g = lane; g < total; g += 32) {
+            const int it = items[g];
+            const int x = it & 63, y = (it >> 6) & 63;
+            const uint8_t* q = sc + (y + 1) * sw2 + x + 1;
+            const int s = q[0];
+            int keep = 0;
+            if (s > 0 && s >= tmin) {
+                keep = (s > q[-1]) & (s > q[1]) & (s > q[-sw2 - 1]) & (s > q[-sw2]) & (s > q[-sw2 + 1]) &
+                       (s > q[sw2 - 1]) & (s > q[sw2]) & (s > q[sw2 + 1]);
+            }
+            flag[g] = keep ? (uint8_t)s : 0;
+            any_keep |= keep;
+        }
+        __syncwarp();
+        // vKeysCell.empty() after the iniTh call decides the fallback to minTh (src/ORBextractor.cc:765-770)
+        if (__any_sync(0xffffffffu, any_keep)) break;
+
     }
-    // vKeysCell.empty() after the iniTh call decides the fallback (src/ORBextractor.cc:767)
-    const int T = __any_sync(0xffffffffu, any_hi) ? P.ini_th : tmin;
-    __syncwarp();
 
     // ---- phase D: ordered emission (raster order inside the cell), coordinates relative to (16,16)
     uint32_t* out = pool + (size_t)frame * P.pool_size + cd.out_off;
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         const int g = g0 + lane;
         int s = 0, it = 0;
         if (g < total) { s = flag[g]; it = items[g]; }
-        const bool keep = s > 0 && s >= T;
+        const bool keep = s > 0;
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int pos = base + __popc(bal & lanemask_lt());

@@ -65,6 +65,25 @@ def test_flat_and_noise_images(gpu, oracle):
     assert len(res[0][0]) == 0
 
 
+@pytest.mark.parametrize("ini,mn", [(20, 7), (60, 7), (120, 3), (7, 20), (12, 12)])
+def test_threshold_fallback(gpu, oracle, synth, ini, mn):
+    """cv::FAST(iniTh) then, for empty cells only, cv::FAST(minTh) (src/ORBextractor.cc:765-770): high iniTh makes most
+    cells take the fallback, iniTh < minTh makes the fallback a no-op; low-contrast image exercises both."""
+    w, h = 320, 240
+    a = synth.synth_frame(17, w, h)
+    b = (a.astype(np.int32) * 40 // 255 + 100).astype(np.uint8)            # low contrast: few corners at iniTh
+    imgs = np.stack([a, b])
+    ex = gpu.ORBextractor(500, 1.2, 8, ini, mn, width=w, height=h, max_batch=2)
+    res = ex.extract_batch(imgs)
+    ox = oracle.Extractor(500, 1.2, 8, ini, mn)
+    for f in range(2):
+        okps, odesc = ox.extract(imgs[f])
+        for l in range(8):
+            assert_kps_equal(ex.candidates(f, l), ox.candidates(l), "candidates level %d" % l)
+        assert_kps_equal(res[f][0], okps, "image %d" % f)
+        assert (res[f][1] == odesc).all()
+
+
 def test_border_pyramid(gpu, oracle, synth):
     w, h = 320, 240
     img = synth.synth_frame(11, w, h)
