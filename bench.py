@@ -370,7 +370,7 @@ def main():
     st = ex.time(B, it)
     bow_ms = mt.time_bow_batch(ex, B, it) / it
     stages = {"pyramid(7 launches)": st["pyramid"] / it, "fast_cells": st["fast_cells"] / it, "octree": st["octree"] / it,
-              "orient_describe": st["describe"] / it, "bow_match": bow_ms}
+              "blur_levels": st["blur"] / it, "orient_describe": st["describe"] / it, "bow_match": bow_ms}
 
     # ---- max over ranks; the ONE collective: all-gather of throughput counters (orb-ygz-slam_b200/shard.py)
     import importlib
@@ -387,10 +387,11 @@ def main():
         e2e_v = total_frames / t_e
         peak, peak_src = measured_peak_gbs()
         dom = max(stages, key=stages.get)
-        alg = {"pyramid(7 launches)": PYR_CHAIN, "fast_cells": SUM_P, "octree": 0, "orient_describe": 0, "bow_match": 0}
-        # algorithmic bytes of gather-type kernels: keypoints * (43x43 raw patch + 60 B out) ; BoW: descriptors of both frames
+        alg = {"pyramid(7 launches)": PYR_CHAIN, "fast_cells": SUM_P, "octree": 0, "blur_levels": 2 * SUM_P,
+               "orient_describe": 0, "bow_match": 0}
+        # algorithmic bytes of gather-type kernels: keypoints * (31x31 raw patch + 512 blurred samples + 60 B out) ; BoW: descriptors of both frames
         kp_per_frame = n_kp / B
-        alg["orient_describe"] = int(kp_per_frame * (43 * 43 + 28 + 32))
+        alg["orient_describe"] = int(kp_per_frame * (31 * 31 + 512 + 28 + 32))
         alg["octree"] = int(4 * 16139 / 16)     # ~4 B per FAST candidate (read once); informative only
         alg["bow_match"] = int(2 * kp_per_frame * (32 + 28) + 4 * cap)
         dom_bytes = alg[dom] * B
@@ -412,7 +413,7 @@ def main():
                     "d2h_bytes_per_step": int(h_kps.numel() * 4 + h_desc.numel() + h_cnt.numel() * 4 + h_match.numel() * 4 + h_nm.numel() * 4),
                     "ms_per_step": t_e / args.steps * 1e3,
                     "pipeline": "2 batches in flight (two handle pairs, ygz_orb_extract_async + ygz_search_by_bow_batch_async + ygz_orb_wait)"},
-            "gpu_launches": int(args.steps * ((ORB["nlevels"] - 1) + 3 + 1)),
+            "gpu_launches": int(args.steps * ((ORB["nlevels"] - 1) + 4 + 1)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,

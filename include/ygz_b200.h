@@ -96,7 +96,7 @@ int ygz_orb_sync(ygz_orb* h);
  * row-major, raster inside a cell), coordinates relative to (16,16) (src/ORBextractor.cc:773-777). */
 int ygz_orb_get_candidates(ygz_orb* h, int frame, int level, ygz_keypoint* out, int cap);
 /* device-timed repeats of ygz_orb_run on the handle's stream (CUDA events): total ms and per-stage ms
- * stage_ms[5] = {pyramid, fast_cells, octree, orient+describe, total}; launches = kernels per run */
+ * stage_ms[6] = {pyramid, fast_cells, octree, blur, orient+describe, total}; launches = kernels per run */
 int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches);
 /* device pointers for zero-copy chaining into the matcher / aligner of the same process */
 int ygz_orb_device_outputs(ygz_orb* h, void** d_kps, void** d_desc, void** d_counts, int* cap);

@@ -306,11 +306,11 @@ class ORBextractor:
         _check(self.L.ygz_orb_download(self.h, n, kps_ptr, desc_ptr, counts_ptr, cap), "ygz_orb_download")
 
     def time(self, n, iters):
-        ms = np.zeros(5, np.float32)
+        ms = np.zeros(6, np.float32)
         launches = C.c_int()
         _check(self.L.ygz_orb_time(self.h, n, iters, _ptr(ms, f32p), C.byref(launches)), "ygz_orb_time")
-        return dict(pyramid=float(ms[0]), fast_cells=float(ms[1]), octree=float(ms[2]), describe=float(ms[3]),
-                    total=float(ms[4]), launches=launches.value)
+        return dict(pyramid=float(ms[0]), fast_cells=float(ms[1]), octree=float(ms[2]), blur=float(ms[3]),
+                    describe=float(ms[4]), total=float(ms[5]), launches=launches.value)
 
     def counters(self, reset=False):
         c = Counters()

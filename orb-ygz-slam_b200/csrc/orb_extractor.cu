@@ -22,6 +22,7 @@ struct LevelHost {
     int w, h, pitch;
     size_t frame_stride;
     uint8_t* d_base = nullptr;
+    uint8_t* d_blur = nullptr;     // GaussianBlur(level), written by k_blur_levels
     ResizeTabX* d_tx = nullptr;
     ResizeTabY* d_ty = nullptr;
 };
@@ -53,9 +54,11 @@ struct ygz_orb {
     int* d_counts = nullptr;
     ExistingKey* d_existing = nullptr;
     int existing_cap = 0;
-    char4* d_pattern = nullptr;
+    float4* d_pattern = nullptr;
     TmaMaps tma;
-    int use_tma = 0;
+    PatchMaps patch;
+    BlurTile* d_blur_tiles = nullptr;
+    int n_blur_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0;
     int fast_warp_smem = 0;
     int oct_node_smem = 0, oct_key_cache = 0;
@@ -94,7 +97,8 @@ static void build_resize_tables(int ssize, int dsize, std::vector<ResizeTabX>* t
 static int orb_free(ygz_orb* h) {
     if (!h) return YGZ_OK;
     cudaSetDevice(h->device);
-    for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_tx); cudaFree(L.d_ty); }
+    for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_blur); cudaFree(L.d_tx); cudaFree(L.d_ty); }
+    cudaFree(h->d_blur_tiles);
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing); cudaFree(h->d_pattern);
@@ -172,6 +176,11 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
             ++v0;
         }
         for (int i = 0; i < 16; i++) h->P.umax[i] = umax[i];
+        for (int u = 0; u < 16; u++) {           // rows covered by column u (umax is non-increasing in v)
+            int vl = -1;
+            for (int vv = 0; vv <= HALF_PATCH; vv++) if (u <= umax[vv]) vl = vv;
+            h->P.vlim[u] = vl;
+        }
     }
 
     // ---- level geometry (:1131-1132), FAST cells (:739-762), octree roots (:537-551)
@@ -280,6 +289,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         LevelHost& L = h->lv[l];
         TRY_OR_FREE(cudaMalloc(&L.d_base, L.frame_stride * B + 64));
         h->P.lv[l].base = L.d_base;
+        TRY_OR_FREE(cudaMalloc(&L.d_blur, L.frame_stride * B + 64));
+        h->P.lv[l].blur = L.d_blur;
         if (l > 0) {
             std::vector<ResizeTabX> tx;
             std::vector<ResizeTabY> ty;
@@ -308,20 +319,36 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
     TRY_OR_FREE(cudaMalloc(&h->d_counts, (size_t)B * 4));
     TRY_OR_FREE(cudaMemset(h->d_counts, 0, (size_t)B * 4));
     TRY_OR_FREE(cudaMemset(h->d_nsel, 0, (size_t)nl * B * 4));
-    // TMA descriptors of the pyramid levels (box 48 x 43 for the descriptor patch); a failed encode only disables the
-    // TMA path (the aligned-word loader is kept), YGZ_NO_TMA=1 forces that for A/B measurements
-    h->use_tma = getenv("YGZ_NO_TMA") ? 0 : 1;
+    // TMA descriptors of the raw pyramid levels for k_blur_levels (box 160 x 38 x 1).  A level narrower / lower than
+    // the box, or a failed encode, falls back to the manual loader for that level; YGZ_NO_TMA=1 forces that (A/B runs).
     std::memset(&h->tma, 0, sizeof(h->tma));
-    for (int l = 0; l < nl && h->use_tma; l++) {
-        const LevelHost& L = h->lv[l];
-        if (L.w < RAWP || L.h < PW ||
-            make_tensor_map_u8_3d(&h->tma.patch[l], L.d_base, L.w, L.h, B, L.pitch, L.frame_stride, RAWP, PW) != 0)
-            h->use_tma = 0;
+    std::memset(&h->patch, 0, sizeof(h->patch));
+    {
+        std::vector<BlurTile> tiles;
+        for (int l = 0; l < nl; l++) {
+            const LevelHost& L = h->lv[l];
+            if (!getenv("YGZ_NO_TMA") && L.w >= BLUR_BOXW && L.h >= BLUR_BOXH &&
+                make_tensor_map_u8_3d(&h->tma.level[l], L.d_base, L.w, L.h, B, L.pitch, L.frame_stride, BLUR_BOXW, BLUR_BOXH) == 0)
+                h->tma.ok |= 1u << l;
+            if (!getenv("YGZ_NO_TMA") && L.w >= PBOX && L.h >= PW &&
+                make_tensor_map_u8_3d(&h->patch.blur[l], L.d_blur, L.w, L.h, B, L.pitch, L.frame_stride, PBOX, PW) == 0 &&
+                make_tensor_map_u8_3d(&h->patch.raw[l], L.d_base, L.w, L.h, B, L.pitch, L.frame_stride, PBOX, ICW) == 0)
+                h->patch.ok |= 1u << l;
+            for (int ty = 0; ty < ceil_div(L.h, BLUR_TH); ty++)
+                for (int tx = 0; tx < ceil_div(L.w, BLUR_TW); tx++) tiles.push_back(BlurTile{(short)l, (short)tx, (short)ty, 0});
+        }
+        h->n_blur_tiles = (int)tiles.size();
+        TRY_OR_FREE(cudaMalloc(&h->d_blur_tiles, tiles.size() * sizeof(BlurTile)));
+        TRY_OR_FREE(cudaMemcpy(h->d_blur_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
     }
-    TRY_OR_FREE(cudaMalloc(&h->d_pattern, sizeof(h_pattern)));
-    TRY_OR_FREE(cudaMemcpy(h->d_pattern, h_pattern, sizeof(h_pattern), cudaMemcpyHostToDevice));
+    {
+        std::vector<float> fp(256 * 4);
+        for (int t = 0; t < 256; t++)            // test t = 8 * byte + j  ->  slot j * 32 + byte
+            for (int c = 0; c < 4; c++) fp[((t & 7) * 32 + (t >> 3)) * 4 + c] = (float)h_pattern[t * 4 + c];
+        TRY_OR_FREE(cudaMalloc(&h->d_pattern, fp.size() * sizeof(float)));
+        TRY_OR_FREE(cudaMemcpy(h->d_pattern, fp.data(), fp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
-    TRY_OR_FREE(cudaFuncSetAttribute(k_orient_describe, cudaFuncAttributeMaxDynamicSharedMemorySize, DESC_WARPS * DESC_WARP_SMEM));
     TRY_OR_FREE(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
     TRY_OR_FREE(cudaDeviceSynchronize());
 #undef TRY_OR_FREE
@@ -403,13 +430,20 @@ static int launch_octree(ygz_orb* h, int n) {
     return YGZ_OK;
 }
 
+static int launch_blur(ygz_orb* h, int n) {
+    dim3 grid(h->n_blur_tiles, n);
+    k_blur_levels<<<grid, BLUR_THREADS, 0, h->stream>>>(h->P, h->tma, h->d_blur_tiles);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    return YGZ_OK;
+}
+
 static int launch_describe(ygz_orb* h, int n, int n_existing) {
     dim3 grid(ceil_div(h->P.sel_total, DESC_WARPS), n);
-    k_orient_describe<<<grid, DESC_THREADS, DESC_WARPS * DESC_WARP_SMEM, h->stream>>>(h->P, h->tma, h->use_tma, 0, n_existing, h->P.sel_total, h->d_pattern, h->d_sel, h->d_nsel, nullptr,
+    k_orient_describe<<<grid, DESC_THREADS, 0, h->stream>>>(h->P, h->patch, 0, n_existing, h->P.sel_total, h->d_pattern, h->d_sel, h->d_nsel, nullptr,
                                                            h->d_kps, h->d_desc, h->d_counts);
     if (n_existing > 0) {
         dim3 g2(ceil_div(n_existing, DESC_WARPS), n);
-        k_orient_describe<<<g2, DESC_THREADS, DESC_WARPS * DESC_WARP_SMEM, h->stream>>>(h->P, h->tma, h->use_tma, 1, n_existing, n_existing, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing,
+        k_orient_describe<<<g2, DESC_THREADS, 0, h->stream>>>(h->P, h->patch, 1, n_existing, n_existing, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing,
                                                              h->d_kps, h->d_desc, h->d_counts);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -423,8 +457,9 @@ int ygz_orb_run(ygz_orb* h, int n) {
     if ((rc = launch_pyramid(h, n))) return rc;
     if ((rc = launch_detect(h, n))) return rc;
     if ((rc = launch_octree(h, n))) return rc;
+    if ((rc = launch_blur(h, n))) return rc;
     if ((rc = launch_describe(h, n, 0))) return rc;
-    h->launches_per_run = (h->cfg.nlevels - 1) + 3;
+    h->launches_per_run = (h->cfg.nlevels - 1) + 4;
     h->ctr.kernel_launches += h->launches_per_run;
     h->ctr.frames += n;
     h->last_n = n;
@@ -545,8 +580,9 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
     if ((rc = launch_pyramid(h, 1))) return rc;
     if ((rc = launch_detect(h, 1))) return rc;
     if ((rc = launch_octree(h, 1))) return rc;
+    if ((rc = launch_blur(h, 1))) return rc;
     if ((rc = launch_describe(h, 1, n_existing))) return rc;
-    h->ctr.kernel_launches += (h->cfg.nlevels - 1) + 3 + (n_existing > 0);
+    h->ctr.kernel_launches += (h->cfg.nlevels - 1) + 4 + (n_existing > 0);
     h->ctr.frames += 1;
     YGZ_CUDA_TRY(cudaMemcpyAsync(count, h->d_counts, 4, cudaMemcpyDeviceToHost, h->stream));
     YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -610,7 +646,7 @@ int ygz_orb_get_candidates(ygz_orb* h, int frame, int level, ygz_keypoint* out, 
 int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches) {
     YGZ_ARG_CHECK(h && n >= 1 && n <= h->cfg.max_batch && iters >= 1 && stage_ms);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
-    float acc[5] = {0, 0, 0, 0, 0};
+    float acc[6] = {0, 0, 0, 0, 0, 0};
     int rc;
     for (int it = 0; it < iters; it++) {
         YGZ_CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
@@ -620,21 +656,23 @@ int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches) {
         YGZ_CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
         if ((rc = launch_octree(h, n))) return rc;
         YGZ_CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-        if ((rc = launch_describe(h, n, 0))) return rc;
+        if ((rc = launch_blur(h, n))) return rc;
         YGZ_CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-        YGZ_CUDA_TRY(cudaEventSynchronize(h->ev[4]));
-        for (int s = 0; s < 4; s++) {
+        if ((rc = launch_describe(h, n, 0))) return rc;
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+        YGZ_CUDA_TRY(cudaEventSynchronize(h->ev[5]));
+        for (int s = 0; s < 5; s++) {
             float ms = 0;
             YGZ_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[s], h->ev[s + 1]));
             acc[s] += ms;
         }
         float ms = 0;
-        YGZ_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[4]));
-        acc[4] += ms;
+        YGZ_CUDA_TRY(cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]));
+        acc[5] += ms;
     }
-    for (int s = 0; s < 5; s++) stage_ms[s] = acc[s];
-    if (launches) *launches = ((h->cfg.nlevels - 1) + 3) * iters;
-    h->ctr.kernel_launches += (uint64_t)((h->cfg.nlevels - 1) + 3) * iters;
+    for (int s = 0; s < 6; s++) stage_ms[s] = acc[s];
+    if (launches) *launches = ((h->cfg.nlevels - 1) + 4) * iters;
+    h->ctr.kernel_launches += (uint64_t)((h->cfg.nlevels - 1) + 4) * iters;
     h->ctr.frames += (uint64_t)n * iters;
     return YGZ_OK;
 }

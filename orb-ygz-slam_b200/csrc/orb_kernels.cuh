@@ -19,6 +19,7 @@ struct ResizeTabY { short y0, y1, b0, b1; };           // clipped source rows / 
 
 struct LevelDev {
     uint8_t* base;          // [batch][h][pitch]
+    uint8_t* blur;          // GaussianBlur(level), same geometry (written by k_blur_levels)
     size_t frame_stride;
     int w, h, pitch;
     float scale;            // mvScaleFactor[l]
@@ -57,6 +58,7 @@ struct OrbParams {
     int sel_total;         // selected-key capacity per frame (sum of node_cap)
     int out_cap;           // keypoints per frame capacity of the output arrays
     int umax[16];
+    int vlim[16];          // vlim[|u|] = largest |v| with |u| <= umax[|v|] (umax is non-increasing: rows of a column are contiguous)
     LevelDev lv[MAX_LEVELS];
 };
 
@@ -684,25 +686,160 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4  orientation + rBRIEF for one keypoint per CTA, with the 7x7 sigma-2 Gaussian evaluated on the fly
-//     from the RAW level (no blurred pyramid in HBM):
+// K4  GaussianBlur 7x7 sigma 2 of every pyramid level (src/ORBextractor.cc:1010,1083): OpenCV's 8-bit path is
+//     8.8 fixed point, separable, weights [18,34,48,56,48,34,18]/256 per pass, BORDER_REFLECT_101 on the cloned
+//     level, 16-bit intermediate, final (v + 2^15) >> 16.
+//     One CTA per 128 x 32 output tile of one level of one frame.  The raw (128+32) x (32+6) box comes in with ONE
+//     TMA bulk tensor copy (cp.async.bulk.tensor.3d; the box starts 16 columns left of the tile so its global address
+//     stays 16-byte aligned; out-of-image elements are zero-filled by the TMA unit and then overwritten by the
+//     REFLECT_101 fix-up, whose sources are always inside the box).  Horizontal pass: 2 x IDP.4A per output
+//     (bytes x weight bytes), stored as VERTICAL u16 pairs so that the vertical pass is 4 x IDP.2A per output
+//     with the rounding constant as the accumulator seed; no unpacking, no 32-bit multiplies.
+// ------------------------------------------------------------------------------------------------
+constexpr int BLUR_TW = 128, BLUR_TH = 32;
+constexpr int BLUR_THREADS = 256;
+constexpr int BLUR_XPAD = 16;                          // left halo in the box (3 needed, 16 keeps the TMA start aligned)
+constexpr int BLUR_BOXW = BLUR_TW + 2 * BLUR_XPAD;     // 160
+constexpr int BLUR_BOXH = BLUR_TH + 6;                 // 38
+constexpr int BLUR_NPAIR = BLUR_BOXH / 2;              // 19 vertical pairs of H rows
+
+struct BlurTile { short level, tx, ty, pad; };
+struct TmaMaps {                       // per level: u8 [frames][h][pitch], box BLUR_BOXW x BLUR_BOXH x 1
+    CUtensorMap level[MAX_LEVELS];
+    unsigned ok;                       // bit l: level l is loaded by TMA (else: manual loader)
+};
+
+__global__ void __launch_bounds__(BLUR_THREADS) k_blur_levels(const __grid_constant__ OrbParams P,
+                                                              const __grid_constant__ TmaMaps maps,
+                                                              const BlurTile* __restrict__ tiles) {
+    __shared__ __align__(128) uint8_t raw[BLUR_BOXH * BLUR_BOXW];          // 6080 B
+    __shared__ __align__(16) uint32_t Hp[BLUR_NPAIR * BLUR_TW];            // 9728 B: H[2p][c] | H[2p+1][c] << 16
+    __shared__ __align__(8) unsigned long long bar;
+    const BlurTile t = tiles[blockIdx.x];
+    const int frame = blockIdx.y;
+    const LevelDev& L = P.lv[t.level];
+    const int x0 = t.tx * BLUR_TW, y0 = t.ty * BLUR_TH;
+    const int gx0 = x0 - BLUR_XPAD, gy0 = y0 - 3;          // image coordinates of raw[0][0]
+    const int tid = threadIdx.x;
+    // columns of the box the passes read: 13 .. 146 (x0-3 .. x0+130)
+    if ((maps.ok >> t.level) & 1u) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, BLUR_BOXH * BLUR_BOXW);
+            tma_load_3d(raw, &maps.level[t.level], gx0, gy0, frame, &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+        const bool edge = x0 == 0 || x0 + BLUR_TW + 3 > L.w || y0 == 0 || y0 + BLUR_TH + 3 > L.h;   // CTA-uniform
+        if (edge) {
+            // REFLECT_101: the three columns left / right of the image first, then the three rows above / below
+            {
+                const int r = tid >> 2, k = tid & 3;                          // 64 rows x 4, k < 3 used
+                if (r < BLUR_BOXH && k < 3) {
+                    uint8_t* row = raw + r * BLUR_BOXW;
+                    if (x0 == 0) row[BLUR_XPAD - 1 - k] = row[BLUR_XPAD + 1 + k];          // x = -1-k  <-  x = 1+k
+                    const int c = L.w + k - gx0;                                           // x = w+k  <-  x = w-2-k
+                    if (c <= 146) row[c] = row[L.w - 2 - k - gx0];
+                }
+            }
+            __syncthreads();
+            if (tid < 136) {
+                uint8_t* col = raw + 12 + tid;
+                if (y0 == 0) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) col[(2 - k) * BLUR_BOXW] = col[(4 + k) * BLUR_BOXW];   // y = -1-k <- y = 1+k
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int r = L.h + k - gy0;                                                      // y = h+k <- y = h-2-k
+                    if (r < BLUR_BOXH) col[r * BLUR_BOXW] = col[(L.h - 2 - k - gy0) * BLUR_BOXW];
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        const uint8_t* img = L.base + (size_t)frame * L.frame_stride;
+        for (int i = tid; i < BLUR_BOXH * 136; i += BLUR_THREADS) {
+            const int r = i / 136, c = 12 + (i - r * 136);
+            const int x = min(max(gx0 + c, -3), L.w + 2), y = min(max(gy0 + r, -3), L.h + 2);
+            raw[r * BLUR_BOXW + c] = img[(size_t)reflect101(y, L.h) * L.pitch + reflect101(x, L.w)];
+        }
+        __syncthreads();
+    }
+    // ---- horizontal pass: item = (row pair p, 4-column group g); b[k] = raw column 4g+13+k
+    for (int i = tid; i < BLUR_NPAIR * (BLUR_TW / 4); i += BLUR_THREADS) {
+        const int p = i >> 5, g = i & 31;
+        unsigned h[2][4];
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + (2 * p + rr) * BLUR_BOXW) + g + 3;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t A = j == 3 ? w1 : __funnelshift_r(w0, w1, 8 * (j + 1));     // b[j .. j+3]
+                const uint32_t Bq = j == 3 ? w2 : __funnelshift_r(w1, w2, 8 * (j + 1));    // b[j+4 .. j+7]
+                h[rr][j] = __dp4a(Bq, 0x00122230u, __dp4a(A, 0x38302212u, 0u));            // 18,34,48,56 | 48,34,18,0
+            }
+        }
+        uint4 o;
+        o.x = h[0][0] | (h[1][0] << 16); o.y = h[0][1] | (h[1][1] << 16);
+        o.z = h[0][2] | (h[1][2] << 16); o.w = h[0][3] | (h[1][3] << 16);
+        *reinterpret_cast<uint4*>(&Hp[p * BLUR_TW + 4 * g]) = o;
+    }
+    __syncthreads();
+    // ---- vertical pass: warp w -> output rows 4w..4w+3, lane g -> columns 4g..4g+3.  Output row o uses H rows
+    //      o..o+6 = pairs (o/2 .. o/2+3) with weights (18,34)(48,56)(48,34)(18,0) for even o, (0,18)(34,48)(56,48)(34,18) for odd.
+    {
+        const int w = tid >> 5, g = tid & 31;
+        if (x0 + 4 * g >= L.pitch) return;
+        const uint32_t* hp = Hp + (2 * w) * BLUR_TW + 4 * g;
+        uint4 q[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) q[k] = *reinterpret_cast<const uint4*>(hp + k * BLUR_TW);
+        uint8_t* dst = L.blur + (size_t)frame * L.frame_stride + (size_t)(y0 + 4 * w) * L.pitch + x0 + 4 * g;
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            if (y0 + 4 * w + o >= L.h) break;
+            const uint4 &p0 = q[o >> 1], &p1 = q[(o >> 1) + 1], &p2 = q[(o >> 1) + 2], &p3 = q[(o >> 1) + 3];
+            const unsigned c0 = (o & 1) ? 0x1200u : 0x2212u, c1 = (o & 1) ? 0x3022u : 0x3830u,
+                           c2 = (o & 1) ? 0x3038u : 0x2230u, c3 = (o & 1) ? 0x1222u : 0x0012u;
+            const unsigned a0 = __dp2a_lo(p3.x, c3, __dp2a_lo(p2.x, c2, __dp2a_lo(p1.x, c1, __dp2a_lo(p0.x, c0, 1u << 15))));
+            const unsigned a1 = __dp2a_lo(p3.y, c3, __dp2a_lo(p2.y, c2, __dp2a_lo(p1.y, c1, __dp2a_lo(p0.y, c0, 1u << 15))));
+            const unsigned a2 = __dp2a_lo(p3.z, c3, __dp2a_lo(p2.z, c2, __dp2a_lo(p1.z, c1, __dp2a_lo(p0.z, c0, 1u << 15))));
+            const unsigned a3 = __dp2a_lo(p3.w, c3, __dp2a_lo(p2.w, c2, __dp2a_lo(p1.w, c1, __dp2a_lo(p0.w, c0, 1u << 15))));
+            // byte 2 of each accumulator = (acc + 2^15) >> 16  (acc < 2^24)
+            const unsigned lo = __byte_perm(a0, a1, 0x0062), hi = __byte_perm(a2, a3, 0x0062);
+            *reinterpret_cast<uint32_t*>(dst + (size_t)o * L.pitch) = __byte_perm(lo, hi, 0x5410);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  orientation + rBRIEF, one warp per keypoint:
 //       IC_Angle              src/ORBextractor.cc:77-101  (raw level, int moments, cv::fastAtan2)
-//       GaussianBlur 7x7 s2   src/ORBextractor.cc:1010,1083 (8.8 fixed point [18,34,48,56,48,34,18], REFLECT_101)
-//       computeOrbDescriptor  src/ORBextractor.cc:105-149 (float, no fma, round-half-even)
+//       computeOrbDescriptor  src/ORBextractor.cc:105-149 (blurred level; float, no fma, round-half-even)
+//     Two TMA bulk tensor copies per keypoint on one mbarrier: the 31-row raw box (orientation) and the 37-row blurred
+//     box (512 rotated samples), each 64 columns wide with the start rounded down to 16 bytes.  Everything after the
+//     wait is shared-memory reads: 32 random global bytes per instruction cost ~20 L1 wavefronts, 32 random shared
+//     bytes ~3.  Measured (C1, B = 256): global-memory IC loop 0.37 ms, this version 0.22 ms.
 // ------------------------------------------------------------------------------------------------
 constexpr int DESC_WARPS = 8;           // one warp per keypoint, DESC_WARPS keypoints per CTA, no block barrier
 constexpr int DESC_THREADS = DESC_WARPS * 32;
-constexpr int PR = 21;                 // patch radius: 18 (pattern reach) + 3 (blur)
-constexpr int PW = 2 * PR + 1;         // 43
-constexpr int RAWP = 64;               // raw pitch = TMA box width: the box must start 16-byte aligned, 43 + 15 columns round up to 64
-constexpr int HW = 37;                 // horizontally blurred columns (-18..18)
-constexpr int HP = 38;                 // pitch of H
-constexpr int DESC_WARP_SMEM = 6144;   // 43*64 raw + 43*38*2 H = 6020 B, rounded to 128 B (TMA destination alignment)
+constexpr int PR = 18;                  // reach of the rotated pattern (|coordinate| <= 13 => <= 18.4 after rotation)
+constexpr int PW = 2 * PR + 1;          // 37 rows / columns
+constexpr int PBOX = 64;                // TMA box width: 37 columns + up to 15 of alignment slack
+constexpr int ICW = 2 * HALF_PATCH + 1; // 31 rows / columns of the orientation patch
+constexpr int DESC_RAW_OFF = 2432;      // blurred box 37 * 64 = 2368 B, rounded to 128 B (TMA destination alignment)
+constexpr int DESC_WARP_SMEM = 4480;    // + raw box 31 * 64 = 1984 B, rounded to 128 B
+struct PatchMaps {                      // per level: blurred u8 [frames][h][pitch], box PBOX x PW x 1; raw, box PBOX x ICW x 1
+    CUtensorMap blur[MAX_LEVELS];
+    CUtensorMap raw[MAX_LEVELS];
+    unsigned ok;
+};
 
-struct TmaMaps { CUtensorMap patch[MAX_LEVELS]; };   // per level: u8 [frames][h][pitch], box 64 x 43 x 1 (rBRIEF / IC patch)
-
-// bit_pattern_31_ (data, src/ORBextractor.cc:152-410) lives in GLOBAL memory as 256 x char4: every lane reads its own
-// eight tests, and lane-divergent addresses serialise on the constant cache.
+// bit_pattern_31_ (data, src/ORBextractor.cc:152-410) lives in GLOBAL memory as float4 (x0,y0,x1,y1) [test j of a byte][lane = byte]:
+// every lane reads its own eight tests (lane-divergent addresses would serialise on the constant cache), and the
+// transposed order makes each of the eight loads one contiguous 512-byte warp access.
 
 __device__ __forceinline__ float fast_atan2_dev(float y, float x) {
     // cv::fastAtan2 (degrees), evaluated without fma contraction
@@ -734,42 +871,46 @@ __device__ void ref_cos_sin(float angle_rad, float* c, float* s);
 struct ExistingKey { float x, y, angle; int octave; };   // pt * mvInvScaleFactor[octave], :1094-1095
 
 // mode 0: keys selected by k_octree (angle computed);  mode 1: pre-existing keys (angle kept, :1088-1099)
-// One WARP per keypoint: raw 43x43 patch -> shared (aligned word loads), IC moments by warp shuffle, horizontal
-// blur pass into H, then every lane evaluates 8 binary tests = one descriptor byte.
-__global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(const __grid_constant__ OrbParams P,
-                                                                  const __grid_constant__ TmaMaps maps, int use_tma,
+// lane = patch column for the IC moments (31 coalesced bytes per row), then lane j = descriptor byte j: 16 gathers
+// from the blurred level, all independent, so the memory system sees 512 loads in flight per warp.
+__global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __grid_constant__ OrbParams P,
+                                                                  const __grid_constant__ PatchMaps maps,
                                                                   int mode, int n_existing, int n_items,
-                                                                  const char4* __restrict__ pattern,
+                                                                  const float4* __restrict__ pattern,
                                                                   const uint32_t* __restrict__ sel_all,
                                                                   const int* __restrict__ nsel_all,
                                                                   const ExistingKey* __restrict__ existing,
                                                                   ygz_keypoint* __restrict__ kps_out,
                                                                   uint8_t* __restrict__ desc_out,
                                                                   int* __restrict__ counts_out) {
-    extern __shared__ __align__(128) uint8_t smem[];            // DESC_WARPS * DESC_WARP_SMEM (dynamic: 48 KB)
+    __shared__ __align__(128) uint8_t smem[DESC_WARPS * DESC_WARP_SMEM];
     __shared__ __align__(8) unsigned long long tma_bar[DESC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * DESC_WARPS + warp;          // (level, slot) index or existing-key index
     const int frame = blockIdx.y;
     if (item >= n_items) return;
-    uint8_t* raw = smem + warp * DESC_WARP_SMEM;               // PW x RAWP
-    uint16_t* H = reinterpret_cast<uint16_t*>(raw + PW * RAWP);
+    uint8_t* G = smem + warp * DESC_WARP_SMEM;                 // blurred patch, PW rows x PBOX
     int level, cx, cy, out_idx, score = 0;
     float angle = 0.f;
     if (mode == 0) {
         const int s = item;
-        level = 0;
-        while (level + 1 < P.nlevels && s >= P.lv[level + 1].sel_off) level++;
-        const int slot = s - P.lv[level].sel_off;
+        // lane l holds level l's slot offset and selected-key count; the level of slot s and the number of keys of
+        // the levels before it come from one ballot and one shuffle reduction
         const int* nsel = nsel_all + (size_t)frame * P.nlevels;
-        int before = n_existing;
-        for (int l = 0; l < level; l++) before += nsel[l];
-        if (s == 0 && lane == 0) {
-            int tot = n_existing;
-            for (int l = 0; l < P.nlevels; l++) tot += nsel[l];
-            counts_out[frame] = tot;
+        const int my_off = lane < P.nlevels ? P.lv[lane].sel_off : 0x7fffffff;
+        const int my_n = lane < P.nlevels ? nsel[lane] : 0;
+        level = __popc(__ballot_sync(0xffffffffu, s >= my_off)) - 1;
+        const int slot = s - __shfl_sync(0xffffffffu, my_off, level);
+        int before = lane < level ? my_n : 0, tot = my_n;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            before += __shfl_xor_sync(0xffffffffu, before, o);
+            tot += __shfl_xor_sync(0xffffffffu, tot, o);
         }
-        if (slot >= nsel[level]) return;
+        before += n_existing;
+        if (s == 0 && lane == 0) counts_out[frame] = tot + n_existing;
+        const int n_level = __shfl_sync(0xffffffffu, my_n, level);
+        if (slot >= n_level) return;
         const uint32_t c = sel_all[(size_t)frame * P.sel_total + s];
         cx = cand_x(c) + MIN_BORDER;          // :794-795
         cy = cand_y(c) + MIN_BORDER;
@@ -786,54 +927,59 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(const __grid_c
     const LevelDev& L = P.lv[level];
     cx = min(max(cx, 0), L.w - 1);
     cy = min(max(cy, 0), L.h - 1);
-    const uint8_t* img = L.base + (size_t)frame * L.frame_stride;
-    // ---- raw patch rows cy-21..cy+21, columns cx-21..cx+21 (REFLECT_101 at the level border)
+    // ---- blurred patch rows cy-18..cy+18, columns cx-18..cx+18 -> shared
     const int x0 = cx - PR, y0 = cy - PR;
-    int shift;                                                  // column of x0 inside the shared row
     const bool inside = x0 >= 0 && y0 >= 0 && y0 + PW <= L.h && x0 + PW <= L.w;
-    if (use_tma && inside) {
-        // TMA: one elected lane issues a single bulk tensor copy of the 64 x 43 box (the box start must be 16-byte
-        // aligned in global memory: x is rounded down, `shift` keeps the offset), the warp waits on its mbarrier.
-        // SASS: UTMALDG.3D.  Columns past the level width are zero-filled by the TMA unit and never read.
+    const bool by_tma = inside && ((maps.ok >> level) & 1u);
+    int shift;                                                  // column of x0 inside the shared row
+    if (by_tma) {
+        // one elected lane issues the bulk tensor copy (SASS: UTMALDG.3D); the box start must be 16-byte aligned in
+        // global memory, so x is rounded down and `shift` keeps the offset.  Columns past the level width are
+        // zero-filled by the TMA unit and never read.
         const int xa16 = x0 & ~15;
         shift = x0 - xa16;
-        __syncwarp();
+        const bool with_raw = mode == 0;                           // raw 31-row box for IC_Angle rides on the same barrier
         if (elect_one()) {
             mbar_init(&tma_bar[warp], 1);
-            mbar_expect_tx(&tma_bar[warp], PW * RAWP);
-            tma_load_3d(raw, &maps.patch[level], xa16, y0, frame, &tma_bar[warp]);
+            mbar_expect_tx(&tma_bar[warp], with_raw ? (PW + ICW) * PBOX : PW * PBOX);
+            if (with_raw) tma_load_3d(G + DESC_RAW_OFF, &maps.raw[level], (cx - HALF_PATCH) & ~15, cy - HALF_PATCH, frame, &tma_bar[warp]);
+            tma_load_3d(G, &maps.blur[level], xa16, y0, frame, &tma_bar[warp]);
         }
         __syncwarp();
-        mbar_wait(&tma_bar[warp], 0);
-    } else {
-    const int xa = x0 & ~3;
-    if (inside && xa + RAWP <= L.pitch) {
-        shift = x0 - xa;
-        for (int i = lane; i < PW * (RAWP / 4); i += 32) {     // 43 rows x 12 aligned words
-            const int r = i / (RAWP / 4), c = i - r * (RAWP / 4);
-            reinterpret_cast<uint32_t*>(raw + r * RAWP)[c] =
-                __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y0 + r) * L.pitch + xa) + c);
-        }
-    } else {                                                    // patch touches the border: byte path with reflection
+    } else {                                                    // small level / patch over the border: byte path, REFLECT_101
+        const uint8_t* img = L.blur + (size_t)frame * L.frame_stride;
         shift = 0;
         for (int i = lane; i < PW * PW; i += 32) {
             const int r = i / PW, c = i - r * PW;
-            raw[r * RAWP + c] = img[(size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w)];
+            G[r * PBOX + c] = img[(size_t)reflect101(y0 + r, L.h) * L.pitch + reflect101(x0 + c, L.w)];
         }
+        __syncwarp();
     }
-    }
-    __syncwarp();
-    const uint8_t* rp = raw + shift;                            // rp[r * RAWP + c], c in [0, 43)
-    // ---- IC_Angle on the raw patch: lane = column u, loop over rows v
+    // ---- IC_Angle on the raw level: lane = column u, loop over rows v (keys of mode 0 are >= 19 px inside)
     if (mode == 0) {
+        const uint8_t* c0 = L.base + (size_t)frame * L.frame_stride + (size_t)cy * L.pitch + cx;
         int m10 = 0, m01 = 0;
         const int u = lane - HALF_PATCH;                        // lanes 0..30 <-> u = -15..15
-        if (lane < 31) {
+        if (by_tma) {
+            // raw 31-row box already on its way by TMA: column u of the circular patch covers rows |v| <= vlim[|u|]
+            mbar_wait(&tma_bar[warp], 0);
+            const int vl = lane < 31 ? P.vlim[abs(u)] : -1;
+            const uint8_t* pc = G + DESC_RAW_OFF + ((cx - HALF_PATCH) & 15) + lane;
+            int colsum = 0;
+#pragma unroll
+            for (int k = 0; k < ICW; k++) {
+                const int v = k - HALF_PATCH;
+                const int I = abs(v) <= vl ? (int)pc[k * PBOX] : 0;
+                colsum += I;
+                m01 += v * I;
+            }
+            m10 = u * colsum;
+        } else if (lane < 31) {
             const int au = abs(u);
-#pragma unroll 1
+#pragma unroll 4
             for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
                 if (au <= P.umax[abs(v)]) {
-                    const int I = rp[(PR + v) * RAWP + PR + u];
+                    const int I = __ldg(c0 + v * L.pitch + u);
                     m10 += u * I;
                     m01 += v * I;
                 }
@@ -846,32 +992,6 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(const __grid_c
         }
         angle = fast_atan2_dev((float)m01, (float)m10);        // every lane computes the same value
     }
-    // ---- horizontal 7-tap pass (8.8 fixed point), columns -18..18 of all 43 rows.
-    //      Each lane produces 4 adjacent outputs from 3 aligned words of the row (10 source bytes).
-    {
-        const int wofs = shift >> 2, sh = shift & 3;           // shift in 0..15 (TMA path) or 0..3 (word loader)
-        for (int i = lane; i < PW * 10; i += 32) {             // 10 groups of 4 outputs cover 37 (+3 spare) columns
-            const int r = i / 10, g4 = i - r * 10;
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(raw + r * RAWP) + g4 + wofs;
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];                   // g4 + wofs + 3 <= 15 < RAWP / 4
-            // bytes b[j] = raw[r][4*g4 + sh + j], j = 0..9
-            const uint32_t q0 = __funnelshift_r(w0, w1, 8 * sh), q1 = __funnelshift_r(w1, w2, 8 * sh),
-                           q2 = __funnelshift_r(w2, w3, 8 * sh);
-            // adjacent byte pairs packed as 16x2: P[j] = b[j] | b[j+1] << 16.  Every partial sum stays below 2^16
-            // (H <= 255 * 256), so ordinary 32-bit adds / multiplies act on both halves independently:
-            // one instruction stream yields two neighbouring H values.
-            unsigned Pk[9];
-            Pk[0] = __byte_perm(q0, 0, 0x4140); Pk[1] = __byte_perm(q0, 0, 0x4241); Pk[2] = __byte_perm(q0, 0, 0x4342);
-            Pk[3] = __byte_perm(q0, q1, 0x7473) & 0x00FF00FFu; Pk[4] = __byte_perm(q1, 0, 0x4140); Pk[5] = __byte_perm(q1, 0, 0x4241);
-            Pk[6] = __byte_perm(q1, 0, 0x4342); Pk[7] = __byte_perm(q1, q2, 0x7473) & 0x00FF00FFu; Pk[8] = __byte_perm(q2, 0, 0x4140);
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                const int c = 4 * g4 + j;
-                const unsigned hp = 18u * (Pk[j] + Pk[j + 6]) + 34u * (Pk[j + 1] + Pk[j + 5]) + 48u * (Pk[j + 2] + Pk[j + 4]) + 56u * Pk[j + 3];
-                if (c + 1 < HP) *reinterpret_cast<uint32_t*>(&H[r * HP + c]) = hp;      // columns c, c+1 (c even; column 37 is padding)
-            }
-        }
-    }
     float a, b;
     {
         const float factorPI = (float)(3.141592653589793238462643383279502884197169399375 / 180.0);   // (float)(CV_PI/180.f)
@@ -880,43 +1000,21 @@ __global__ void __launch_bounds__(DESC_THREADS) k_orient_describe(const __grid_c
         a = __shfl_sync(0xffffffffu, ca, 0);
         b = __shfl_sync(0xffffffffu, sb, 0);
     }
-    __syncwarp();
-    // ---- vertical 7-tap pass: lane = column, sliding 7-row window in registers -> blurred 37x37 patch (u8) that
-    //      overwrites the raw patch (no longer needed); one shared load per sample afterwards
-    uint8_t* G = raw;                                           // G[(dy+18) * GP + (dx+18)]
-    constexpr int GP = 40;
-    {   // columns 0..31: one lane per column, 7-row sliding window
-        const int c = lane;
-        uint32_t w0 = H[0 * HP + c], w1 = H[1 * HP + c], w2 = H[2 * HP + c], w3 = H[3 * HP + c], w4 = H[4 * HP + c],
-                 w5 = H[5 * HP + c];
-#pragma unroll 4
-        for (int r = 0; r < HW; r++) {
-            const uint32_t w6 = H[(r + 6) * HP + c];
-            const uint32_t acc = 18u * (w0 + w6) + 34u * (w1 + w5) + 48u * (w2 + w4) + 56u * w3;
-            G[r * GP + c] = (uint8_t)((acc + (1u << 15)) >> 16);
-            w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
-        }
-        // columns 32..36: 5 x 37 outputs spread over the warp, direct 7-tap
-        for (int i = lane; i < 5 * HW; i += 32) {
-            const int r = i / 5, cc = 32 + (i - r * 5);
-            const uint16_t* h = H + r * HP + cc;
-            const uint32_t acc = 18u * (h[0] + h[6 * HP]) + 34u * (h[HP] + h[5 * HP]) + 48u * (h[2 * HP] + h[4 * HP]) + 56u * h[3 * HP];
-            G[r * GP + cc] = (uint8_t)((acc + (1u << 15)) >> 16);
-        }
-    }
-    __syncwarp();
-    // ---- lane j evaluates tests 8j..8j+7 = descriptor byte j (:118-145)
+    if (by_tma && mode != 0) mbar_wait(&tma_bar[warp], 0);
+    // ---- lane j evaluates tests 8j..8j+7 = descriptor byte j (:118-145) on the blurred patch
     {
-        auto sample = [&](int px, int py) -> int {
-            const float xf = (float)px, yf = (float)py;
-            const int dy = __float2int_rn(__fadd_rn(__fmul_rn(xf, b), __fmul_rn(yf, a)));   // cvRound(x*b + y*a)
-            const int dx = __float2int_rn(__fsub_rn(__fmul_rn(xf, a), __fmul_rn(yf, b)));   // cvRound(x*a - y*b)
-            return G[(dy + 18) * GP + (dx + 18)];
+        const uint8_t* ctr = G + PR * PBOX + PR + shift;
+        // cvRound = cvtss2si = F2I.RN (the magic-add alternative, v + 1.5 * 2^23, measured no faster)
+        auto rnd = [](float v) -> int { return __float2int_rn(v); };
+        auto sample = [&](float xf, float yf) -> int {
+            const int dy = rnd(__fadd_rn(__fmul_rn(xf, b), __fmul_rn(yf, a)));   // cvRound(x*b + y*a)
+            const int dx = rnd(__fsub_rn(__fmul_rn(xf, a), __fmul_rn(yf, b)));   // cvRound(x*a - y*b)
+            return ctr[dy * PBOX + dx];
         };
         int byte = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const char4 pt = __ldg(pattern + lane * 8 + j);
+            const float4 pt = __ldg(pattern + j * 32 + lane);         // transposed table: one instruction reads 512 contiguous bytes
             const int t0 = sample(pt.x, pt.y);
             const int t1 = sample(pt.z, pt.w);
             byte |= (t0 < t1) << j;
