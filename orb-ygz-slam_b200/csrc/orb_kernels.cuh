@@ -176,14 +176,15 @@ constexpr int FAST_WARPS = 8;                       // one warp per cell, FAST_W
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 
 // FAST-9 score of one pixel, both polarities at once in the two 16-bit halves of a register (VIMNMX3.S16x2):
-//   low  half: c - r_k + 256  (darker ring),   high half: r_k - c + 255  (brighter ring), all values in [0, 511].
+//   low  half: c - r_k + 256  (darker ring),   high half: r_k - c + 255 = 511 - low  (brighter ring), all in [0, 511],
+//   i.e. E_k = 0x01FF0000 - low * 0xFFFF = r_k * 0xFFFF + K2 with K2 = 0x01FF0000 - (c + 256) * 0xFFFF: one IMAD per ring pixel.
 // min over 9 contiguous = min3 of three min3 (32 instructions for all 16 arcs), then a max3 tree.
 // No negated operand feeds a min/max (ptxas 12.9 drops the negation when fusing into VIMNMX3).
 __device__ __forceinline__ int fast9_best_packed(int c, const int* r) {
-    const unsigned K = (unsigned)(c + 256) * 0x00010001u;
+    const unsigned K2 = 0x01FF0000u - (unsigned)(c + 256) * 0xFFFFu;
     unsigned E[16], e3[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) E[k] = (K - (unsigned)r[k] * 0x00010001u) ^ 0x01FF0000u;
+    for (int k = 0; k < 16; k++) E[k] = (unsigned)r[k] * 0xFFFFu + K2;
 #pragma unroll
     for (int k = 0; k < 16; k++) e3[k] = __vimin3_s16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
     unsigned m[16];
@@ -198,13 +199,20 @@ __device__ __forceinline__ int fast9_best_packed(int c, const int* r) {
     return max(dark, bright);
 }
 
+// Fixed-pitch fast path: every cell image is at most 37 px wide (cw + 3 <= FAST_TPC), so the tile pitch, the score
+// pitch and therefore all 16 ring offsets are compile-time immediates of the shared-memory loads.
+constexpr int FAST_TPC = 40;
+constexpr int FAST_SW2C = 34;
+
 // shared-memory bytes one warp needs for a cell image of cw x ch (x0 & 3 = worst-case 3 extra columns)
-__host__ __device__ inline int fast_warp_smem(int cw, int ch) {
+__host__ __device__ inline int fast_warp_smem(int cw, int ch, bool fixed_pitch) {
     const int dw = cw - 6, dh = ch - 6;
-    const int tp = round4(cw + 3);
-    return round4(ch * tp) + round4((dw + 2) * (dh + 2)) + round4(dw * dh) + round4(2 * dw * dh);
+    const int tp = fixed_pitch ? FAST_TPC : round4(cw + 3);
+    const int sw2 = fixed_pitch ? FAST_SW2C : dw + 2;
+    return round4((ch + 1) * tp) + round4(sw2 * (dh + 2)) + round4(dw * dh) + round4(2 * dw * dh);
 }
 
+template <int TPC>      // TPC = FAST_TPC: fixed-pitch path (all cells <= 37 px wide); 0: any cell size, run-time pitch
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const CellDesc* __restrict__ cells,
                                                              uint32_t* __restrict__ pool,
                                                              uint16_t* __restrict__ cell_count, int warp_smem) {
@@ -220,23 +228,20 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
     uint16_t* cnt_out = cell_count + (size_t)frame * P.n_cells + cell;
     if (dw <= 0 || dh <= 0) { if (lane == 0) *cnt_out = 0; return; }
     const int npx = dw * dh;
-    const int sw2 = dw + 2;
+    const int sw2 = TPC ? FAST_SW2C : dw + 2;
     const int xa = cd.x0 & ~3, shift = cd.x0 - xa;    // tile is loaded as aligned 32-bit words
-    const int TP = round4(cw + shift);
-    uint8_t* tile = smem_raw + (size_t)warp * warp_smem;               // ch x TP
-    uint8_t* sc = tile + round4(ch * TP);                              // (dh+2) x (dw+2) scores, zero border
+    const int TP = TPC ? TPC : round4(cw + shift);
+    uint8_t* tile = smem_raw + (size_t)warp * warp_smem;               // (ch + 1) x TP (one spare row: the packed pre-test reads row pairs)
+    uint8_t* sc = tile + round4((ch + 1) * TP);                        // (dh+2) x sw2 scores, zero border
     uint8_t* flag = sc + round4(sw2 * (dh + 2));                       // per item: score if NMS survivor else 0
     uint16_t* items = reinterpret_cast<uint16_t*>(flag + round4(npx)); // pre-test survivors: x | y<<6
 
     {   // ---- tile load (coalesced words) + score tile clear
         const int wpr = TP >> 2;
         const uint8_t* g0 = L.base + (size_t)frame * L.frame_stride + (size_t)cd.y0 * L.pitch + xa;
-        int r = 0, c = lane;
-        while (c >= wpr) { c -= wpr; r++; }
-        while (r < ch) {
+        for (int i = lane; i < ch * wpr; i += 32) {
+            const int r = i / wpr, c = i - r * wpr;
             reinterpret_cast<uint32_t*>(tile + r * TP)[c] = __ldg(reinterpret_cast<const uint32_t*>(g0 + (size_t)r * L.pitch) + c);
-            c += 32;
-            while (c >= wpr) { c -= wpr; r++; }
         }
         const int nsw = round4(sw2 * (dh + 2)) >> 2;
         for (int i = lane; i < nsw; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0u;
@@ -256,56 +261,56 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
     int total = 0;
     for (int pass = 0; pass < 2; pass++) {
         const int tmin = pass ? P.min_th : P.ini_th;          // threshold of this cv::FAST call
-        // ---- phase A: opposite-pair pre-test at the call's threshold (necessary for 9 contiguous): with da = a-c, db = b-c of an
-        //      opposite pair, a brighter arc needs max(da,db) > t for every pair and a darker arc min(da,db) < -t.
-        //      Straight-line (no early exits: a warp almost always has a surviving lane), one detection row per step;
-        //      ordered compaction keeps raster order.
+        // ---- phase A: opposite-pair pre-test at the call's threshold (necessary for 9 contiguous): a brighter arc
+        //      needs max(a,b) > c + t for every opposite pair (a,b), a darker arc min(a,b) < c - t.
+        //      Straight-line (no early exits: a warp almost always has a surviving lane); ordered compaction keeps
+        //      raster order.
         total = 0;
-        if (dw <= 32) {
-            // two detection rows per step, packed in the 16-bit halves of a register (VIMNMX.U16x2): lo = row y, hi = row y+1.
-            // D = r - c + 256 per half (always in [1, 511], so plain 32-bit adds never carry between the halves).
-            const int x = lane;
-            const unsigned thi = 256u + (unsigned)tmin, tlo = 256u - (unsigned)tmin;
+        if (TPC || dw <= 32) {
+            // two detection rows per step, packed in the 16-bit halves of a register (VIMNMX.U16x2): lo = row y, hi = row y+1,
+            // on the RAW ring values.  With K3 = 0x7FFF - t per half, bit 15 / 31 of (bmin + K3 - c) is "bmin > c + t" and
+            // of (c + K3 - dmax) is "dmax < c - t"; every half stays inside [0, 0xFFFF], so plain 32-bit adds never carry
+            // between the halves.  Lanes >= dw compute on the neighbouring bytes and are masked afterwards.
+            const unsigned K3 = (0x7FFFu - (unsigned)tmin) * 0x00010001u;
+            const unsigned lane_mask = lane < dw ? 0x80008000u : 0u;
             for (int y = 0; y < dh; y += 2) {
-                bool pass0 = false, pass1 = false;
-                if (x < dw) {
-                    const uint8_t* p = t0 + y * TP + x;
-    #define LD2(o) ((unsigned)p[(o)] | ((unsigned)p[(o) + TP] << 16))
-                    const unsigned KB = 0x01000100u - LD2(0);
-                    const unsigned D0 = LD2(o0) + KB, D8 = LD2(o8) + KB, D4 = LD2(o4) + KB, D12 = LD2(o12) + KB;
-                    const unsigned D2 = LD2(o2) + KB, D10 = LD2(o10) + KB, D6 = LD2(o6) + KB, D14 = LD2(o14) + KB;
-    #undef LD2
-                    const unsigned bmin = __vminu2(__vminu2(__vmaxu2(D0, D8), __vmaxu2(D4, D12)), __vminu2(__vmaxu2(D2, D10), __vmaxu2(D6, D14)));
-                    const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(D0, D8), __vminu2(D4, D12)), __vmaxu2(__vminu2(D2, D10), __vminu2(D6, D14)));
-                    pass0 = ((bmin & 0xFFFFu) > thi) | ((dmax & 0xFFFFu) < tlo);
-                    pass1 = (y + 1 < dh) & (((bmin >> 16) > thi) | ((dmax >> 16) < tlo));
-                }
-                const unsigned bal0 = __ballot_sync(0xffffffffu, pass0);
-                const unsigned bal1 = __ballot_sync(0xffffffffu, pass1);
-                if (pass0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)(x | (y << 6));
+                const uint8_t* p = t0 + y * TP + lane;
+#define LD2(o) ((unsigned)p[(o)] | ((unsigned)p[(o) + TP] << 16))
+                const unsigned c2 = LD2(0);
+                const unsigned A0 = LD2(o0), A8 = LD2(o8), A4 = LD2(o4), A12 = LD2(o12);
+                const unsigned A2 = LD2(o2), A10 = LD2(o10), A6 = LD2(o6), A14 = LD2(o14);
+#undef LD2
+                const unsigned bmin = __vminu2(__vminu2(__vmaxu2(A0, A8), __vmaxu2(A4, A12)), __vminu2(__vmaxu2(A2, A10), __vmaxu2(A6, A14)));
+                const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(A0, A8), __vminu2(A4, A12)), __vmaxu2(__vminu2(A2, A10), __vminu2(A6, A14)));
+                unsigned z = ((bmin + K3 - c2) | (c2 + K3 - dmax)) & lane_mask;
+                if (y + 1 >= dh) z &= 0xFFFFu;
+                const int p0 = z & 0x8000u, p1 = z >> 31;
+                const unsigned bal0 = __ballot_sync(0xffffffffu, p0);
+                const unsigned bal1 = __ballot_sync(0xffffffffu, p1);
+                if (p0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)(lane | (y << 6));
                 total += __popc(bal0);
-                if (pass1) items[total + __popc(bal1 & lanemask_lt())] = (uint16_t)(x | ((y + 1) << 6));
+                if (p1) items[total + __popc(bal1 & lanemask_lt())] = (uint16_t)(lane | ((y + 1) << 6));
                 total += __popc(bal1);
             }
         } else {
-        for (int y = 0; y < dh; y++) {
-            for (int xb = 0; xb < dw; xb += 32) {
-                const int x = xb + lane;
-                bool pass = false;
-                if (x < dw) {
-                    const uint8_t* p = t0 + y * TP + x;
-                    const int c = p[0];
-                    const int d0 = p[o0] - c, d8 = p[o8] - c, d4 = p[o4] - c, d12 = p[o12] - c;
-                    const int d2 = p[o2] - c, d10 = p[o10] - c, d6 = p[o6] - c, d14 = p[o14] - c;
-                    const int bmin = min(min(max(d0, d8), max(d4, d12)), min(max(d2, d10), max(d6, d14)));
-                    const int dmax = max(max(min(d0, d8), min(d4, d12)), max(min(d2, d10), min(d6, d14)));
-                    pass = (bmin > tmin) | (dmax + tmin < 0);
+            for (int y = 0; y < dh; y++) {
+                for (int xb = 0; xb < dw; xb += 32) {
+                    const int x = xb + lane;
+                    bool pass_px = false;
+                    if (x < dw) {
+                        const uint8_t* p = t0 + y * TP + x;
+                        const int c = p[0];
+                        const int d0 = p[o0] - c, d8 = p[o8] - c, d4 = p[o4] - c, d12 = p[o12] - c;
+                        const int d2 = p[o2] - c, d10 = p[o10] - c, d6 = p[o6] - c, d14 = p[o14] - c;
+                        const int bmin = min(min(max(d0, d8), max(d4, d12)), min(max(d2, d10), max(d6, d14)));
+                        const int dmax = max(max(min(d0, d8), min(d4, d12)), max(min(d2, d10), min(d6, d14)));
+                        pass_px = (bmin > tmin) | (dmax + tmin < 0);
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, pass_px);
+                    if (pass_px) items[total + __popc(bal & lanemask_lt())] = (uint16_t)(x | (y << 6));
+                    total += __popc(bal);
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) items[total + __popc(bal & lanemask_lt())] = (uint16_t)(x | (y << 6));
-                total += __popc(bal);
             }
-        }
         }
         __syncwarp();
 
@@ -314,12 +319,12 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         //      and the halved lane utilisation of the last iteration cost more than the shared min/max network saves.
         for (int g = lane; g < total; g += 32) {
             const int it = items[g];
-            const int x = it & 63, y = (it >> 6) & 63;
+            const int x = it & 63, y = it >> 6;
             const uint8_t* p = t0 + y * TP + x;
             const int r[16] = {p[o0], p[o1], p[o2], p[o3], p[o4], p[o5], p[o6], p[o7],
                                p[o8], p[o9], p[o10], p[o11], p[o12], p[o13], p[o14], p[o15]};
             const int best = fast9_best_packed(p[0], r);
-            if (best > tmin) sc[(y + 1) * sw2 + x + 1] = (uint8_t)(best - 1);   // corner at minTh; response = best-1
+            if (best > tmin) sc[(y + 1) * sw2 + x + 1] = (uint8_t)(best - 1);   // corner at this threshold; response = best-1
         }
         __syncwarp();
 
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         int any_keep = 0;
         for (int g = lane; g < total; g += 32) {
             const int it = items[g];
-            const int x = it & 63, y = (it >> 6) & 63;
+            const int x = it & 63, y = it >> 6;
             const uint8_t* q = sc + (y + 1) * sw2 + x + 1;
             const int s = q[0];
             int keep = 0;
@@ -341,7 +346,6 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         __syncwarp();
         // vKeysCell.empty() after the iniTh call decides the fallback to minTh (src/ORBextractor.cc:765-770)
         if (__any_sync(0xffffffffu, any_keep)) break;
-
     }
 
     // ---- phase D: ordered emission (raster order inside the cell), coordinates relative to (16,16)
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int pos = base + __popc(bal & lanemask_lt());
-            if (pos < cd.cap) out[pos] = pack_cand((it & 63) + 3 + cd.offx, ((it >> 6) & 63) + 3 + cd.offy, s);
+            if (pos < cd.cap) out[pos] = pack_cand((it & 63) + 3 + cd.offx, (it >> 6) + 3 + cd.offy, s);
         }
         base += __popc(bal);
     }
