@@ -400,8 +400,8 @@ def main():
         pf_ms = stages["pyramid(7 launches)"] + stages["fast_cells"]
         # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the ncu --set full capture of this very
         # command shape (B=256), profiles/r1_full_B256_raw.csv; None for other shapes
-        NCU_TRAFFIC_B256 = {"fast_cells": 271869696 + 32466688, "orient_describe": 270863616 + 16201472,
-                            "octree": 70613504 + 52721408}
+        NCU_TRAFFIC_B256 = {"fast_cells": 271660800 + 31598336, "orient_describe": 521018112 + 17215488,
+                            "octree": 70602752 + 52727552, "blur_levels": 289890816 + 252677888}
         traffic = NCU_TRAFFIC_B256.get(dom) if B == 256 else None
         out = {
             "metric": "front-end frames/sec (752x480, 1000 feat, 8-lvl pyr)", "value": value, "unit": "frames/s",
@@ -417,7 +417,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                         "limiter": "issue slots, not bytes: ncu smsp__issue_active 78 % (fast_cells), 78 % (orient_describe); see DESIGN.md §4",
+                         "limiter": "issue slots, not bytes: ncu smsp__issue_active 80 % (fast_cells; ALU pipe 61 %), 87 % (blur_levels, which streams 2 x SUM_P at 2.4 TB/s); see DESIGN.md §4",
                          "kernel_ms_per_launch": stages[dom],
                          "pyramid_plus_fast": {"strict_bytes_per_step": pf_bytes, "ms_per_step": pf_ms,
                                                "achieved": pf_bytes / (pf_ms / 1e3) / 1e9,

@@ -61,7 +61,6 @@ struct ygz_orb {
     int n_blur_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0;
     int fast_warp_smem = 0;
-    int fast_fixed_pitch = 0;
     int oct_node_smem = 0, oct_key_cache = 0;
     int launches_per_run = 0;
     ygz_counters ctr = {};
@@ -265,12 +264,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
     h->P.key_total = std::max(key_total, 1);
     h->P.sel_total = sel_total;
     h->P.out_cap = sel_total;
-    // FAST kernel flavour: fixed 40-byte tile pitch when every cell image is <= 37 px wide (C1, C5), else run-time pitch
-    h->fast_fixed_pitch = 1;
-    for (const CellDesc& c : h->cells) if (c.cw + 3 > FAST_TPC) h->fast_fixed_pitch = 0;
-    if (getenv("YGZ_FAST_GENERIC")) h->fast_fixed_pitch = 0;      // A/B knob
     for (const CellDesc& c : h->cells)
-        if (c.cw > 6 && c.ch > 6) fast_smem = std::max(fast_smem, (size_t)fast_warp_smem(c.cw, c.ch, h->fast_fixed_pitch != 0));
+        if (c.cw > 6 && c.ch > 6) fast_smem = std::max(fast_smem, (size_t)fast_warp_smem(c.cw, c.ch));
     h->fast_warp_smem = (int)round_up((int)fast_smem, 16);
     fast_smem = (size_t)h->fast_warp_smem * FAST_WARPS;
     h->fast_smem = fast_smem;
@@ -354,8 +349,7 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         TRY_OR_FREE(cudaMalloc(&h->d_pattern, fp.size() * sizeof(float)));
         TRY_OR_FREE(cudaMemcpy(h->d_pattern, fp.data(), fp.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells<FAST_TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
-    TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
     TRY_OR_FREE(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
     TRY_OR_FREE(cudaDeviceSynchronize());
 #undef TRY_OR_FREE
@@ -423,10 +417,7 @@ static int launch_pyramid(ygz_orb* h, int n) {
 static int launch_detect(ygz_orb* h, int n) {
     if (h->P.n_cells > 0) {
         dim3 grid(ceil_div(h->P.n_cells, FAST_WARPS), n);
-        if (h->fast_fixed_pitch)
-            k_fast_cells<FAST_TPC><<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->fast_warp_smem);
-        else
-            k_fast_cells<0><<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->fast_warp_smem);
+        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->fast_warp_smem);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     return YGZ_OK;

@@ -71,6 +71,8 @@ __device__ __forceinline__ int cand_s(uint32_t c) { return c >> 24; }
 // ------------------------------------------------------------------------------------------------
 // K1  pyramid level from the previous level: cv::resize(INTER_LINEAR) on CV_8UC1, 11-bit fixed point
 //     (src/ORBextractor.cc:1139).  4 output pixels per thread, one 32-bit store.
+//     (Measured alternative: horizontal pass of the whole staged window into shared int32 rows, then a vertical
+//     pass, 256 x 16 tiles — 0.372 vs 0.381 ms for the 7 levels, not worth a second kernel.)
 // ------------------------------------------------------------------------------------------------
 constexpr int PYR_ROWS = 8;          // output rows per CTA / thread
 constexpr int PYR_THREADS = 64;      // 4 output columns per thread -> 256 columns per CTA
@@ -199,20 +201,14 @@ __device__ __forceinline__ int fast9_best_packed(int c, const int* r) {
     return max(dark, bright);
 }
 
-// Fixed-pitch fast path: every cell image is at most 37 px wide (cw + 3 <= FAST_TPC), so the tile pitch, the score
-// pitch and therefore all 16 ring offsets are compile-time immediates of the shared-memory loads.
-constexpr int FAST_TPC = 40;
-constexpr int FAST_SW2C = 34;
-
 // shared-memory bytes one warp needs for a cell image of cw x ch (x0 & 3 = worst-case 3 extra columns)
-__host__ __device__ inline int fast_warp_smem(int cw, int ch, bool fixed_pitch) {
+__host__ __device__ inline int fast_warp_smem(int cw, int ch) {
     const int dw = cw - 6, dh = ch - 6;
-    const int tp = fixed_pitch ? FAST_TPC : round4(cw + 3);
-    const int sw2 = fixed_pitch ? FAST_SW2C : dw + 2;
-    return round4((ch + 1) * tp) + round4(sw2 * (dh + 2)) + round4(dw * dh) + round4(2 * dw * dh);
+    const int tp = round4(cw + 3);
+    return round4((ch + 1) * tp) + round4((dw + 2) * (dh + 2)) + round4(dw * dh) + round4(2 * dw * dh);
 }
 
-template <int TPC>      // TPC = FAST_TPC: fixed-pitch path (all cells <= 37 px wide); 0: any cell size, run-time pitch
+// (A compile-time tile pitch for the common <= 37 px cells was measured: same 1.09 ms, so only this flavour is kept.)
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const CellDesc* __restrict__ cells,
                                                              uint32_t* __restrict__ pool,
                                                              uint16_t* __restrict__ cell_count, int warp_smem) {
@@ -228,9 +224,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
     uint16_t* cnt_out = cell_count + (size_t)frame * P.n_cells + cell;
     if (dw <= 0 || dh <= 0) { if (lane == 0) *cnt_out = 0; return; }
     const int npx = dw * dh;
-    const int sw2 = TPC ? FAST_SW2C : dw + 2;
+    const int sw2 = dw + 2;
     const int xa = cd.x0 & ~3, shift = cd.x0 - xa;    // tile is loaded as aligned 32-bit words
-    const int TP = TPC ? TPC : round4(cw + shift);
+    const int TP = round4(cw + shift);
     uint8_t* tile = smem_raw + (size_t)warp * warp_smem;               // (ch + 1) x TP (one spare row: the packed pre-test reads row pairs)
     uint8_t* sc = tile + round4((ch + 1) * TP);                        // (dh+2) x sw2 scores, zero border
     uint8_t* flag = sc + round4(sw2 * (dh + 2));                       // per item: score if NMS survivor else 0
@@ -266,7 +262,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
         //      Straight-line (no early exits: a warp almost always has a surviving lane); ordered compaction keeps
         //      raster order.
         total = 0;
-        if (TPC || dw <= 32) {
+        if (dw <= 32) {
             // two detection rows per step, packed in the 16-bit halves of a register (VIMNMX.U16x2): lo = row y, hi = row y+1,
             // on the RAW ring values.  With K3 = 0x7FFF - t per half, bit 15 / 31 of (bmin + K3 - c) is "bmin > c + t" and
             // of (c + K3 - dmax) is "dmax < c - t"; every half stays inside [0, 0xFFFF], so plain 32-bit adds never carry
