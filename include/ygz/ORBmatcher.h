@@ -21,7 +21,7 @@ public:
             h_ = nullptr;
         }
     }
-    ~ORBmatcher() { if (h_) ygz_matcher_destroy(h_); }
+    ~ORBmatcher() { if (h_) ygz_matcher_destroy(h_); if (d_) ygz_direct_destroy(d_); }
     ORBmatcher(const ORBmatcher&) = delete;
     ORBmatcher& operator=(const ORBmatcher&) = delete;
 
@@ -57,6 +57,38 @@ public:
     }
     ygz_matcher* handle() { return h_; }
 
+    // ---- direct (patch) projection search, SURVEY.md §8(f) rank 1 -------------------------------------------------
+    // FindDirectProjection(KeyFrame* ref, Frame* curr, MapPoint* mp, Vector2f& px_curr, int& search_level)  :1575-1602,
+    // batched over the (map point, observing keyframe) pairs Tracking::SearchLocalPointsDirect tries for one frame
+    // (src/Tracking.cc:2174-2326).  Pyramids live in device slots: BindDirect once, UploadDirectFrame per keyframe /
+    // per current frame, then one FindDirectProjection call per frame.
+    bool BindDirect(int max_slots, int max_items, size_t max_pyramid_bytes, int device = 0) {
+        if (d_) { ygz_direct_destroy(d_); d_ = nullptr; }
+        return ygz_direct_create(device, max_slots, max_items, max_pyramid_bytes, &d_) == YGZ_OK || (ok(-1), false);
+    }
+    bool UploadDirectFrame(int slot, const ygz_direct_frame& f, int nlevels) {
+        return d_ && (ygz_direct_upload_frame(d_, slot, &f, nlevels) == YGZ_OK || (ok(-1), false));
+    }
+    bool SetDirectPose(int slot, const float q_xyzw[4], const float t[3]) {
+        return d_ && (ygz_direct_set_pose(d_, slot, q_xyzw, t) == YGZ_OK || (ok(-1), false));
+    }
+    // px_curr (in: mp->mTrackProjX/Y, out: refined), search_level and the returned bool per item; returns #successes
+    int FindDirectProjection(int cur_slot, const float K4[4], const std::vector<float>& mvScaleFactors,
+                             const std::vector<float>& mvInvScaleFactors, float invLevelSigma2_1,
+                             const std::vector<ygz_direct_item>& items, std::vector<float>& px_curr,
+                             std::vector<int>& search_level, std::vector<uint8_t>& success) {
+        const int n = (int)items.size();
+        px_curr.assign((size_t)2 * n, 0.f); search_level.assign(n, 0); success.assign(n, 0);
+        if (!d_ || n == 0) return 0;
+        if (ygz_find_direct_projection(d_, cur_slot, K4, mvScaleFactors.data(), mvInvScaleFactors.data(), invLevelSigma2_1,
+                                       (int)mvScaleFactors.size(), items.data(), n, px_curr.data(), search_level.data(),
+                                       success.data()) != YGZ_OK)
+            return ok(-1);
+        int cnt = 0;
+        for (uint8_t s : success) cnt += s;
+        return cnt;
+    }
+
 protected:
     static int ok(int rc) {        // reference convention: failures surface as "0 matches" + a log line
         if (rc < 0) { std::fprintf(stderr, "ygz::ORBmatcher: %d %s\n", rc, ygz_last_error()); return 0; }
@@ -65,6 +97,7 @@ protected:
     float mfNNratio;
     bool mbCheckOrientation;
     ygz_matcher* h_ = nullptr;
+    ygz_direct* d_ = nullptr;
 };
 
 }  // namespace ygz

@@ -247,6 +247,41 @@ int ygz_sia_last_trace(ygz_sia* h, int problem, float* out, int cap, int* n);
 int ygz_sia_time(ygz_sia* h, int n_problems, int max_level, int min_level, int n_iter, float eps, int iters,
                  float* ms);
 
+/* ------------------------------------------------------------------ direct (patch) projection search
+ * ORBmatcher::FindDirectProjection(KeyFrame* ref, Frame* curr, MapPoint* mp,
+ * Vector2f& px_curr, int& search_level), /root/reference/src/ORBmatcher.cc:1575-1602, with GetWarpAffineMatrix
+ * :1525-1547, WarpAffine :1549-1573, GetBestSearchLevel / GetBilateralInterpUchar include/ORBmatcher.h:185-211 and
+ * ygz::Align2D src/Align.cc:8-103 — batched over the (map point, observing keyframe) pairs that
+ * Tracking::SearchLocalPointsDirect (src/Tracking.cc:2174-2326) tries for one current frame.  Keyframe and
+ * current-frame pyramids live in device slots (a keyframe is uploaded once, the current frame once per frame). */
+typedef struct {
+    const uint8_t* level[16];       /* mvImagePyramid[l].data (host), row stride pitch[l] */
+    int w[16], h[16], pitch[16];
+    float q[4], t[3];               /* mTcw / GetPose(): unit quaternion (x,y,z,w) + translation */
+} ygz_direct_frame;
+typedef struct {
+    int ref;                        /* slot of the observing keyframe */
+    float px_ref[2];                /* ref->mvKeys[idx].pt */
+    int octave;                     /* ref->mvKeys[idx].octave */
+    float pw[3];                    /* mp->GetWorldPos() */
+    float px_cur[2];                /* initial guess: mp->mTrackProjX / mTrackProjY */
+} ygz_direct_item;
+typedef struct ygz_direct ygz_direct;
+int ygz_direct_create(int device, int max_slots, int max_items, size_t max_pyramid_bytes, ygz_direct** out);
+int ygz_direct_destroy(ygz_direct* h);
+/* copy a frame's pyramid (nlevels images) and pose into device slot `slot` */
+int ygz_direct_upload_frame(ygz_direct* h, int slot, const ygz_direct_frame* f, int nlevels);
+/* new pose for a resident slot (the tracker refines curr->mTcw between searches) */
+int ygz_direct_set_pose(ygz_direct* h, int slot, const float* q, const float* t);
+/* K4 = {fx, fy, cx, cy} (static members of Frame / KeyFrame), scale / inv_scale = mvScaleFactors / mvInvScaleFactors,
+ * inv_level_sigma2_1 = ref->mvInvLevelSigma2[1].  Per item: out_px[2] = px_curr after the search (level-0 pixels),
+ * out_level = search_level, out_ok = the bool FindDirectProjection returns. */
+int ygz_find_direct_projection(ygz_direct* h, int cur_slot, const float* K4, const float* scale, const float* inv_scale,
+                               float inv_level_sigma2_1, int nlevels, const ygz_direct_item* items, int n_items,
+                               float* out_px, int* out_level, uint8_t* out_ok);
+/* device-timed repeats of the last search (items resident) for bench.py */
+int ygz_direct_time(ygz_direct* h, int iters, float* ms);
+
 /* ------------------------------------------------------------------ throughput counters (multi-GPU)
  * The only cross-rank exchange of the path is one all-gather of these; the library
  * fills them, the launcher (torch.distributed / NCCL) gathers them. */

@@ -125,6 +125,25 @@ typedef struct {
  * trace (optional, 8 floats per evaluated iteration: level, iter, chi2, n_meas, max|x|, accepted,0,0) */
 int orc_sia_run(const orc_sia_problem* p, int max_level, int min_level, int n_iter, float eps,
                 float* out_q, float* out_t, float* H_out, float* trace, int trace_cap, int* trace_n);
+/* ---- direct (patch) projection search: ORBmatcher::FindDirectProjection src/ORBmatcher.cc:1575-1602 with
+ * GetWarpAffineMatrix :1525-1547, WarpAffine :1549-1573 and ygz::Align2D src/Align.cc:8-103.   */
+typedef struct {
+    const uint8_t* level[16];       /* mvImagePyramid[l] data (row stride pitch[l]) */
+    int w[16], h[16], pitch[16];
+    float q[4], t[3];               /* mTcw / GetPose(): unit quaternion (x,y,z,w) + translation */
+} orc_direct_frame;
+typedef struct {
+    int ref;                        /* index of the observing keyframe in `refs` */
+    float px_ref[2];                /* ref->mvKeys[idx].pt */
+    int octave;                     /* ref->mvKeys[idx].octave */
+    float pw[3];                    /* mp->GetWorldPos() */
+    float px_cur[2];                /* initial guess (mp->mTrackProjX/Y) */
+} orc_direct_item;
+/* per item: out_px = refined px_curr (level-0 pixels), out_level = search_level, out_ok = return value */
+int orc_find_direct_projection(const orc_direct_frame* refs, int n_refs, const orc_direct_frame* cur,
+                               const float* K4, const float* scale, const float* inv_scale,
+                               float inv_level_sigma2_1, int nlevels, const orc_direct_item* items,
+                               int n_items, float* out_px, int* out_level, uint8_t* out_ok);
 /* CPU front-end baseline: extractor + SearchByBoW vs previous frame, `threads` std::threads (bench.py) */
 long orc_frontend_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs,
                         int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints,

@@ -61,6 +61,22 @@ class SiaProblem(C.Structure):
                 ("cur_q", C.c_float * 4), ("cur_t", C.c_float * 3)]
 
 
+class DirectFrame(C.Structure):
+    """== ygz_direct_frame (include/ygz_b200.h)."""
+    _fields_ = [("level", u8p * 16), ("w", C.c_int * 16), ("h", C.c_int * 16), ("pitch", C.c_int * 16),
+                ("q", C.c_float * 4), ("t", C.c_float * 3)]
+
+
+class DirectItem(C.Structure):
+    """== ygz_direct_item."""
+    _fields_ = [("ref", C.c_int), ("px_ref", C.c_float * 2), ("octave", C.c_int), ("pw", C.c_float * 3),
+                ("px_cur", C.c_float * 2)]
+
+
+DIRECT_ITEM_DTYPE = np.dtype([("ref", np.int32), ("px_ref", np.float32, 2), ("octave", np.int32), ("pw", np.float32, 3),
+                              ("px_cur", np.float32, 2)])
+
+
 class Counters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("frames", "keypoints", "matches", "sia_iters", "bytes_in", "bytes_out",
                                           "kernel_launches", "elapsed_ns")]
@@ -78,6 +94,8 @@ ABI_SYMBOLS = [
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
     "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
+    "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
+    "ygz_find_direct_projection", "ygz_direct_time",
 ]
 
 _lib = None
@@ -132,6 +150,12 @@ def lib():
     sigs.setdefault('ygz_search_by_projection_kf', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), u8p, C.c_float, C.c_int]
     sigs.setdefault('ygz_search_for_initialization', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, i32p, C.c_int]
     sigs.setdefault('ygz_search_by_bow_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, u32p, i32p, i32p]
+    sigs.setdefault('ygz_direct_create', {})['argtypes'] = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
+    sigs.setdefault('ygz_direct_destroy', {})['argtypes'] = [C.c_void_p]
+    sigs.setdefault('ygz_direct_upload_frame', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(DirectFrame), C.c_int]
+    sigs.setdefault('ygz_direct_set_pose', {})['argtypes'] = [C.c_void_p, C.c_int, f32p, f32p]
+    sigs.setdefault('ygz_find_direct_projection', {})['argtypes'] = [C.c_void_p, C.c_int, f32p, f32p, f32p, C.c_float, C.c_int, C.c_void_p, C.c_int, f32p, i32p, u8p]
+    sigs.setdefault('ygz_direct_time', {})['argtypes'] = [C.c_void_p, C.c_int, f32p]
     sigs.setdefault('ygz_search_by_bow_batch_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, f32p]
     sigs.setdefault('ygz_sia_create', {})['argtypes'] = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     sigs.setdefault('ygz_sia_destroy', {})['argtypes'] = [C.c_void_p]
@@ -557,6 +581,69 @@ def make_sia_problem(ref_levels, cur_levels, inv_scale, K, ref_px, world_xyz, va
     v.cur_q = (C.c_float * 4)(*cq)
     v.cur_t = (C.c_float * 3)(*ct)
     return _Keep(v, [ref_levels, cur_levels, lw, lh, isf, px, xyz, val, refp, curp])
+
+
+def make_direct_frame(levels, q=(0, 0, 0, 1), t=(0, 0, 0), cls=None):
+    """ygz_direct_frame from a list of 2-D uint8 level images and a pose (q xyzw, t)."""
+    cls = cls or DirectFrame
+    levels = [np.ascontiguousarray(a, np.uint8) for a in levels]
+    f = cls()
+    for l, a in enumerate(levels):
+        f.level[l] = _ptr(a, u8p)
+        f.w[l], f.h[l], f.pitch[l] = a.shape[1], a.shape[0], a.strides[0]
+    f.q = (C.c_float * 4)(*[float(x) for x in q])
+    f.t = (C.c_float * 3)(*[float(x) for x in t])
+    return _Keep(f, levels)
+
+
+class DirectMatcher:
+    """Batched ORBmatcher::FindDirectProjection (src/ORBmatcher.cc:1575-1602): keyframe / current-frame pyramids live
+    in device slots, one call searches all (map point, keyframe) items of a frame."""
+
+    def __init__(self, K, scale, inv_scale, inv_level_sigma2_1, max_slots=8, max_items=4096,
+                 max_pyramid_bytes=2 * 752 * 480, device=0):
+        self.L = lib()
+        self.K = np.ascontiguousarray(K, np.float32)
+        self.scale = np.ascontiguousarray(scale, np.float32)
+        self.inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+        self.inv_sigma2_1 = float(inv_level_sigma2_1)
+        self.nlevels = len(self.scale)
+        self.h = C.c_void_p()
+        _check(self.L.ygz_direct_create(device, max_slots, max_items, max_pyramid_bytes, C.byref(self.h)), "ygz_direct_create")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ygz_direct_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_frame(self, slot, frame):
+        _check(self.L.ygz_direct_upload_frame(self.h, slot, C.byref(frame.struct), self.nlevels), "ygz_direct_upload_frame")
+
+    def set_pose(self, slot, q, t):
+        q = np.ascontiguousarray(q, np.float32); t = np.ascontiguousarray(t, np.float32)
+        _check(self.L.ygz_direct_set_pose(self.h, slot, _ptr(q, f32p), _ptr(t, f32p)), "ygz_direct_set_pose")
+
+    def FindDirectProjection(self, cur_slot, items):
+        """items: structured array of DIRECT_ITEM_DTYPE.  Returns (px[n,2], level[n], ok[n])."""
+        items = np.ascontiguousarray(items, DIRECT_ITEM_DTYPE)
+        n = len(items)
+        px = np.zeros((n, 2), np.float32); lvl = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+        _check(self.L.ygz_find_direct_projection(self.h, cur_slot, _ptr(self.K, f32p), _ptr(self.scale, f32p),
+                                                 _ptr(self.inv_scale, f32p), self.inv_sigma2_1, self.nlevels,
+                                                 items.ctypes.data, n, _ptr(px, f32p), _ptr(lvl, i32p), _ptr(ok, u8p)),
+               "ygz_find_direct_projection")
+        return px, lvl, ok
+
+    def time(self, iters):
+        ms = C.c_float()
+        _check(self.L.ygz_direct_time(self.h, iters, C.byref(ms)), "ygz_direct_time")
+        return ms.value
 
 
 class SparseImgAlign:

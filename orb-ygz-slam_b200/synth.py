@@ -145,3 +145,75 @@ def synth_sia_pair(seed, n_pts=200, w=752, h=480, K=EUROC_K, depth=4.0, max_t=0.
                     np.full(n_pts, depth)], -1).astype(np.float32)
     return dict(ref=np.ascontiguousarray(ref), cur=np.ascontiguousarray(cur), px=px, xyz=xyz,
                 q_true=q, t_true=t.astype(np.float32), K=K)
+
+
+def render_plane(tex, K, q, t, depth, w, h):
+    """Image of the textured world plane z = depth seen by a camera with pose x_cam = R(q) x_world + t.  The texture is
+    pinned to the plane by su = fx X / depth + cx, sv = fy Y / depth + cy (so the identity camera sees `tex` itself)."""
+    fx, fy, cx, cy = K
+    R = quat_to_R(q)
+    t = np.asarray(t, np.float64)
+    uu, vv = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
+    d_cam = np.stack([(uu - cx) / fx, (vv - cy) / fy, np.ones_like(uu)], -1)
+    d_w = d_cam @ R                        # R^T d
+    o_w = -R.T @ t                         # camera centre in the world
+    lam = (depth - o_w[2]) / d_w[..., 2]
+    X = o_w[0] + lam * d_w[..., 0]
+    Y = o_w[1] + lam * d_w[..., 1]
+    su = fx * X / depth + cx
+    sv = fy * Y / depth + cy
+    th, tw = tex.shape
+    inside = (su >= 0) & (sv >= 0) & (su <= tw - 1) & (sv <= th - 1)
+    x0 = np.clip(np.floor(su).astype(np.int64), 0, tw - 2)
+    y0 = np.clip(np.floor(sv).astype(np.int64), 0, th - 2)
+    ax = np.clip(su - x0, 0, 1)
+    ay = np.clip(sv - y0, 0, 1)
+    tex = tex.astype(np.float64)
+    img = ((1 - ax) * (1 - ay) * tex[y0, x0] + ax * (1 - ay) * tex[y0, x0 + 1] +
+           (1 - ax) * ay * tex[y0 + 1, x0] + ax * ay * tex[y0 + 1, x0 + 1])
+    img = np.where(inside, img, 0.0)
+    return np.ascontiguousarray(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+
+
+def synth_direct_scene(seed, n_kf=3, n_items=300, w=752, h=480, K=EUROC_K, depth=4.0, nlevels=8, scale=1.2, noise_px=1.5):
+    """Keyframes + one current frame looking at the textured plane z = depth, and (map point, keyframe) items for
+    ORBmatcher::FindDirectProjection.  The last keyframe stands twice as far from the plane (affine determinant ~4,
+    so its items search one pyramid level up).  Returns dict(kf_imgs, kf_poses [(q,t)], cur_img, cur_pose, items
+    (structured: ref, px_ref, octave, pw, px_cur), px_true [n,2])."""
+    fx, fy, cx, cy = K
+    rng = np.random.default_rng(seed)
+    tex = synth_texture(seed + 77, w, h, passes=5, n_rect=60)
+    def pose(max_t, max_rot_deg, tz=0.0):
+        rv = (rng.random(3) * 2 - 1) * np.deg2rad(max_rot_deg)
+        t = (rng.random(3) * 2 - 1) * max_t
+        t[2] += tz
+        return quat_from_rotvec(rv), t.astype(np.float32)
+    kf_poses = [pose(0.08, 1.5) for _ in range(n_kf - 1)] + [pose(0.05, 1.0, tz=depth)]   # x_cam.z = z_w + t_z: twice as far
+    cur_pose = pose(0.06, 1.0)
+    kf_imgs = [render_plane(tex, K, q, t, depth, w, h) for q, t in kf_poses]
+    cur_img = render_plane(tex, K, cur_pose[0], cur_pose[1], depth, w, h)
+    dt = np.dtype([("ref", np.int32), ("px_ref", np.float32, 2), ("octave", np.int32), ("pw", np.float32, 3),
+                   ("px_cur", np.float32, 2)])
+    items = np.zeros(n_items, dt)
+    px_true = np.zeros((n_items, 2), np.float32)
+    Rc = quat_to_R(cur_pose[0]); tc = np.asarray(cur_pose[1], np.float64)
+    for i in range(n_items):
+        k = int(rng.integers(0, n_kf))
+        q, t = kf_poses[k]
+        R = quat_to_R(q); t = np.asarray(t, np.float64)
+        margin = 8 if i % 11 == 0 else 40            # a few items hug the border: warp samples fall outside -> zeros
+        px = np.array([rng.uniform(margin, w - margin), rng.uniform(margin, h - margin)])
+        d_w = R.T @ np.array([(px[0] - cx) / fx, (px[1] - cy) / fy, 1.0])
+        o_w = -R.T @ t
+        lam = (depth - o_w[2]) / d_w[2]
+        pw = o_w + lam * d_w
+        pc = Rc @ pw + tc
+        uv = np.array([fx * pc[0] / pc[2] + cx, fy * pc[1] / pc[2] + cy])
+        items["ref"][i] = k
+        items["px_ref"][i] = px
+        items["octave"][i] = int(rng.integers(0, min(nlevels, 4)))
+        items["pw"][i] = pw
+        items["px_cur"][i] = uv + (rng.random(2) * 2 - 1) * noise_px
+        px_true[i] = uv
+    return dict(kf_imgs=kf_imgs, kf_poses=kf_poses, cur_img=cur_img, cur_pose=cur_pose, items=items, px_true=px_true,
+                K=K, nlevels=nlevels, scale=scale)

@@ -144,6 +144,19 @@ def make_sia():
     np.savez_compressed(os.path.join(HERE, "sia_752x480.npz"), **rec)
 
 
+def make_direct():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_oracle_direct as T
+    rec = {}
+    for seed in (1, 2):
+        s, t, kfs, cur = T.build_scene(pkg, O, synth, seed)
+        px, lvl, ok = O.find_direct_projection(kfs, cur, s["K"], t["scale"], t["inv_scale"], t["inv_sigma2"][1], s["items"])
+        rec["px%d" % seed], rec["lvl%d" % seed], rec["ok%d" % seed] = px, lvl, ok
+        rec["cur_sha%d" % seed] = np.array(sha(s["cur_img"]))
+        print("direct", seed, ok.mean(), np.bincount(lvl))
+    np.savez_compressed(os.path.join(HERE, "direct_v1.npz"), **rec)
+
+
 if __name__ == "__main__":
     make_prims()
     make_extract("c1_752x480_seed1", 1, 752, 480, 1000, 1.2, 8)
@@ -152,3 +165,4 @@ if __name__ == "__main__":
     make_extract("small_320x240_seed3", 3, 320, 240, 500, 1.2, 8)
     make_matcher()
     make_sia()
+    make_direct()

@@ -105,6 +105,8 @@ def lib(native=False):
     L.orc_bf_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p]
     L.orc_sia_run.argtypes = [C.POINTER(SiaProblem), C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p,
                               f32p, C.c_int, i32p]
+    L.orc_find_direct_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, f32p, f32p, f32p, C.c_float, C.c_int,
+                                             C.c_void_p, C.c_int, f32p, i32p, u8p]
     L.orc_frontend_batch.restype = C.c_long
     L.orc_frontend_batch.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_float, C.c_int, C.POINTER(C.c_long), C.c_int]
@@ -278,3 +280,24 @@ def frontend_batch(imgs, threads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=2
     m = lib(native).orc_frontend_batch(nfeatures, scale, nlevels, ini_th, min_th, _ptr(imgs, u8p), n, w, h, threads,
                                        nnratio, int(check_ori), C.byref(kp), repeat)
     return m, kp.value
+
+
+def find_direct_projection(ref_frames, cur_frame, K, scale, inv_scale, inv_level_sigma2_1, items):
+    """Oracle FindDirectProjection over a batch.  ref_frames: list of _Keep(DirectFrame) (the product's ctypes struct has the
+    same layout as orc_direct_frame), cur_frame: _Keep(DirectFrame), items: structured array with the layout of
+    ygz_direct_item / orc_direct_item.  Returns (px[n,2], level[n], ok[n])."""
+    L = lib()
+    n = len(items)
+    items = np.ascontiguousarray(items)
+    Frame = type(cur_frame.struct)
+    refs = (Frame * len(ref_frames))(*[f.struct for f in ref_frames])
+    K = np.ascontiguousarray(K, np.float32)
+    scale = np.ascontiguousarray(scale, np.float32)
+    inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    px = np.zeros((n, 2), np.float32); lvl = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+    rc = L.orc_find_direct_projection(C.cast(refs, C.c_void_p), len(ref_frames), C.cast(C.pointer(cur_frame.struct), C.c_void_p),
+                                      K.ctypes.data_as(f32p), scale.ctypes.data_as(f32p), inv_scale.ctypes.data_as(f32p),
+                                      float(inv_level_sigma2_1), len(scale), items.ctypes.data, n,
+                                      px.ctypes.data_as(f32p), lvl.ctypes.data_as(i32p), ok.ctypes.data_as(u8p))
+    assert rc == 0, rc
+    return px, lvl, ok
