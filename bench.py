@@ -235,6 +235,32 @@ def aux_metrics(m, device):
         aux["bf_top2_c5"] = {"nq": 2000, "nt": 2000, "ms_per_call_host_buffers": dt * 1e3, "comparisons_per_s": 4e6 / dt}
     except Exception as e:
         aux["bf_top2_c5"] = {"error": str(e)[:200]}
+    try:
+        # FindDirectProjection over the (map point, keyframe) items of a batch of frames
+        import time as _t
+        s = synth.synth_direct_scene(9, n_kf=3, n_items=16384, w=W, h=H)
+        px = m.ORBextractor(1000, 1.2, 8, 20, 7, width=W, height=H, max_batch=1, device=device)
+        tb = px.tables()
+
+        def pyr(img):
+            px.ComputePyramid(img)
+            return [px.level(0, l) for l in range(8)]
+        frames = [m.make_direct_frame(pyr(im), q, t) for im, (q, t) in zip(s["kf_imgs"], s["kf_poses"])]
+        frames.append(m.make_direct_frame(pyr(s["cur_img"]), *s["cur_pose"]))
+        dm = m.DirectMatcher(s["K"], tb["scale"], tb["inv_scale"], tb["inv_sigma2"][1], max_slots=4, max_items=16384,
+                             max_pyramid_bytes=4 * W * H, device=device)
+        for k, f in enumerate(frames):
+            dm.upload_frame(k, f)
+        dm.FindDirectProjection(3, s["items"])
+        t0 = _t.perf_counter()
+        for _ in range(10):
+            _, _, ok = dm.FindDirectProjection(3, s["items"])
+        dt = (_t.perf_counter() - t0) / 10
+        ms = dm.time(20) / 20
+        aux["direct_projection"] = {"items_per_call": 16384, "ms_kernel": ms, "ms_per_call_host_buffers": dt * 1e3,
+                                    "items_per_s": 16384 / dt, "success_rate": float(ok.mean())}
+    except Exception as e:
+        aux["direct_projection"] = {"error": str(e)[:200]}
     return aux
 
 
@@ -243,7 +269,7 @@ def workload_config(batch):
                         "ORBmatcher(0.7,checkOri).SearchByBoW vs previous frame (synthetic vocabulary byte0>>2)",
             "frames_per_step": batch, "l2_policy": "inputs larger than L2 (%d distinct frames/step, pyramid working set %.0f MB)"
                                                    % (batch, batch * (SUM_P + 361e3 * 0) / 1e6),
-            "in_flight": "2 independent batches per GPU on 2 streams (device-resident `value` and pipelined `e2e`)",
+            "in_flight": "2 independent batches per GPU on 2 streams for the device-resident `value`; `e2e.pipeline` states its own depth",
             "parallelism": "replicas: one independent batch per GPU"}
 
 
@@ -256,6 +282,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the end-to-end (host buffer) path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -298,6 +325,15 @@ def main():
                  cnt=pin((B,), torch.int32), match=pin((B, cap), torch.int32), nm=pin((B,), torch.int32))
     bufs2["img"].numpy()[:] = frames
     bufs1 = dict(img=h_img, kps=h_kps, desc=h_desc, cnt=h_cnt, match=h_match, nm=h_nm)
+    pairs = [(ex, mt, bufs1), (ex2, mt2, bufs2)]
+    for _ in range(max(0, args.inflight - 2)):          # further handle pairs for the end-to-end pipeline
+        exn = m.ORBextractor(width=W, height=H, max_batch=B, device=local, **ORB)
+        mtn = m.ORBmatcher(NNRATIO, CHECK_ORI, device=local)
+        bn = dict(img=pin((B, H, W), torch.uint8), kps=pin((B, cap, 7), torch.float32), desc=pin((B, cap, 32), torch.uint8),
+                  cnt=pin((B,), torch.int32), match=pin((B, cap), torch.int32), nm=pin((B,), torch.int32))
+        bn["img"].numpy()[:] = frames
+        pairs.append((exn, mtn, bn))
+    pairs = pairs[:max(1, args.inflight)]
     import ctypes as C
 
     def enqueue(exh, mth, b):
@@ -308,11 +344,11 @@ def main():
                  "ygz_search_by_bow_batch_async")
 
     def e2e_pipelined(steps):
-        pairs = [(ex, mt, bufs1), (ex2, mt2, bufs2)]
+        np_ = len(pairs)
         for i in range(steps):
-            exh, mth, b = pairs[i & 1]
-            if i >= 2:
-                m._check(m.lib().ygz_orb_wait(exh.h), "ygz_orb_wait")      # results of step i-2 are on the host now
+            exh, mth, b = pairs[i % np_]
+            if i >= np_:
+                m._check(m.lib().ygz_orb_wait(exh.h), "ygz_orb_wait")      # results of step i - inflight are on the host now
             enqueue(exh, mth, b)
         for exh, _, _ in pairs:
             m._check(m.lib().ygz_orb_wait(exh.h), "ygz_orb_wait")
@@ -338,6 +374,10 @@ def main():
     m._check(m.lib().ygz_orb_upload(ex2.h, h_img.data_ptr(), B, W * H, W), "ygz_orb_upload")
     ex2.run(B)
     mt2.SearchByBoWBatch(ex2, kf_idx, f_idx, None)          # prepares the resident pair lists of the second handle pair
+    for exn, mtn, bn in pairs[2:]:
+        m._check(m.lib().ygz_orb_upload(exn.h, h_img.data_ptr(), B, W * H, W), "ygz_orb_upload")
+        exn.run(B)
+        mtn.SearchByBoWBatch(exn, kf_idx, f_idx, None)
     for _ in range(args.warmup):
         mt.time_frontend(ex, B, 1)
         mt.time_frontend2(ex, mt2, ex2, B, 2)
@@ -361,7 +401,8 @@ def main():
     e2e_pipelined(args.steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    assert int(bufs2["cnt"].numpy().sum()) == n_kp and int(bufs2["nm"].numpy().sum()) == n_match   # pipelined results == serial results
+    for _, _, bn in pairs[1:]:
+        assert int(bn["cnt"].numpy().sum()) == n_kp and int(bn["nm"].numpy().sum()) == n_match   # pipelined results == serial results
     barrier()
     clocks = sampler.finish()
 
@@ -412,7 +453,7 @@ def main():
             "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(h_img.numel()),
                     "d2h_bytes_per_step": int(h_kps.numel() * 4 + h_desc.numel() + h_cnt.numel() * 4 + h_match.numel() * 4 + h_nm.numel() * 4),
                     "ms_per_step": t_e / args.steps * 1e3,
-                    "pipeline": "2 batches in flight (two handle pairs, ygz_orb_extract_async + ygz_search_by_bow_batch_async + ygz_orb_wait)"},
+                    "pipeline": "%d batches in flight (one handle pair each, ygz_orb_extract_async + ygz_search_by_bow_batch_async + ygz_orb_wait)" % len(pairs)},
             "gpu_launches": int(args.steps * ((ORB["nlevels"] - 1) + 4 + 1)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

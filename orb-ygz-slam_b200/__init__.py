@@ -601,7 +601,7 @@ class DirectMatcher:
     in device slots, one call searches all (map point, keyframe) items of a frame."""
 
     def __init__(self, K, scale, inv_scale, inv_level_sigma2_1, max_slots=8, max_items=4096,
-                 max_pyramid_bytes=2 * 752 * 480, device=0):
+                 max_pyramid_bytes=4 * 752 * 480, device=0):
         self.L = lib()
         self.K = np.ascontiguousarray(K, np.float32)
         self.scale = np.ascontiguousarray(scale, np.float32)
