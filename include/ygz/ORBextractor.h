@@ -63,12 +63,28 @@ public:
     }
 
     // operator()(Frame*, vector<KeyPoint>&, OutputArray, KeyPointMethod, bool leftEye), src/ORBextractor.cc:1031-1127.
-    // ORBSLAM_KEYPOINT is the device path; FAST_KEYPOINT / DSO_KEYPOINT are "next" rows and are
-    // reported, not silently substituted.
+    // ORBSLAM_KEYPOINT (octree) and DSO_KEYPOINT (ComputeKeyPointsDSOSingleLevel, :1277-1381; mnGridSize is kept in the
+    // handle like the reference's member) are device paths; FAST_KEYPOINT (ComputeKeyPointsFast, which upstream marks as
+    // broken, :1190) is reported, not silently substituted.
     void operator()(ExtractorFrame* frame, std::vector<KeyPoint>& keypoints, std::vector<uint8_t>& descriptors,
                     KeyPointMethod method, bool leftEye = true) {
-        if (method != ORBSLAM_KEYPOINT) {
-            std::fprintf(stderr, "ygz::ORBextractor: KeyPointMethod %d is not on the B200 path yet\n", (int)method);
+        if (method == FAST_KEYPOINT) {
+            std::fprintf(stderr, "ygz::ORBextractor: KeyPointMethod FAST_KEYPOINT is not on the B200 path\n");
+            return;
+        }
+        if (method == DSO_KEYPOINT) {
+            const ImageView& im = leftEye ? frame->mImGray : frame->mImRight;
+            if (im.empty() || !ensure(im.cols, im.rows)) return;
+            const int n_existing = (int)keypoints.size();             // ComputeKeyPointsDSOSingleLevel(kps, frame->mvKeys)
+            const int cap = 3 * (im.rows / 7) * (im.cols / 7) + n_existing;
+            keypoints.resize(cap);
+            descriptors.resize((size_t)cap * 32);
+            int n = 0;
+            int rc = ygz_orb_extract_frame_dso(h_, im.data, im.step, n_existing, keypoints.data(), descriptors.data(), &n, cap, nullptr);
+            if (rc != YGZ_OK) { report("operator()(Frame*, DSO_KEYPOINT)", rc); n = n_existing; }
+            keypoints.resize(n);
+            descriptors.resize((size_t)n * 32);
+            pyramid_stale_ = true;
             return;
         }
         const ImageView& im = leftEye ? frame->mImGray : frame->mImRight;

@@ -81,6 +81,15 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
                           ygz_keypoint* kps, uint8_t* desc, int* count, int cap);
 
 /* ORBextractor::ComputePyramid (src/ORBextractor.cc:1129-1150) only: builds levels on the device. */
+/* ORBextractor::operator()(Frame*, keypoints, descriptors, DSO_KEYPOINT), src/ORBextractor.cc:1031-1127 — what
+ * Frame::ExtractORB runs for frames that already carry direct-tracked points (src/Frame.cc:335-337):
+ * ComputeKeyPointsDSOSingleLevel :1277-1381 (FAST-10 of Thirdparty/fast per adaptive grid cell, thresholds 20 -> 5,
+ * ShiTomasiScore :1152-1186, three best corners per cell, cell size shrunk by 5 until nfeatures are found) on level 0,
+ * then descriptors of the n_existing keys (angles refreshed by IC_Angle, :1377-1380) and of the new keys (size 7,
+ * octave 0).  *grid_size carries mnGridSize from frame to frame (-1 before the first frame; NULL: kept in the handle).
+ * SURVEY.md §8(f) rank 2. */
+int ygz_orb_extract_frame_dso(ygz_orb* h, const uint8_t* image, int row_stride, int n_existing, ygz_keypoint* kps,
+                              uint8_t* desc, int* count, int cap, int* grid_size);
 int ygz_orb_compute_pyramid(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride);
 /* mvImagePyramid[level] of frame f (include/ORBextractor.h:106), continuous w*h bytes (step == cols,
  * as Frame clones it, src/Frame.cc:810-813).  border > 0 additionally reproduces the EDGE_THRESHOLD

@@ -83,6 +83,27 @@ int orc_extract_frame(orc_extractor* h, const uint8_t* img, int w, int hh, int s
     return emit(k, d, kps, desc, cap);
 }
 
+int orc_extract_frame_dso(orc_extractor* h, const uint8_t* img, int w, int hh, int stride, int n_existing,
+                          orc_keypoint* kps, uint8_t* desc, int cap, int* grid_size) {
+    std::vector<KeyPoint> k((KeyPoint*)kps, (KeyPoint*)kps + n_existing);
+    std::vector<uint8_t> d;
+    h->ex.ComputePyramid(img, w, hh, stride);
+    if (grid_size) h->ex.mnGridSize = *grid_size;
+    h->ex.extract_frame_dso(k, d);
+    if (grid_size) *grid_size = h->ex.mnGridSize;
+    return emit(k, d, kps, desc, cap);
+}
+
+int orc_fast10_detect_cell(const uint8_t* img, int w, int hh, int stride, int barrier, short* xy, int cap) {
+    std::vector<std::pair<int, int>> c;
+    orc::fast10_detect_cell(img, w, hh, stride, barrier, c);
+    const int n = (int)c.size();
+    for (int i = 0; i < n && i < cap; i++) { xy[2 * i] = (short)c[i].first; xy[2 * i + 1] = (short)c[i].second; }
+    return n;
+}
+
+float orc_shi_tomasi(orc_extractor* h, int u, int v) { return h->ex.ShiTomasiScore(h->ex.pyramid[0], u, v); }
+
 int orc_level_size(orc_extractor* h, int level, int* w, int* hh) {
     if (level < 0 || level >= h->ex.nlevels) return -1;
     *w = h->ex.pyramid[level].w;

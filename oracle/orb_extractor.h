@@ -9,6 +9,7 @@
 //   * Frame::N (uninitialised in the reference) := number of pre-existing keys passed in.
 #pragma once
 #include "cvprims.h"
+#include <utility>
 #include <vector>
 
 namespace orc {
@@ -60,9 +61,23 @@ public:
     // src/ORBextractor.cc:105-149
     void computeOrbDescriptor(const KeyPoint& kp, const Image& im, uint8_t* desc) const;
 
+    // ---- YGZ "DSO" key points, oracle/dso_detect.cpp
+    int mnGridSize = -1;                                // adaptive cell size, carried from frame to frame (:1295-1381)
+    // src/ORBextractor.cc:1152-1186
+    float ShiTomasiScore(const Image& img, int u, int v) const;
+    // src/ORBextractor.cc:1277-1381 (level-0 key points, size 7; also refreshes the angles of exist_kps)
+    void ComputeKeyPointsDSOSingleLevel(std::vector<KeyPoint>& allKeypoints, std::vector<KeyPoint>& exist_kps);
+    // src/ORBextractor.cc:1031-1127 with DSO_KEYPOINT
+    void extract_frame_dso(std::vector<KeyPoint>& keypoints, std::vector<uint8_t>& descriptors);
+    void blur_all_public() { blur_all(); }
+
 private:
     void blur_all();
 };
+
+// FAST-10 of Thirdparty/fast as the reference calls it on a w x h window (plain below 22 px width, SSE2 region otherwise)
+bool fast10_is_corner(const uint8_t* p, int stride, int barrier);
+void fast10_detect_cell(const uint8_t* img, int w, int h, int stride, int barrier, std::vector<std::pair<int, int>>& out);
 
 extern const int ORB_PATTERN[256 * 4];
 

@@ -30,6 +30,15 @@ int  orc_extract(orc_extractor*, const uint8_t* img, int w, int h, int stride, o
 int  orc_extract_frame(orc_extractor*, const uint8_t* img, int w, int h, int stride, int n_existing,
                        orc_keypoint* kps, uint8_t* desc, int cap);
 /* stage outputs of the last extract call */
+/* operator()(Frame*, ..., DSO_KEYPOINT) :1031-1127 = ComputeKeyPointsDSOSingleLevel :1277-1381 + descriptors.  kps holds the
+ * n_existing direct-tracked keys on entry (their angles are refreshed, :1377-1380) and all keys on return;
+ * *grid_size is mnGridSize before / after the call (-1 = first frame). */
+int  orc_extract_frame_dso(orc_extractor*, const uint8_t* img, int w, int h, int stride, int n_existing,
+                           orc_keypoint* kps, uint8_t* desc, int cap, int* grid_size);
+/* fast::fast_corner_detect_10_sse2 semantics on a w x h window inside a larger image (Thirdparty/fast) */
+int  orc_fast10_detect_cell(const uint8_t* img, int w, int h, int stride, int barrier, short* xy, int cap);
+/* ShiTomasiScore(mvImagePyramid[0], u, v) :1152-1186 (after a ComputePyramid / extract call) */
+float orc_shi_tomasi(orc_extractor*, int u, int v);
 int  orc_level_size(orc_extractor*, int level, int* w, int* h);
 int  orc_get_level(orc_extractor*, int level, int blurred, uint8_t* out);
 int  orc_get_candidates(orc_extractor*, int level, orc_keypoint* out, int cap);

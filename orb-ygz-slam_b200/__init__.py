@@ -86,7 +86,8 @@ class Counters(C.Structure):
 ABI_SYMBOLS = [
     "ygz_last_error", "ygz_device_count", "ygz_device_info",
     "ygz_orb_create", "ygz_orb_destroy", "ygz_orb_tables", "ygz_orb_level_size", "ygz_orb_max_keypoints",
-    "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_compute_pyramid", "ygz_orb_get_level",
+    "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_extract_frame_dso",
+    "ygz_orb_compute_pyramid", "ygz_orb_get_level",
     "ygz_orb_upload", "ygz_orb_run", "ygz_orb_download", "ygz_orb_sync", "ygz_orb_get_candidates",
     "ygz_orb_time", "ygz_debug_cos_sin", "ygz_orb_device_outputs", "ygz_orb_device_level", "ygz_orb_stream", "ygz_orb_counters",
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
@@ -125,6 +126,7 @@ def lib():
     sigs.setdefault('ygz_orb_max_keypoints', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_orb_extract', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     sigs.setdefault('ygz_orb_extract_frame', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, i32p, C.c_int]
+    sigs.setdefault('ygz_orb_extract_frame_dso', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, i32p, C.c_int, i32p]
     sigs.setdefault('ygz_orb_compute_pyramid', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
     sigs.setdefault('ygz_orb_get_level', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     sigs.setdefault('ygz_orb_upload', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
@@ -282,6 +284,21 @@ class ORBextractor:
         _check(self.L.ygz_orb_extract_frame(self.h, image.ctypes.data, image.strides[0], ne, kps.ctypes.data,
                                             desc.ctypes.data, C.byref(cnt), cap), "ygz_orb_extract_frame")
         return kps[:cnt.value].copy(), desc[:cnt.value].copy()
+
+    def extract_frame_dso(self, image, existing, grid_size=-1, cap=None):
+        """operator()(Frame*, keys, desc, DSO_KEYPOINT): returns (keypoints incl. the existing ones with refreshed angles,
+        descriptors, mnGridSize after the call).  grid_size = mnGridSize before the call (-1: first frame)."""
+        image = self._imgs(image)[0]
+        ne = len(existing)
+        cap = cap or (3 * (image.shape[0] // 7) * (image.shape[1] // 7) + ne)
+        kps = np.zeros(cap, KP_DTYPE)
+        kps[:ne] = existing
+        desc = np.zeros((cap, 32), np.uint8)
+        cnt = C.c_int()
+        g = C.c_int(int(grid_size))
+        _check(self.L.ygz_orb_extract_frame_dso(self.h, image.ctypes.data, image.strides[0], ne, kps.ctypes.data,
+                                                desc.ctypes.data, C.byref(cnt), cap, C.byref(g)), "ygz_orb_extract_frame_dso")
+        return kps[:cnt.value].copy(), desc[:cnt.value].copy(), g.value
 
     def ComputePyramid(self, images):
         images = self._imgs(images)

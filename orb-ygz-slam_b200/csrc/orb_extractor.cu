@@ -2,6 +2,7 @@
 // ORBextractor constructor and cell loop (src/ORBextractor.cc:412-470, 725-762, 1129-1133), device
 // buffers, kernel launches and the extern "C" entry points declared in include/ygz_b200.h.
 #include "orb_kernels.cuh"
+#include "dso_kernels.cuh"
 #include "trig_glibc.cuh"
 #include <algorithm>
 #include <cmath>
@@ -64,6 +65,15 @@ struct ygz_orb {
     int oct_node_smem = 0, oct_key_cache = 0;
     int launches_per_run = 0;
     ygz_counters ctr = {};
+    // DSO key-point selection (ygz_orb_extract_frame_dso): occupancy map, per-cell winners, compacted list, mnGridSize
+    uint8_t* d_occ = nullptr;
+    uint32_t* d_cell_keys = nullptr;
+    uint8_t* d_cell_cnt = nullptr;
+    uint32_t* d_dso_keys = nullptr;
+    int* d_dso_total = nullptr;
+    float2* d_dso_pts = nullptr;
+    int dso_pts_cap = 0;
+    int dso_grid = -1;
     int last_n = 0;
 };
 
@@ -99,6 +109,7 @@ static int orb_free(ygz_orb* h) {
     cudaSetDevice(h->device);
     for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_blur); cudaFree(L.d_tx); cudaFree(L.d_ty); }
     cudaFree(h->d_blur_tiles);
+    cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_pts);
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing); cudaFree(h->d_pattern);
@@ -595,6 +606,121 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
     if (*count > 0)
         YGZ_CUDA_TRY(cudaMemcpyAsync(desc, h->d_desc, (size_t)(*count) * 32, cudaMemcpyDeviceToHost, h->stream));
     YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->ctr.keypoints += *count;
+    return YGZ_OK;
+}
+
+// operator()(Frame*, keypoints, descriptors, DSO_KEYPOINT), src/ORBextractor.cc:1031-1127: ComputeKeyPointsDSOSingleLevel
+// (:1277-1381) on level 0 + descriptors of the pre-existing and the new keys.  One frame per call: the adaptive cell size
+// mnGridSize is state carried from frame to frame (*grid_size in/out; NULL = the handle keeps it).
+int ygz_orb_extract_frame_dso(ygz_orb* h, const uint8_t* image, int row_stride, int n_existing, ygz_keypoint* kps, uint8_t* desc,
+                              int* count, int cap, int* grid_size) {
+    YGZ_ARG_CHECK(h && image && kps && desc && count && n_existing >= 0 && cap >= n_existing);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const int W = h->cfg.width, H = h->cfg.height, n = h->cfg.nfeatures;
+    const LevelHost& L0 = h->lv[0];
+    const int max_cells = (H / 7) * (W / 7);
+    if (!h->d_occ) {
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_occ, (size_t)W * H));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_cell_keys, (size_t)std::max(max_cells, 1) * 3 * 4));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_cell_cnt, (size_t)std::max(max_cells, 1)));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_keys, (size_t)std::max(max_cells, 1) * 3 * 4));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_total, 4));
+        YGZ_CUDA_TRY(cudaFuncSetAttribute(k_dso_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, DSO_WARPS * dso_warp_smem(DSO_GMAX)));
+    }
+    int rc;
+    if ((rc = ygz_orb_upload(h, image, 1, (size_t)row_stride * H, row_stride))) return rc;
+    if (n_existing > h->existing_cap) {
+        cudaFree(h->d_existing); h->d_existing = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_existing, (size_t)n_existing * sizeof(ExistingKey)));
+        h->existing_cap = n_existing;
+    }
+    if (n_existing > h->dso_pts_cap) {
+        cudaFree(h->d_dso_pts); h->d_dso_pts = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_pts, (size_t)n_existing * sizeof(float2)));
+        h->dso_pts_cap = n_existing;
+    }
+    std::vector<ExistingKey> ek(n_existing);
+    std::vector<float2> pts(n_existing);
+    for (int i = 0; i < n_existing; i++) {
+        const int oct = kps[i].octave;
+        if (oct < 0 || oct >= h->cfg.nlevels) { set_last_error("existing key octave out of range"); return YGZ_ERR_ARG; }
+        ek[i].x = kps[i].x * h->inv_scale[oct];        // kp.pt * mvInvScaleFactor[kp.octave], :1095 and :1379
+        ek[i].y = kps[i].y * h->inv_scale[oct];
+        ek[i].angle = kps[i].angle;
+        ek[i].octave = oct;
+        pts[i] = make_float2(kps[i].x, kps[i].y);
+    }
+    YGZ_CUDA_TRY(cudaMemsetAsync(h->d_occ, 0, (size_t)W * H, h->stream));
+    if (n_existing) {
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_existing, ek.data(), (size_t)n_existing * sizeof(ExistingKey), cudaMemcpyHostToDevice, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_dso_pts, pts.data(), (size_t)n_existing * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+        k_dso_mark_occupancy<<<ceil_div(n_existing, 256), 256, 0, h->stream>>>(h->d_dso_pts, n_existing, h->d_occ, W, H);
+    }
+    if ((rc = launch_pyramid(h, 1))) return rc;
+    if ((rc = launch_blur(h, 1))) return rc;
+    int launches = (h->cfg.nlevels - 1) + 1 + (n_existing > 0);
+    // ---- the while (cnt < n) loop of :1300-1371, one device pass per cell size
+    int g = grid_size ? *grid_size : h->dso_grid;
+    if (g < 0) g = static_cast<int>(std::sqrt(1.0 * H * W / n));
+    int cnt = 0;
+    while (cnt < n) {
+        if (cnt > 0) {
+            g -= 5;
+            if (g < 7) { g = 7; break; }
+        }
+        if (g < 7 || g > DSO_GMAX) { set_last_error("DSO grid size outside [7, 96]"); return YGZ_ERR_ARG; }
+        DsoParams D;
+        D.img = L0.d_base; D.occ = h->d_occ; D.w = W; D.h = H; D.pitch = L0.pitch;
+        D.g = g; D.n_rows = H / g; D.n_cols = W / g;
+        const int cells = D.n_rows * D.n_cols;
+        cnt = 0;
+        if (cells > 0) {
+            const int ws = dso_warp_smem(g);
+            k_dso_cells<<<ceil_div(cells, DSO_WARPS), DSO_WARPS * 32, (size_t)DSO_WARPS * ws, h->stream>>>(D, h->d_cell_keys, h->d_cell_cnt, ws);
+            k_dso_compact<<<1, 1024, 0, h->stream>>>(h->d_cell_keys, h->d_cell_cnt, cells, h->d_dso_keys, h->d_dso_total);
+            YGZ_CUDA_TRY(cudaGetLastError());
+            YGZ_CUDA_TRY(cudaMemcpyAsync(&cnt, h->d_dso_total, 4, cudaMemcpyDeviceToHost, h->stream));
+            YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+            launches += 2;
+        }
+        if (cnt == 0) break;       // the reference would spin forever on a frame without corners; the oracle stops here
+    }
+    if (cnt > n) g += 5;           // :1373-1375
+    if (grid_size) *grid_size = g;
+    h->dso_grid = g;
+    // ---- descriptors: existing keys (angles refreshed, :1377-1380) then the new level-0 keys
+    if (n_existing + cnt > h->P.out_cap) {
+        const int B = h->cfg.max_batch, oc = n_existing + cnt;
+        cudaFree(h->d_kps); cudaFree(h->d_desc);
+        h->d_kps = nullptr; h->d_desc = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_kps, (size_t)oc * B * sizeof(ygz_keypoint)));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_desc, (size_t)oc * B * 32));
+        h->P.out_cap = oc;
+    }
+    *count = n_existing + cnt;
+    if (*count > cap) { set_last_error("keypoint buffer too small"); return YGZ_ERR_CAPACITY; }
+    if (n_existing > 0) {
+        k_orient_describe<<<dim3(ceil_div(n_existing, DESC_WARPS), 1), DESC_THREADS, 0, h->stream>>>(
+            h->P, h->patch, 3, n_existing, n_existing, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing, h->d_kps, h->d_desc, h->d_counts);
+        launches++;
+    }
+    if (cnt > 0) {
+        k_orient_describe<<<dim3(ceil_div(cnt, DESC_WARPS), 1), DESC_THREADS, 0, h->stream>>>(
+            h->P, h->patch, 2, n_existing, cnt, h->d_pattern, h->d_dso_keys, h->d_nsel, nullptr, h->d_kps, h->d_desc, h->d_counts);
+        launches++;
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    if (*count > 0) {
+        std::vector<ygz_keypoint> tmp((size_t)*count);
+        YGZ_CUDA_TRY(cudaMemcpyAsync(tmp.data(), h->d_kps, (size_t)(*count) * sizeof(ygz_keypoint), cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpyAsync(desc, h->d_desc, (size_t)(*count) * 32, cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < n_existing; i++) kps[i].angle = tmp[i].angle;
+        for (int i = n_existing; i < *count; i++) kps[i] = tmp[i];
+    }
+    h->ctr.kernel_launches += launches;
+    h->ctr.frames += 1;
     h->ctr.keypoints += *count;
     return YGZ_OK;
 }

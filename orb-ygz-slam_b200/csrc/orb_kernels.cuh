@@ -870,7 +870,9 @@ __device__ void ref_cos_sin(float angle_rad, float* c, float* s);
 
 struct ExistingKey { float x, y, angle; int octave; };   // pt * mvInvScaleFactor[octave], :1094-1095
 
-// mode 0: keys selected by k_octree (angle computed);  mode 1: pre-existing keys (angle kept, :1088-1099)
+// mode 0: keys selected by k_octree (angle computed);  mode 1: pre-existing keys (angle kept, :1088-1099);
+// mode 2: level-0 keys of ComputeKeyPointsDSOSingleLevel (flat list of x | y << 12, angle computed, size 7, :1363-1367);
+// mode 3: pre-existing keys whose angle that function refreshes (:1377-1380) — only the angle is written back
 // lane = patch column for the IC moments (31 coalesced bytes per row), then lane j = descriptor byte j: 16 gathers
 // from the blurred level, all independent, so the memory system sees 512 loads in flight per warp.
 __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __grid_constant__ OrbParams P,
@@ -916,6 +918,13 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
         cy = cand_y(c) + MIN_BORDER;
         score = cand_s(c);
         out_idx = before + slot;
+    } else if (mode == 2) {
+        const uint32_t c = sel_all[item];
+        level = 0;
+        cx = (int)(c & 0xFFFu);
+        cy = (int)((c >> 12) & 0xFFFu);
+        out_idx = n_existing + item;
+        if (item == 0 && lane == 0) counts_out[frame] = n_existing + n_items;
     } else {
         const ExistingKey ek = existing[(size_t)frame * n_existing + item];
         level = ek.octave;
@@ -938,7 +947,7 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
         // zero-filled by the TMA unit and never read.
         const int xa16 = x0 & ~15;
         shift = x0 - xa16;
-        const bool with_raw = mode == 0;                           // raw 31-row box for IC_Angle rides on the same barrier
+        const bool with_raw = mode != 1;                           // raw 31-row box for IC_Angle rides on the same barrier
         if (elect_one()) {
             mbar_init(&tma_bar[warp], 1);
             mbar_expect_tx(&tma_bar[warp], with_raw ? (PW + ICW) * PBOX : PW * PBOX);
@@ -955,8 +964,8 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
         }
         __syncwarp();
     }
-    // ---- IC_Angle on the raw level: lane = column u, loop over rows v (keys of mode 0 are >= 19 px inside)
-    if (mode == 0) {
+    // ---- IC_Angle on the raw level: lane = column u, loop over rows v (keys of modes 0 and 2 are >= 19 px inside)
+    if (mode != 1) {
         const uint8_t* c0 = L.base + (size_t)frame * L.frame_stride + (size_t)cy * L.pitch + cx;
         int m10 = 0, m01 = 0;
         const int u = lane - HALF_PATCH;                        // lanes 0..30 <-> u = -15..15
@@ -974,12 +983,15 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
                 m01 += v * I;
             }
             m10 = u * colsum;
-        } else if (lane < 31) {
+        } else if (lane < 31) {                                   // small level, or a pre-existing key near the border (REFLECT_101)
             const int au = abs(u);
+            const bool in15 = cx >= HALF_PATCH && cy >= HALF_PATCH && cx + HALF_PATCH < L.w && cy + HALF_PATCH < L.h;
+            const uint8_t* img0 = L.base + (size_t)frame * L.frame_stride;
 #pragma unroll 4
             for (int v = -HALF_PATCH; v <= HALF_PATCH; v++) {
                 if (au <= P.umax[abs(v)]) {
-                    const int I = __ldg(c0 + v * L.pitch + u);
+                    const int I = in15 ? (int)__ldg(c0 + v * L.pitch + u)
+                                       : (int)img0[(size_t)reflect101(cy + v, L.h) * L.pitch + reflect101(cx + u, L.w)];
                     m10 += u * I;
                     m01 += v * I;
                 }
@@ -1000,7 +1012,7 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
         a = __shfl_sync(0xffffffffu, ca, 0);
         b = __shfl_sync(0xffffffffu, sb, 0);
     }
-    if (by_tma && mode != 0) mbar_wait(&tma_bar[warp], 0);
+    if (by_tma && mode == 1) mbar_wait(&tma_bar[warp], 0);
     // ---- lane j evaluates tests 8j..8j+7 = descriptor byte j (:118-145) on the blurred patch
     {
         const uint8_t* ctr = G + PR * PBOX + PR + shift;
@@ -1020,6 +1032,12 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
             byte |= (t0 < t1) << j;
         }
         desc_out[((size_t)frame * P.out_cap + out_idx) * 32 + lane] = (uint8_t)byte;
+    }
+    if (lane == 0 && mode == 3) kps_out[(size_t)frame * P.out_cap + out_idx].angle = angle;
+    if (lane == 0 && mode == 2) {
+        ygz_keypoint kp;           // cv::KeyPoint(Point2f(x, y), 7): response 0, octave 0, class_id -1
+        kp.x = (float)cx; kp.y = (float)cy; kp.size = 7.f; kp.angle = angle; kp.response = 0.f; kp.octave = 0; kp.class_id = -1;
+        kps_out[(size_t)frame * P.out_cap + out_idx] = kp;
     }
     if (lane == 0 && mode == 0) {
         ygz_keypoint kp;

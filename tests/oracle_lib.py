@@ -73,6 +73,9 @@ def lib(native=False):
     L.orc_extractor_destroy.argtypes = [C.c_void_p]
     L.orc_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
     L.orc_extract_frame.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.orc_extract_frame_dso.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int, i32p]
+    L.orc_shi_tomasi.restype = C.c_float
+    L.orc_shi_tomasi.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.orc_level_size.argtypes = [C.c_void_p, C.c_int, i32p, i32p]
     L.orc_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p]
     L.orc_get_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
@@ -162,6 +165,19 @@ class Extractor:
                                      kps.ctypes.data, _ptr(desc, u8p), cap)
         assert n >= 0, n
         return kps[:n].copy(), desc[:n].copy()
+
+    def extract_frame_dso(self, img, existing, grid_size=-1, cap=None):
+        img = np.ascontiguousarray(img, np.uint8)
+        ne = len(existing)
+        cap = cap or (3 * (img.shape[0] // 7) * (img.shape[1] // 7) + ne)
+        kps = np.zeros(cap, KP_DTYPE)
+        kps[:ne] = existing
+        desc = np.zeros((cap, 32), np.uint8)
+        g = C.c_int(int(grid_size))
+        n = self.L.orc_extract_frame_dso(self.h, _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0], ne,
+                                         kps.ctypes.data, _ptr(desc, u8p), cap, C.byref(g))
+        assert n >= 0, n
+        return kps[:n].copy(), desc[:n].copy(), g.value
 
     def level_size(self, level):
         w, h = C.c_int(), C.c_int()
