@@ -256,6 +256,16 @@ int ygz_sia_last_trace(ygz_sia* h, int problem, float* out, int cap, int* n);
 int ygz_sia_time(ygz_sia* h, int n_problems, int max_level, int min_level, int n_iter, float eps, int iters,
                  float* ms);
 
+/* ------------------------------------------------------------------ stereo association
+ * Frame::ComputeStereoMatches, /root/reference/src/Frame.cc:509-682: for every left key point the
+ * best right key point of the row band (Hamming, compatible octave, disparity in [0, mbf/mb]), an 11x11 SAD sliding
+ * window of +-5 px on the key's pyramid level, parabola refinement, then the median-based outlier cut.  The pyramids are
+ * read in place from the two extractor handles (frame `frame` of their last batch).  Outputs mvuRight / mvDepth
+ * (-1 = no match); returns the number of stereo matches or a negative ygz_status. */
+int ygz_compute_stereo_matches(ygz_orb* left, ygz_orb* right, int frame, const ygz_keypoint* keysL, const uint8_t* descL, int N,
+                               const ygz_keypoint* keysR, const uint8_t* descR, int Nr, float mb, float mbf,
+                               float* mvuRight, float* mvDepth);
+
 /* ------------------------------------------------------------------ direct (patch) projection search
  * ORBmatcher::FindDirectProjection(KeyFrame* ref, Frame* curr, MapPoint* mp,
  * Vector2f& px_curr, int& search_level), /root/reference/src/ORBmatcher.cc:1575-1602, with GetWarpAffineMatrix

@@ -153,6 +153,14 @@ int orc_find_direct_projection(const orc_direct_frame* refs, int n_refs, const o
                                const float* K4, const float* scale, const float* inv_scale,
                                float inv_level_sigma2_1, int nlevels, const orc_direct_item* items,
                                int n_items, float* out_px, int* out_level, uint8_t* out_ok);
+/* Frame::ComputeStereoMatches src/Frame.cc:509-682.  pyrL / pyrR: the two extractors'
+ * mvImagePyramid (pose fields unused); keys in level-0 pixels.  Outputs mvuRight / mvDepth (-1 = no match); returns the
+ * number of matched left key points. */
+int orc_compute_stereo_matches(const orc_direct_frame* pyrL, const orc_direct_frame* pyrR, int nlevels,
+                               const orc_keypoint* keysL, const uint8_t* descL, int N,
+                               const orc_keypoint* keysR, const uint8_t* descR, int Nr,
+                               const float* mvScaleFactors, const float* mvInvScaleFactors, float mb, float mbf,
+                               float* mvuRight, float* mvDepth);
 /* CPU front-end baseline: extractor + SearchByBoW vs previous frame, `threads` std::threads (bench.py) */
 long orc_frontend_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs,
                         int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints,

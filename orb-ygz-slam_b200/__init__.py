@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
     "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
-    "ygz_find_direct_projection", "ygz_direct_time",
+    "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
 ]
 
 _lib = None
@@ -152,6 +152,7 @@ def lib():
     sigs.setdefault('ygz_search_by_projection_kf', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), u8p, C.c_float, C.c_int]
     sigs.setdefault('ygz_search_for_initialization', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, i32p, C.c_int]
     sigs.setdefault('ygz_search_by_bow_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, u32p, i32p, i32p]
+    sigs.setdefault('ygz_compute_stereo_matches', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p]
     sigs.setdefault('ygz_direct_create', {})['argtypes'] = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
     sigs.setdefault('ygz_direct_destroy', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_direct_upload_frame', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(DirectFrame), C.c_int]
@@ -598,6 +599,20 @@ def make_sia_problem(ref_levels, cur_levels, inv_scale, K, ref_px, world_xyz, va
     v.cur_q = (C.c_float * 4)(*cq)
     v.cur_t = (C.c_float * 3)(*ct)
     return _Keep(v, [ref_levels, cur_levels, lw, lh, isf, px, xyz, val, refp, curp])
+
+
+def ComputeStereoMatches(ex_left, ex_right, keysL, descL, keysR, descR, mb, mbf, frame=0):
+    """Frame::ComputeStereoMatches (src/Frame.cc:509-682) on the pyramids held by two ORBextractor handles.
+    Returns (mvuRight[N], mvDepth[N], n_matches)."""
+    keysL = np.ascontiguousarray(keysL, KP_DTYPE); keysR = np.ascontiguousarray(keysR, KP_DTYPE)
+    descL = np.ascontiguousarray(descL, np.uint8); descR = np.ascontiguousarray(descR, np.uint8)
+    u = np.zeros(len(keysL), np.float32); z = np.zeros(len(keysL), np.float32)
+    n = lib().ygz_compute_stereo_matches(ex_left.h, ex_right.h, frame, keysL.ctypes.data, descL.ctypes.data, len(keysL),
+                                         keysR.ctypes.data, descR.ctypes.data, len(keysR), float(mb), float(mbf),
+                                         _ptr(u, f32p), _ptr(z, f32p))
+    if n < 0:
+        _check(n, "ygz_compute_stereo_matches")
+    return u, z, n
 
 
 def make_direct_frame(levels, q=(0, 0, 0, 1), t=(0, 0, 0), cls=None):

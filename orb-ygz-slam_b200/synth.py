@@ -217,3 +217,18 @@ def synth_direct_scene(seed, n_kf=3, n_items=300, w=752, h=480, K=EUROC_K, depth
         px_true[i] = uv
     return dict(kf_imgs=kf_imgs, kf_poses=kf_poses, cur_img=cur_img, cur_pose=cur_pose, items=items, px_true=px_true,
                 K=K, nlevels=nlevels, scale=scale)
+
+
+def synth_stereo_pair(seed, w=752, h=480, disparities=(6, 14, 25), noise=2):
+    """Rectified pair: the right image is the left one shifted by a per-band disparity (uR = uL - d), plus small
+    integer noise.  Returns (left, right, band_of_row[h], disparities)."""
+    left = synth_frame(seed, w + max(disparities) + 4, h)
+    rng = np.random.default_rng(seed + 15485863)
+    right = np.empty((h, w), np.uint8)
+    band = np.minimum(np.arange(h) * len(disparities) // h, len(disparities) - 1)
+    for y in range(h):
+        d = disparities[band[y]]
+        right[y] = left[y, d:d + w]
+    if noise:
+        right = np.clip(right.astype(np.int32) + rng.integers(-noise, noise + 1, right.shape), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(left[:, :w]), np.ascontiguousarray(right), band, tuple(disparities)

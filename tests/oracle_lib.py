@@ -317,3 +317,19 @@ def find_direct_projection(ref_frames, cur_frame, K, scale, inv_scale, inv_level
                                       px.ctypes.data_as(f32p), lvl.ctypes.data_as(i32p), ok.ctypes.data_as(u8p))
     assert rc == 0, rc
     return px, lvl, ok
+
+
+def compute_stereo_matches(pyrL, pyrR, keysL, descL, keysR, descR, scale, inv_scale, mb, mbf):
+    """Oracle Frame::ComputeStereoMatches.  pyrL / pyrR: _Keep(DirectFrame) built by make_direct_frame (poses unused)."""
+    L = lib()
+    L.orc_compute_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_int, f32p, f32p, C.c_float, C.c_float, f32p, f32p]
+    keysL = np.ascontiguousarray(keysL, KP_DTYPE); keysR = np.ascontiguousarray(keysR, KP_DTYPE)
+    descL = np.ascontiguousarray(descL, np.uint8); descR = np.ascontiguousarray(descR, np.uint8)
+    scale = np.ascontiguousarray(scale, np.float32); inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    u = np.zeros(len(keysL), np.float32); z = np.zeros(len(keysL), np.float32)
+    n = L.orc_compute_stereo_matches(C.cast(C.pointer(pyrL.struct), C.c_void_p), C.cast(C.pointer(pyrR.struct), C.c_void_p), len(scale),
+                                     keysL.ctypes.data, descL.ctypes.data, len(keysL), keysR.ctypes.data, descR.ctypes.data, len(keysR),
+                                     scale.ctypes.data_as(f32p), inv_scale.ctypes.data_as(f32p), float(mb), float(mbf),
+                                     u.ctypes.data_as(f32p), z.ctypes.data_as(f32p))
+    return u, z, n
