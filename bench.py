@@ -261,6 +261,19 @@ def aux_metrics(m, device):
                                     "items_per_s": 16384 / dt, "success_rate": float(ok.mean())}
     except Exception as e:
         aux["direct_projection"] = {"error": str(e)[:200]}
+    try:
+        # Frame::ComputeBoW for a batch: vocabulary descent of every descriptor the extractor holds on the device
+        voc = m.ORBVocabulary(data=synth.synth_vocabulary(1, k=10, L=5), device=device)
+        Bv = 64
+        exv = m.ORBextractor(width=W, height=H, max_batch=Bv, device=device, **ORB)
+        exv.upload(make_frames(77, Bv)); exv.run(Bv); exv.sync()
+        voc.transform_orb(exv, Bv, 4, want=(), timed=True)
+        r = voc.transform_orb(exv, Bv, 4, want=(), timed=True)
+        nd = int(exv.download(Bv)[2].sum())
+        aux["vocab_transform"] = {"vocabulary": "synthetic k=10 L=5 (101 k nodes)", "frames": Bv, "descriptors": nd,
+                                  "ms_kernel": r["ms"], "descriptors_per_s": nd / (r["ms"] / 1e3)}
+    except Exception as e:
+        aux["vocab_transform"] = {"error": str(e)[:200]}
     return aux
 
 

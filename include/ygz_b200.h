@@ -256,6 +256,25 @@ int ygz_sia_last_trace(ygz_sia* h, int problem, float* out, int cap, int* n);
 int ygz_sia_time(ygz_sia* h, int n_problems, int max_level, int min_level, int n_iter, float eps, int iters,
                  float* ms);
 
+/* ------------------------------------------------------------------ bag-of-words vocabulary
+ * the DBoW2 ORB vocabulary of Frame::ComputeBoW (src/Frame.cc:495-501):
+ * TemplatedVocabulary::loadFromBinaryFile (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1478-1522; ORBvoc.bin: 24-byte
+ * header {nb_nodes, size_node = 41, k, L, scoring, weighting} + records {i32 parent, u8 desc[32], f32 weight, u8 is_leaf})
+ * and transform(feature, word_id, weight, &nid, levelsup) (:1249-1282) for batches of descriptors.  The BowVector /
+ * FeatureVector assembly (std::map inserts, :1151-1227) is a per-frame host step over these arrays (see the C++ and
+ * Python mirrors). */
+typedef struct ygz_vocab ygz_vocab;
+int ygz_vocab_load(const char* path, int device, ygz_vocab** out);
+int ygz_vocab_from_memory(const uint8_t* buf, size_t bytes, int device, ygz_vocab** out);
+int ygz_vocab_destroy(ygz_vocab* v);
+int ygz_vocab_info(const ygz_vocab* v, int* k, int* L, int* scoring, int* weighting, int* n_nodes, int* n_words);
+/* per descriptor: word id (leaf index), its weight (0 = stopped word), node id at level L - levelsup */
+int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, int* word_id, float* weight, int* node_id);
+/* the same for the descriptors an extractor holds on the device (last batch, n_frames frames, zero copy); outputs are
+ * [n_frames][ygz_orb_max_keypoints] (NULL to skip one); ms (optional) = device time of the kernel */
+int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levelsup, int* word_id, float* weight, int* node_id,
+                            float* ms);
+
 /* ------------------------------------------------------------------ stereo association
  * Frame::ComputeStereoMatches, /root/reference/src/Frame.cc:509-682: for every left key point the
  * best right key point of the row band (Hamming, compatible octave, disparity in [0, mbf/mb]), an 11x11 SAD sliding

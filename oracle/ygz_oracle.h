@@ -2,6 +2,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (libygz_b200.so) never links or calls it. */
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -161,6 +162,15 @@ int orc_compute_stereo_matches(const orc_direct_frame* pyrL, const orc_direct_fr
                                const orc_keypoint* keysR, const uint8_t* descR, int Nr,
                                const float* mvScaleFactors, const float* mvInvScaleFactors, float mb, float mbf,
                                float* mvuRight, float* mvDepth);
+/* ---- DBoW2 vocabulary: loadFromBinaryFile TemplatedVocabulary.h:1478-1522, transform :1151-1292 */
+typedef struct orc_vocab orc_vocab;
+orc_vocab* orc_vocab_from_memory(const uint8_t* buf, size_t bytes);
+orc_vocab* orc_vocab_load(const char* path);
+void orc_vocab_destroy(orc_vocab*);
+void orc_vocab_info(const orc_vocab*, int* k, int* L, int* scoring, int* weighting, int* n_nodes, int* n_words);
+void orc_vocab_transform(const orc_vocab*, const uint8_t* desc, int n, int levelsup, int* word_id, float* weight, int* node_id);
+int orc_vocab_transform_bow(const orc_vocab*, const uint8_t* desc, int n, int levelsup, int* bow_ids, double* bow_vals,
+                            int* fv_nodes, int* fv_node_id, int* fv_offset, int* fv_index);
 /* CPU front-end baseline: extractor + SearchByBoW vs previous frame, `threads` std::threads (bench.py) */
 long orc_frontend_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs,
                         int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints,

@@ -97,6 +97,7 @@ ABI_SYMBOLS = [
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
+    "ygz_vocab_load", "ygz_vocab_from_memory", "ygz_vocab_destroy", "ygz_vocab_info", "ygz_vocab_transform", "ygz_vocab_transform_orb",
 ]
 
 _lib = None
@@ -153,6 +154,12 @@ def lib():
     sigs.setdefault('ygz_search_for_initialization', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, i32p, C.c_int]
     sigs.setdefault('ygz_search_by_bow_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, u32p, i32p, i32p]
     sigs.setdefault('ygz_compute_stereo_matches', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p]
+    sigs.setdefault('ygz_vocab_load', {})['argtypes'] = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    sigs.setdefault('ygz_vocab_from_memory', {})['argtypes'] = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    sigs.setdefault('ygz_vocab_destroy', {})['argtypes'] = [C.c_void_p]
+    sigs.setdefault('ygz_vocab_info', {})['argtypes'] = [C.c_void_p, i32p, i32p, i32p, i32p, i32p, i32p]
+    sigs.setdefault('ygz_vocab_transform', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, f32p, i32p]
+    sigs.setdefault('ygz_vocab_transform_orb', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, f32p, i32p, f32p]
     sigs.setdefault('ygz_direct_create', {})['argtypes'] = [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]
     sigs.setdefault('ygz_direct_destroy', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_direct_upload_frame', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(DirectFrame), C.c_int]
@@ -599,6 +606,69 @@ def make_sia_problem(ref_levels, cur_levels, inv_scale, K, ref_px, world_xyz, va
     v.cur_q = (C.c_float * 4)(*cq)
     v.cur_t = (C.c_float * 3)(*ct)
     return _Keep(v, [ref_levels, cur_levels, lw, lh, isf, px, xyz, val, refp, curp])
+
+
+class ORBVocabulary:
+    """Mirror of ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h) for the calls
+    the front end makes: loadFromBinaryFile and transform(features, BowVector, FeatureVector, levelsup)."""
+
+    def __init__(self, path=None, data=None, device=0):
+        self.L_ = lib()
+        self.h = C.c_void_p()
+        if path is not None:
+            _check(self.L_.ygz_vocab_load(str(path).encode(), device, C.byref(self.h)), "ygz_vocab_load")
+        else:
+            data = np.ascontiguousarray(np.frombuffer(data, np.uint8))
+            _check(self.L_.ygz_vocab_from_memory(data.ctypes.data, data.size, device, C.byref(self.h)), "ygz_vocab_from_memory")
+        v = [C.c_int() for _ in range(6)]
+        _check(self.L_.ygz_vocab_info(self.h, *[C.byref(x) for x in v]), "ygz_vocab_info")
+        self.k, self.L, self.scoring, self.weighting, self.n_nodes, self.n_words = [x.value for x in v]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L_.ygz_vocab_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def transform_features(self, desc, levelsup=4):
+        """per descriptor: (word_id, weight, node_id at level L - levelsup)"""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid = np.zeros(n, np.int32); w = np.zeros(n, np.float32); nid = np.zeros(n, np.int32)
+        _check(self.L_.ygz_vocab_transform(self.h, desc.ctypes.data, n, levelsup, _ptr(wid, i32p), _ptr(w, f32p), _ptr(nid, i32p)),
+               "ygz_vocab_transform")
+        return wid, w, nid
+
+    def transform(self, desc, levelsup=4):
+        """transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1151-1227, TF-IDF + L1):
+        returns (bow_ids ascending, bow_vals float64 L1-normalised, fv: dict node -> feature indices ascending)."""
+        wid, w, nid = self.transform_features(desc, levelsup)
+        keep = np.nonzero(w > 0)[0]                       # w > 0: not a stopped word
+        ids, inv = np.unique(wid[keep], return_inverse=True)
+        vals = np.zeros(len(ids), np.float64)
+        np.add.at(vals, inv, w[keep].astype(np.float64))  # addWeight in feature order (sequential double sums)
+        norm = float(np.cumsum(np.abs(vals))[-1]) if len(vals) else 0.0      # map iteration order, sequential
+        if norm > 0.0:
+            vals = vals / norm
+        fv = {}
+        for i in keep:
+            fv.setdefault(int(nid[i]), []).append(int(i))
+        return ids.astype(np.int32), vals, dict(sorted(fv.items()))
+
+    def transform_orb(self, ex, n_frames, levelsup=4, want=("node",), timed=False):
+        cap = ex.cap
+        wid = np.zeros((n_frames, cap), np.int32) if "word" in want else None
+        w = np.zeros((n_frames, cap), np.float32) if "weight" in want else None
+        nid = np.zeros((n_frames, cap), np.int32) if "node" in want else None
+        ms = C.c_float()
+        _check(self.L_.ygz_vocab_transform_orb(self.h, ex.h, n_frames, levelsup, _ptr(wid, i32p), _ptr(w, f32p), _ptr(nid, i32p),
+                                               C.byref(ms) if timed else None), "ygz_vocab_transform_orb")
+        return dict(word=wid, weight=w, node=nid, ms=ms.value)
 
 
 def ComputeStereoMatches(ex_left, ex_right, keysL, descL, keysR, descR, mb, mbf, frame=0):

@@ -1,0 +1,244 @@
+// DBoW2 vocabulary on the device — SURVEY.md §8(f) rank 4:
+//   TemplatedVocabulary::loadFromBinaryFile   /root/reference/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1478-1522
+//   TemplatedVocabulary::transform(feature, word_id, weight, &nid, levelsup)   :1249-1282
+//   FORB::distance                            Thirdparty/DBoW2/DBoW2/FORB.cpp:82-102
+// `Frame::ComputeBoW` (src/Frame.cc:495-501, levelsup = 4) turns every descriptor into a word (leaf) and the id of its
+// ancestor at level L - levelsup; the latter is the FeatureVector SearchByBoW walks.  The tree (1 082 073 nodes x 32 B
+// for ORBvoc.bin = 35 MB) stays resident in HBM/L2; one WARP descends the tree per descriptor: lanes = the k children
+// of the current node, 256-bit Hamming distance each, first-minimum by child order (the reference's strict `<`).
+#include "common.cuh"
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <vector>
+
+namespace {
+using namespace ygz_b200;
+
+struct VocabDev {
+    const uint4* desc;          // 2 x uint4 per node
+    const int* child_begin;     // CSR of children in the reference's insertion order (ascending node id)
+    const uint8_t* child_count;
+    const int* children;
+    const float* weight;
+    const int* word_id;         // -1 for inner nodes
+    int L;
+};
+
+__global__ void __launch_bounds__(256) k_vocab_transform(VocabDev V, const uint4* __restrict__ desc, size_t desc_stride_u4,
+                                                         const int* __restrict__ counts, int cap, int n_total, int levelsup,
+                                                         int* __restrict__ word_id, float* __restrict__ weight,
+                                                         int* __restrict__ node_id) {
+    // feature f = (frame, slot): frame = f / cap, slot = f % cap (cap = n_total and counts = NULL for a flat list)
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= n_total) return;
+    if (counts) {
+        const int frame = f / cap, slot = f - frame * cap;
+        if (slot >= counts[frame]) return;
+    }
+    const uint4* d = desc + (size_t)f * desc_stride_u4;
+    const uint4 a0 = d[0], a1 = d[1];
+    const int nid_level = V.L - levelsup;
+    int nid = 0, cur = 0, level = 0;
+    while (true) {
+        const int cnt = V.child_count[cur];
+        if (cnt == 0) break;
+        const int cb = V.child_begin[cur];
+        ++level;
+        int best = INT_MAX, bestc = INT_MAX;
+        for (int c = lane; c < cnt; c += 32) {
+            const int id = V.children[cb + c];
+            const uint4 b0 = V.desc[2 * (size_t)id], b1 = V.desc[2 * (size_t)id + 1];
+            const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                             __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            if (dist < best) { best = dist; bestc = c; }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const int ob = __shfl_xor_sync(0xffffffffu, best, o), oc = __shfl_xor_sync(0xffffffffu, bestc, o);
+            if (ob < best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
+        }
+        cur = V.children[cb + bestc];
+        if (level == nid_level) nid = cur;
+        if (V.word_id[cur] >= 0) break;               // isLeaf()
+    }
+    if (lane == 0) {
+        word_id[f] = V.word_id[cur];
+        weight[f] = V.weight[cur];
+        node_id[f] = nid;
+    }
+}
+
+}  // namespace
+
+struct ygz_vocab {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int k = 0, L = 0, scoring = 0, weighting = 0, n_nodes = 0, n_words = 0;
+    uint4* d_desc = nullptr;
+    int *d_child_begin = nullptr, *d_children = nullptr, *d_word = nullptr;
+    uint8_t* d_child_count = nullptr;
+    float* d_weight = nullptr;
+    // scratch for transforms
+    int cap = 0;
+    uint8_t* d_in = nullptr;
+    int *d_wid = nullptr, *d_nid = nullptr;
+    float* d_w = nullptr;
+    VocabDev dev() const { return VocabDev{d_desc, d_child_begin, d_child_count, d_children, d_weight, d_word, L}; }
+};
+
+static int vocab_free(ygz_vocab* v) {
+    if (!v) return YGZ_OK;
+    cudaSetDevice(v->device);
+    cudaFree(v->d_desc); cudaFree(v->d_child_begin); cudaFree(v->d_children); cudaFree(v->d_word); cudaFree(v->d_child_count);
+    cudaFree(v->d_weight); cudaFree(v->d_in); cudaFree(v->d_wid); cudaFree(v->d_nid); cudaFree(v->d_w);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+    return YGZ_OK;
+}
+
+static int vocab_scratch(ygz_vocab* v, int n, bool with_input) {
+    if (n <= v->cap) return YGZ_OK;
+    cudaFree(v->d_in); cudaFree(v->d_wid); cudaFree(v->d_nid); cudaFree(v->d_w);
+    v->d_in = nullptr; v->d_wid = v->d_nid = nullptr; v->d_w = nullptr; v->cap = 0;
+    (void)with_input;
+    YGZ_CUDA_TRY(cudaMalloc(&v->d_in, (size_t)n * 32));
+    YGZ_CUDA_TRY(cudaMalloc(&v->d_wid, (size_t)n * 4));
+    YGZ_CUDA_TRY(cudaMalloc(&v->d_nid, (size_t)n * 4));
+    YGZ_CUDA_TRY(cudaMalloc(&v->d_w, (size_t)n * 4));
+    v->cap = n;
+    return YGZ_OK;
+}
+
+extern "C" {
+
+int ygz_vocab_from_memory(const uint8_t* buf, size_t bytes, int device, ygz_vocab** out) {
+    YGZ_ARG_CHECK(buf && out && bytes >= 24);
+    if (ygz_device_count() <= device) { set_last_error("no such CUDA device"); return YGZ_ERR_NO_DEVICE; }
+    unsigned nb_nodes, size_node;
+    int k, L, scoring, weighting;
+    std::memcpy(&nb_nodes, buf, 4); std::memcpy(&size_node, buf + 4, 4); std::memcpy(&k, buf + 8, 4); std::memcpy(&L, buf + 12, 4);
+    std::memcpy(&scoring, buf + 16, 4); std::memcpy(&weighting, buf + 20, 4);
+    if (size_node != 41) { set_last_error("vocabulary: size_node != 41 (not an ORB binary vocabulary)"); return YGZ_ERR_ARG; }
+    const size_t nrec = (bytes - 24) / size_node, n = nrec + 1;
+    // each record once (the reference's eof loop re-reads the last one; the duplicate child can never be selected)
+    std::vector<int> parent(n, 0), word(n, -1), cbegin(n, 0), children(nrec > 0 ? nrec : 1);
+    std::vector<uint8_t> ccount(n, 0), desc(n * 32, 0);
+    std::vector<float> weight(n, 0.f);
+    std::vector<int> cnt(n, 0);
+    int n_words = 0;
+    for (size_t r = 0; r < nrec; r++) {
+        const uint8_t* p = buf + 24 + r * size_node;
+        const int nid = (int)r + 1;
+        int par; std::memcpy(&par, p, 4);
+        if (par < 0 || par >= nid) { set_last_error("vocabulary: parent id out of order"); return YGZ_ERR_ARG; }
+        parent[nid] = par;
+        if (++cnt[par] > 255) { set_last_error("vocabulary: more than 255 children"); return YGZ_ERR_ARG; }
+        std::memcpy(&desc[(size_t)nid * 32], p + 4, 32);
+        std::memcpy(&weight[nid], p + 36, 4);
+        if (p[40]) word[nid] = n_words++;
+    }
+    int off = 0;
+    for (size_t i = 0; i < n; i++) { cbegin[i] = off; off += cnt[i]; ccount[i] = (uint8_t)cnt[i]; }
+    std::vector<int> fill(cbegin);
+    for (size_t nid = 1; nid < n; nid++) children[fill[parent[nid]]++] = (int)nid;      // ascending node id = insertion order
+    YGZ_CUDA_TRY(cudaSetDevice(device));
+    ygz_vocab* v = new ygz_vocab();
+    v->device = device; v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->n_nodes = (int)n; v->n_words = n_words;
+#define TRY_OR_FREE(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); vocab_free(v); return YGZ_ERR_CUDA; } } while (0)
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+    TRY_OR_FREE(cudaMalloc(&v->d_desc, n * 32));
+    TRY_OR_FREE(cudaMalloc(&v->d_child_begin, n * 4));
+    TRY_OR_FREE(cudaMalloc(&v->d_children, children.size() * 4));
+    TRY_OR_FREE(cudaMalloc(&v->d_word, n * 4));
+    TRY_OR_FREE(cudaMalloc(&v->d_child_count, n));
+    TRY_OR_FREE(cudaMalloc(&v->d_weight, n * 4));
+    TRY_OR_FREE(cudaMemcpy(v->d_desc, desc.data(), n * 32, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_child_begin, cbegin.data(), n * 4, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_children, children.data(), children.size() * 4, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_word, word.data(), n * 4, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_child_count, ccount.data(), n, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_weight, weight.data(), n * 4, cudaMemcpyHostToDevice));
+#undef TRY_OR_FREE
+    (void)nb_nodes;
+    *out = v;
+    return YGZ_OK;
+}
+
+int ygz_vocab_load(const char* path, int device, ygz_vocab** out) {
+    YGZ_ARG_CHECK(path && out);
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { set_last_error(std::string("cannot open vocabulary file ") + path); return YGZ_ERR_ARG; }
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf((size_t)std::max(sz, 0L));
+    const size_t got = std::fread(buf.data(), 1, buf.size(), f);
+    std::fclose(f);
+    if (got != buf.size()) { set_last_error("short read on vocabulary file"); return YGZ_ERR_ARG; }
+    return ygz_vocab_from_memory(buf.data(), buf.size(), device, out);
+}
+
+int ygz_vocab_destroy(ygz_vocab* v) { return vocab_free(v); }
+
+int ygz_vocab_info(const ygz_vocab* v, int* k, int* L, int* scoring, int* weighting, int* n_nodes, int* n_words) {
+    YGZ_ARG_CHECK(v);
+    if (k) *k = v->k;
+    if (L) *L = v->L;
+    if (scoring) *scoring = v->scoring;
+    if (weighting) *weighting = v->weighting;
+    if (n_nodes) *n_nodes = v->n_nodes;
+    if (n_words) *n_words = v->n_words;
+    return YGZ_OK;
+}
+
+int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, int* word_id, float* weight, int* node_id) {
+    YGZ_ARG_CHECK(v && n >= 0 && (n == 0 || (desc && word_id && weight && node_id)));
+    if (n == 0) return YGZ_OK;
+    YGZ_CUDA_TRY(cudaSetDevice(v->device));
+    int rc = vocab_scratch(v, n, true);
+    if (rc) return rc;
+    YGZ_CUDA_TRY(cudaMemcpyAsync(v->d_in, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
+    k_vocab_transform<<<ceil_div(n, 8), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n, levelsup,
+                                                            v->d_wid, v->d_w, v->d_nid);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(weight, v->d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(node_id, v->d_nid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(v->stream));
+    return YGZ_OK;
+}
+
+/* transform of the descriptors an extractor holds on the device (its last batch of n_frames frames, zero copy):
+ * outputs are [n_frames][cap] arrays with cap = ygz_orb_max_keypoints(orb) rows per frame (entries past a frame's count:
+ * word -1, node -1, weight 0).  The node ids are what ygz_search_by_bow_batch takes as `node_of_feature`. */
+int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levelsup, int* word_id, float* weight, int* node_id,
+                            float* ms) {
+    YGZ_ARG_CHECK(v && orb && n_frames >= 1);
+    YGZ_CUDA_TRY(cudaSetDevice(v->device));
+    void *d_kps = nullptr, *d_desc = nullptr, *d_counts = nullptr;
+    int cap = 0;
+    int rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap);
+    if (rc) return rc;
+    const int n = n_frames * cap;
+    if ((rc = vocab_scratch(v, n, false))) return rc;
+    YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
+    YGZ_CUDA_TRY(cudaMemsetAsync(v->d_wid, 0xFF, (size_t)n * 4, v->stream));      // slots past a frame's count: word -1, node -1, weight 0
+    YGZ_CUDA_TRY(cudaMemsetAsync(v->d_nid, 0xFF, (size_t)n * 4, v->stream));
+    YGZ_CUDA_TRY(cudaMemsetAsync(v->d_w, 0, (size_t)n * 4, v->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms) { YGZ_CUDA_TRY(cudaEventCreate(&e0)); YGZ_CUDA_TRY(cudaEventCreate(&e1)); YGZ_CUDA_TRY(cudaEventRecord(e0, v->stream)); }
+    k_vocab_transform<<<ceil_div(n, 8), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2,
+                                                            reinterpret_cast<const int*>(d_counts), cap, n, levelsup, v->d_wid, v->d_w, v->d_nid);
+    YGZ_CUDA_TRY(cudaGetLastError());
+    if (ms) { YGZ_CUDA_TRY(cudaEventRecord(e1, v->stream)); }
+    if (word_id) YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    if (weight) YGZ_CUDA_TRY(cudaMemcpyAsync(weight, v->d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    if (node_id) YGZ_CUDA_TRY(cudaMemcpyAsync(node_id, v->d_nid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(v->stream));
+    if (ms) { YGZ_CUDA_TRY(cudaEventElapsedTime(ms, e0, e1)); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+    return YGZ_OK;
+}
+
+}  // extern "C"

@@ -232,3 +232,38 @@ def synth_stereo_pair(seed, w=752, h=480, disparities=(6, 14, 25), noise=2):
     if noise:
         right = np.clip(right.astype(np.int32) + rng.integers(-noise, noise + 1, right.shape), 0, 255).astype(np.uint8)
     return np.ascontiguousarray(left[:, :w]), np.ascontiguousarray(right), band, tuple(disparities)
+
+
+def synth_vocabulary(seed, k=10, L=3, stop_frac=0.05, early_leaf_frac=0.03):
+    """A k-ary, depth-L ORB vocabulary in the binary layout of ORBvoc.bin (TemplatedVocabulary::saveToBinaryFile,
+    Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1527-1551): header {u32 nb_nodes, u32 size_node = 41, i32 k, i32 L,
+    i32 scoring = 0 (L1), i32 weighting = 0 (TF-IDF)} + one 41-byte record per node {i32 parent, u8 desc[32], f32 weight,
+    u8 is_leaf}, level by level.  Children are bit-flipped copies of their parent, a few leaves sit above the last level,
+    a few words are stopped (weight 0).  Returns bytes."""
+    rng = np.random.default_rng(seed)
+    rec = np.dtype([("parent", "<i4"), ("desc", "u1", 32), ("weight", "<f4"), ("leaf", "u1")])
+    assert rec.itemsize == 41
+    levels = []
+    parent_ids = np.zeros(1, np.int64)                       # node ids of the current frontier (root = 0)
+    parent_desc = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    next_id = 1
+    for level in range(1, L + 1):
+        m = len(parent_ids) * k
+        par = np.repeat(parent_ids, k)
+        base = np.repeat(parent_desc, k, axis=0)
+        flips = np.packbits(rng.random((m, 256)) < (0.22 / level), axis=1)
+        d = base ^ flips
+        leaf = np.full(m, level == L)
+        if level >= 2 and level < L:
+            leaf |= rng.random(m) < early_leaf_frac
+        w = np.where(leaf, np.where(rng.random(m) < stop_frac, 0.0, rng.uniform(0.5, 9.0, m)), 0.0).astype(np.float32)
+        r = np.zeros(m, rec)
+        r["parent"], r["desc"], r["weight"], r["leaf"] = par, d, w, leaf
+        levels.append(r)
+        ids = np.arange(next_id, next_id + m)
+        next_id += m
+        parent_ids, parent_desc = ids[~leaf], d[~leaf]
+        if len(parent_ids) == 0:
+            break
+    recs = np.concatenate(levels)
+    return np.array([len(recs) + 1, 41], np.uint32).tobytes() + np.array([k, L, 0, 0], np.int32).tobytes() + recs.tobytes()

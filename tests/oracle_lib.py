@@ -333,3 +333,50 @@ def compute_stereo_matches(pyrL, pyrR, keysL, descL, keysR, descR, scale, inv_sc
                                      scale.ctypes.data_as(f32p), inv_scale.ctypes.data_as(f32p), float(mb), float(mbf),
                                      u.ctypes.data_as(f32p), z.ctypes.data_as(f32p))
     return u, z, n
+
+
+class Vocabulary:
+    """Oracle DBoW2 vocabulary (oracle/vocabulary.cpp)."""
+
+    def __init__(self, path=None, data=None):
+        self.L_ = lib()
+        L = self.L_
+        L.orc_vocab_load.restype = C.c_void_p; L.orc_vocab_load.argtypes = [C.c_char_p]
+        L.orc_vocab_from_memory.restype = C.c_void_p; L.orc_vocab_from_memory.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_vocab_destroy.argtypes = [C.c_void_p]
+        L.orc_vocab_info.argtypes = [C.c_void_p] + [i32p] * 6
+        L.orc_vocab_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, f32p, i32p]
+        L.orc_vocab_transform_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, C.POINTER(C.c_double), i32p, i32p, i32p, i32p]
+        if path is not None:
+            self.h = L.orc_vocab_load(str(path).encode())
+        else:
+            buf = np.ascontiguousarray(np.frombuffer(data, np.uint8))
+            self.h = L.orc_vocab_from_memory(buf.ctypes.data, buf.size)
+        assert self.h, "vocabulary did not load"
+        v = [C.c_int() for _ in range(6)]
+        L.orc_vocab_info(self.h, *[C.byref(x) for x in v])
+        self.k, self.L, self.scoring, self.weighting, self.n_nodes, self.n_words = [x.value for x in v]
+
+    def __del__(self):
+        try:
+            self.L_.orc_vocab_destroy(self.h)
+        except Exception:
+            pass
+
+    def transform_features(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid = np.zeros(n, np.int32); w = np.zeros(n, np.float32); nid = np.zeros(n, np.int32)
+        self.L_.orc_vocab_transform(self.h, desc.ctypes.data, n, levelsup, wid.ctypes.data_as(i32p), w.ctypes.data_as(f32p), nid.ctypes.data_as(i32p))
+        return wid, w, nid
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        ids = np.zeros(max(n, 1), np.int32); vals = np.zeros(max(n, 1), np.float64)
+        fvn = C.c_int(); node = np.zeros(max(n, 1), np.int32); off = np.zeros(n + 2, np.int32); idx = np.zeros(max(n, 1), np.int32)
+        nb = self.L_.orc_vocab_transform_bow(self.h, desc.ctypes.data, n, levelsup, ids.ctypes.data_as(i32p),
+                                            vals.ctypes.data_as(C.POINTER(C.c_double)), C.byref(fvn), node.ctypes.data_as(i32p),
+                                            off.ctypes.data_as(i32p), idx.ctypes.data_as(i32p))
+        fv = {int(node[j]): [int(x) for x in idx[off[j]:off[j + 1]]] for j in range(fvn.value)}
+        return ids[:nb].copy(), vals[:nb].copy(), fv

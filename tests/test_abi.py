@@ -65,7 +65,7 @@ def test_cpp_class_mirror_compiles_and_links(tmp_path):
     """include/ygz/*.h (the reference-named C++ classes) compile against the C ABI and link with the library."""
     import subprocess
     src = tmp_path / "shim.cpp"
-    src.write_text('#include "ygz/ORBextractor.h"\n#include "ygz/ORBmatcher.h"\n#include "ygz/SparseImageAlign.h"\n'
+    src.write_text('#include "ygz/ORBextractor.h"\n#include "ygz/ORBmatcher.h"\n#include "ygz/SparseImageAlign.h"\n#include "ygz/ORBVocabulary.h"\n'
                    'int main() { unsigned char a[32] = {1}, b[32] = {0};\n'
                    '  ygz::ORBextractor ex(1000, 1.2f, 8, 20, 7);\n'
                    '  return ygz::ORBmatcher::DescriptorDistance(a, b) == 1 && ex.GetLevels() == 8 ? 0 : 1; }\n')

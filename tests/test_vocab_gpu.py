@@ -1,0 +1,56 @@
+"""GPU parity of the DBoW2 vocabulary transform (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1151-1292) against the
+oracle: word id, weight and level-(L - levelsup) node id per descriptor identical; BowVector (float64, L1-normalised) and
+FeatureVector identical; zero-copy transform of an extractor's device descriptors feeds the batched SearchByBoW."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k,L,levelsup", [(10, 3, 1), (10, 4, 2), (6, 3, 2), (3, 5, 4), (10, 2, 4)])
+def test_transform_bit_exact(gpu, oracle, synth, k, L, levelsup):
+    data = synth.synth_vocabulary(11 + k + L, k=k, L=L)
+    gv = gpu.ORBVocabulary(data=data)
+    ov = oracle.Vocabulary(data=data)
+    assert (gv.k, gv.L, gv.n_nodes, gv.n_words) == (ov.k, ov.L, ov.n_nodes, ov.n_words)
+    q, t, _ = synth.synth_descriptors(5, 1500, 1500)
+    desc = np.concatenate([q, t])
+    wid, w, nid = gv.transform_features(desc, levelsup)
+    owid, ow, onid = ov.transform_features(desc, levelsup)
+    assert (wid == owid).all() and (nid == onid).all() and (w.view(np.uint32) == ow.view(np.uint32)).all()
+    ids, vals, fv = gv.transform(desc[:1000], levelsup)
+    oids, ovals, ofv = ov.transform(desc[:1000], levelsup)
+    assert (ids == oids).all() and (vals == ovals).all() and fv == ofv
+
+
+def test_transform_orb_feeds_search_by_bow(gpu, oracle, synth):
+    """Frame::ComputeBoW on the device for a batch of frames, then the batched SearchByBoW with those node ids equals the
+    oracle's SearchByBoW on FeatureVectors built from the oracle's transform."""
+    import helpers as H
+    w, h, B = 480, 360, 3
+    frames = synth.synth_stream(21, B, w, h)
+    data = synth.synth_vocabulary(4, k=10, L=4)
+    gv = gpu.ORBVocabulary(data=data)
+    ov = oracle.Vocabulary(data=data)
+    ex = gpu.ORBextractor(600, 1.2, 8, 20, 7, width=w, height=h, max_batch=B)
+    res = ex.extract_batch(frames)
+    out = gv.transform_orb(ex, B, levelsup=2, want=("node", "word", "weight"), timed=True)
+    for f, (kps, desc) in enumerate(res):
+        owid, ow, onid = ov.transform_features(desc, 2)
+        n = len(kps)
+        assert (out["node"][f, :n] == onid).all() and (out["word"][f, :n] == owid).all()
+        assert (out["weight"][f, :n].view(np.uint32) == ow.view(np.uint32)).all()
+        assert (out["node"][f, n:] == -1).all()
+    mt = gpu.ORBmatcher(0.7, True)
+    kf_idx = np.array([0, 1], np.int32); f_idx = np.array([1, 2], np.int32)
+    node = out["node"].astype(np.uint32)
+    nm, matches = mt.SearchByBoWBatch(ex, kf_idx, f_idx, node)
+    for p in range(2):
+        (ka, da), (kb, db) = res[kf_idx[p]], res[f_idx[p]]
+        mp = np.arange(len(ka), dtype=np.int32)
+        kf = gpu.make_frame_view(ka, da, map_point=mp, node_of_feature=out["node"][kf_idx[p], :len(ka)].astype(np.uint32), cls=oracle.FrameView)
+        fr = gpu.make_frame_view(kb, db, node_of_feature=out["node"][f_idx[p], :len(kb)].astype(np.uint32), cls=oracle.FrameView)
+        mps = gpu.make_map_points(np.zeros((len(ka), 3)), da, cls=oracle.MapPoints)
+        o = np.zeros(len(kb), np.int32)
+        n_bow = oracle.lib().orc_search_by_bow(0.7, 1, kf.ptr(), mps.ptr(), fr.ptr(), o.ctypes.data_as(oracle.i32p))
+        assert nm[p] == n_bow and (matches[p, :len(kb)] == o).all()
