@@ -193,7 +193,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit_json(out)
     return 0
 
 
@@ -286,6 +286,18 @@ def workload_config(batch):
             "parallelism": "replicas: one independent batch per GPU"}
 
 
+_JSON_FD = None
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -298,6 +310,13 @@ def main():
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the end-to-end (host buffer) path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there) share fd 1, so
+    # everything except the final line goes to stderr: fd 1 is pointed at fd 2 for the whole run and the JSON line is
+    # written to the saved descriptor.
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -489,7 +508,7 @@ def main():
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                    "sample": "%d frames of the same stream in %.1f s, oracle port (%s build), %d threads (%s)" %
                                              (done, dt, "-march=native" if native else "portable", threads, cpu_note)}
-        print(json.dumps(out))
+        emit_json(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
