@@ -22,6 +22,8 @@ CONFIGS = [
     (752, 480, 1000, 2.0, 4, [7]),           # C3 pyramid (EuRoC.yaml): level 3 has no FAST cells
     (320, 240, 500, 1.2, 8, [3, 4]),
     (200, 150, 300, 1.5, 5, [9]),
+    (1920, 1080, 2000, 1.2, 8, [11]),       # full HD: 4x the C1 pixels, 5.8 k cells
+    (641, 479, 700, 1.2, 8, [12]),           # odd sizes: row pitch padding on every level
 ]
 
 
