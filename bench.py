@@ -473,8 +473,8 @@ def main():
         pf_ms = stages["pyramid(7 launches)"] + stages["fast_cells"]
         # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the ncu --set full capture of this very
         # command shape (B=256), profiles/r1_full_B256_raw.csv; None for other shapes
-        NCU_TRAFFIC_B256 = {"fast_cells": 271660800 + 31598336, "orient_describe": 521018112 + 17215488,
-                            "octree": 70602752 + 52727552, "blur_levels": 289890816 + 252677888}
+        NCU_TRAFFIC_B256 = {"fast_cells": 271616768 + 31951360, "orient_describe": 520987904 + 19014144,
+                            "octree": 70572544 + 53032448, "blur_levels": 290054656 + 252909568}
         traffic = NCU_TRAFFIC_B256.get(dom) if B == 256 else None
         out = {
             "metric": "front-end frames/sec (752x480, 1000 feat, 8-lvl pyr)", "value": value, "unit": "frames/s",

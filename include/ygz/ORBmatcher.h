@@ -4,6 +4,7 @@
 // mutation of mvpMapPoints (as index arrays) follow the reference.
 #pragma once
 #include <cstdio>
+#include <utility>
 #include <vector>
 #include "../ygz_b200.h"
 
@@ -46,6 +47,23 @@ public:
         std::vector<int> tmp((size_t)(F.n > 0 ? F.n : 1));
         int n = ok(ygz_search_by_bow(h_, mfNNratio, mbCheckOrientation, &KF, &mps, &F, tmp.data()));
         for (int i = 0; i < F.n; i++) vpMapPointMatches[i] = tmp[i];
+        return n;
+    }
+    // SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)  :480-595
+    int SearchByBoW(const ygz_frame_view& KF1, const ygz_frame_view& KF2, const ygz_map_points& mps, std::vector<int>& vpMatches12) {
+        vpMatches12.assign(KF1.n > 0 ? KF1.n : 1, -1);
+        int n = ok(ygz_search_by_bow_kf(h_, mfNNratio, mbCheckOrientation, &KF1, &KF2, &mps, vpMatches12.data()));
+        vpMatches12.resize(KF1.n > 0 ? KF1.n : 0);
+        return n;
+    }
+    // SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo)  :597-746; epipole = KF1's centre seen from KF2
+    int SearchForTriangulation(const ygz_frame_view& KF1, const ygz_frame_view& KF2, const float F12[9], float ex, float ey,
+                               const std::vector<float>& mvLevelSigma2, std::vector<std::pair<size_t, size_t> >& vMatchedPairs,
+                               bool bOnlyStereo) {
+        std::vector<int> p((size_t)2 * (KF1.n > 0 ? KF1.n : 1));
+        int n = ok(ygz_search_for_triangulation(h_, mbCheckOrientation, &KF1, &KF2, F12, ex, ey, mvLevelSigma2.data(), bOnlyStereo, p.data()));
+        vMatchedPairs.clear();
+        for (int i = 0; i < n; i++) vMatchedPairs.push_back(std::make_pair((size_t)p[2 * i], (size_t)p[2 * i + 1]));
         return n;
     }
     // SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  :375-478

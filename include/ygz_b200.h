@@ -177,6 +177,16 @@ typedef struct {
  * out_matches[f->n] = map-point index or -1; returns nmatches (>= 0) or a negative ygz_status. */
 int ygz_search_by_bow(ygz_matcher* h, float nnratio, int check_orientation, const ygz_frame_view* kf,
                       const ygz_map_points* mps, const ygz_frame_view* f, int* out_matches);
+/* SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12), src/ORBmatcher.cc:480-595 (loop closing /
+ * relocalisation candidates): matches12[i] = index of the KF2 map point matched to feature i of KF1, -1 = none. */
+int ygz_search_by_bow_kf(ygz_matcher* h, float nnratio, int check_ori, const ygz_frame_view* kf1, const ygz_frame_view* kf2,
+                         const ygz_map_points* mps, int* matches12);
+/* SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo), src/ORBmatcher.cc:597-746 with
+ * CheckDistEpipolarLine :136-153.  F12 row-major 3x3; (ex, ey) = projection of KF1's camera centre into KF2 (:603-609);
+ * level_sigma2 = pKF2->mvLevelSigma2.  pairs receives (idx1, idx2) in ascending idx1 (capacity 2 * kf1->n ints);
+ * returns the number of pairs. */
+int ygz_search_for_triangulation(ygz_matcher* h, int check_ori, const ygz_frame_view* kf1, const ygz_frame_view* kf2,
+                                 const float* F12, float ex, float ey, const float* level_sigma2, int only_stereo, int* pairs);
 /* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, checkLevel), src/ORBmatcher.cc:43-126 */
 int ygz_search_by_projection_points(ygz_matcher* h, float nnratio, ygz_frame_view* f, const ygz_map_points* mps,
                                     const int* query_ids, int nq, float th, int check_level);

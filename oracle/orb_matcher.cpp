@@ -179,6 +179,139 @@ int orc_search_by_bow(float nnratio, int check_ori, const orc_frame_view* kf, co
     return nmatches;
 }
 
+// ---- src/ORBmatcher.cc:480-595  SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+int orc_search_by_bow_kf(float nnratio, int check_ori, const orc_frame_view* kf1, const orc_frame_view* kf2,
+                         const orc_map_points* mps, int* matches12) {
+    for (int i = 0; i < kf1->n; i++) matches12[i] = -1;
+    std::vector<char> vbMatched2(kf2->n, 0);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = 0;
+    int i1n = 0, i2n = 0;
+    while (i1n < kf1->fv_nodes && i2n < kf2->fv_nodes) {
+        const uint32_t n1 = kf1->fv_node_id[i1n], n2 = kf2->fv_node_id[i2n];
+        if (n1 == n2) {
+            for (int a = kf1->fv_offset[i1n]; a < kf1->fv_offset[i1n + 1]; a++) {
+                const int idx1 = (int)kf1->fv_index[a];
+                const int pMP1 = kf1->map_point[idx1];
+                if (pMP1 < 0) continue;
+                if (mp_bad(mps, pMP1)) continue;
+                const uint8_t* d1 = kf1->desc + 32 * (size_t)idx1;
+                int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                for (int b = kf2->fv_offset[i2n]; b < kf2->fv_offset[i2n + 1]; b++) {
+                    const int idx2 = (int)kf2->fv_index[b];
+                    const int pMP2 = kf2->map_point[idx2];
+                    if (vbMatched2[idx2] || pMP2 < 0) continue;
+                    if (mp_bad(mps, pMP2)) continue;
+                    const int dist = descriptor_distance(d1, kf2->desc + 32 * (size_t)idx2);
+                    if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                    else if (dist < bestDist2) bestDist2 = dist;
+                }
+                if (bestDist1 < TH_LOW) {
+                    if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        matches12[idx1] = kf2->map_point[bestIdx2];
+                        vbMatched2[bestIdx2] = 1;
+                        if (check_ori) rotHist[rot_bin(kf1->keys[idx1].angle, kf2->keys[bestIdx2].angle)].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+            }
+            i1n++; i2n++;
+        } else if (n1 < n2) {
+            while (i1n < kf1->fv_nodes && kf1->fv_node_id[i1n] < n2) i1n++;
+        } else {
+            while (i2n < kf2->fv_nodes && kf2->fv_node_id[i2n] < n1) i2n++;
+        }
+    }
+    if (check_ori) {
+        int sz[HISTO_LENGTH], a1 = -1, a2 = -1, a3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)rotHist[i].size();
+        three_maxima(sz, HISTO_LENGTH, a1, a2, a3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == a1 || i == a2 || i == a3) continue;
+            for (int idx : rotHist[i]) { matches12[idx] = -1; nmatches--; }
+        }
+    }
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:136-153 CheckDistEpipolarLine (F12 row-major 3x3; sigma2 = pKF2->mvLevelSigma2)
+static bool check_dist_epipolar_line(const orc_keypoint& kp1, const orc_keypoint& kp2, const float* F12, const float* sigma2) {
+    const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+    const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+    const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * sigma2[kp2.octave];
+}
+
+// ---- src/ORBmatcher.cc:597-746  SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo).
+// ex_ey: epipole of KF1's centre in KF2 (:603-609, computed by the caller from the poses); level_sigma2 = pKF2->mvLevelSigma2.
+// pairs: up to kf1->n (idx1, idx2) pairs in ascending idx1.  Returns nmatches.
+int orc_search_for_triangulation(int check_ori, const orc_frame_view* kf1, const orc_frame_view* kf2, const float* F12,
+                                 float ex, float ey, const float* level_sigma2, int only_stereo, int* pairs) {
+    int nmatches = 0;
+    std::vector<char> vbMatched2(kf2->n, 0);
+    std::vector<int> vMatches12(kf1->n, -1);
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int i1n = 0, i2n = 0;
+    while (i1n < kf1->fv_nodes && i2n < kf2->fv_nodes) {
+        const uint32_t n1 = kf1->fv_node_id[i1n], n2 = kf2->fv_node_id[i2n];
+        if (n1 == n2) {
+            for (int a = kf1->fv_offset[i1n]; a < kf1->fv_offset[i1n + 1]; a++) {
+                const int idx1 = (int)kf1->fv_index[a];
+                if (kf1->map_point[idx1] >= 0) continue;                 // already a MapPoint
+                const bool bStereo1 = uright(kf1, idx1) >= 0;
+                if (only_stereo && !bStereo1) continue;
+                const orc_keypoint& kp1 = kf1->keys[idx1];
+                const uint8_t* d1 = kf1->desc + 32 * (size_t)idx1;
+                int bestDist = TH_LOW, bestIdx2 = -1;
+                for (int b = kf2->fv_offset[i2n]; b < kf2->fv_offset[i2n + 1]; b++) {
+                    const int idx2 = (int)kf2->fv_index[b];
+                    if (vbMatched2[idx2] || kf2->map_point[idx2] >= 0) continue;
+                    const bool bStereo2 = uright(kf2, idx2) >= 0;
+                    if (only_stereo && !bStereo2) continue;
+                    const int dist = descriptor_distance(d1, kf2->desc + 32 * (size_t)idx2);
+                    if (dist > TH_LOW || dist > bestDist) continue;
+                    const orc_keypoint& kp2 = kf2->keys[idx2];
+                    if (!bStereo1 && !bStereo2) {
+                        const float distex = ex - kp2.x, distey = ey - kp2.y;
+                        if (distex * distex + distey * distey < 100 * kf2->scale_factors[kp2.octave]) continue;
+                    }
+                    if (check_dist_epipolar_line(kp1, kp2, F12, level_sigma2)) { bestIdx2 = idx2; bestDist = dist; }
+                }
+                if (bestIdx2 >= 0) {
+                    vMatches12[idx1] = bestIdx2;
+                    nmatches++;
+                    if (check_ori) rotHist[rot_bin(kp1.angle, kf2->keys[bestIdx2].angle)].push_back(idx1);
+                }
+            }
+            i1n++; i2n++;
+        } else if (n1 < n2) {
+            while (i1n < kf1->fv_nodes && kf1->fv_node_id[i1n] < n2) i1n++;
+        } else {
+            while (i2n < kf2->fv_nodes && kf2->fv_node_id[i2n] < n1) i2n++;
+        }
+    }
+    if (check_ori) {
+        int sz[HISTO_LENGTH], a1 = -1, a2 = -1, a3 = -1;
+        for (int i = 0; i < HISTO_LENGTH; i++) sz[i] = (int)rotHist[i].size();
+        three_maxima(sz, HISTO_LENGTH, a1, a2, a3);
+        for (int i = 0; i < HISTO_LENGTH; i++) {
+            if (i == a1 || i == a2 || i == a3) continue;
+            for (int idx : rotHist[i]) { vMatches12[idx] = -1; nmatches--; }
+        }
+    }
+    int np = 0;
+    for (int i = 0; i < kf1->n; i++) {
+        if (vMatches12[i] < 0) continue;
+        pairs[2 * np] = i; pairs[2 * np + 1] = vMatches12[i];
+        np++;
+    }
+    return nmatches;
+}
+
 // ---- src/ORBmatcher.cc:43-133
 int orc_search_by_projection_points(float nnratio, orc_frame_view* F, const orc_map_points* mps,
                                     const int* query_ids, int nq, float th, int check_level) {

@@ -107,6 +107,13 @@ int orc_search_by_projection_kf(int check_ori, orc_frame_view* cur, const orc_fr
 /* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) :375-478 */
 int orc_search_for_initialization(float nnratio, int check_ori, const orc_frame_view* f1, const orc_frame_view* f2,
                                   float* prev_matched_xy, int* matches12, int window);
+/* SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) :480-595: matches12[i] = map point (of KF2) matched to feature i of KF1 */
+int orc_search_by_bow_kf(float nnratio, int check_ori, const orc_frame_view* kf1, const orc_frame_view* kf2,
+                         const orc_map_points* mps, int* matches12);
+/* SearchForTriangulation :597-746 (+ CheckDistEpipolarLine :136-153).  F12 row-major; (ex, ey) = epipole of KF1 in KF2
+ * (:603-609); level_sigma2 = pKF2->mvLevelSigma2; pairs = (idx1, idx2) in ascending idx1 (capacity kf1->n). */
+int orc_search_for_triangulation(int check_ori, const orc_frame_view* kf1, const orc_frame_view* kf2, const float* F12,
+                                 float ex, float ey, const float* level_sigma2, int only_stereo, int* pairs);
 /* ComputeThreeMaxima :1471-1502 */
 void orc_three_maxima(const int* hist_sizes, int L, int* ind1, int* ind2, int* ind3);
 /* Frame::GetFeaturesInArea src/Frame.cc:424-481 (grid built as AssignFeaturesToGrid :314-330) */

@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "ygz_orb_upload", "ygz_orb_run", "ygz_orb_download", "ygz_orb_sync", "ygz_orb_get_candidates",
     "ygz_orb_time", "ygz_debug_cos_sin", "ygz_orb_device_outputs", "ygz_orb_device_level", "ygz_orb_stream", "ygz_orb_counters",
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
-    "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_projection_points",
+    "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_bow_kf", "ygz_search_for_triangulation", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
     "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
@@ -148,6 +148,8 @@ def lib():
     sigs.setdefault('ygz_hamming_bf_top2', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, i32p, i32p, i32p]
     sigs.setdefault('ygz_hamming_pairs', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, i32p, i32p, C.c_int, i32p]
     sigs.setdefault('ygz_search_by_bow', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(MapPoints), C.POINTER(FrameView), i32p]
+    sigs.setdefault('ygz_search_by_bow_kf', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), i32p]
+    sigs.setdefault('ygz_search_for_triangulation', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, C.c_float, C.c_float, f32p, C.c_int, i32p]
     sigs.setdefault('ygz_search_by_projection_points', {})['argtypes'] = [C.c_void_p, C.c_float, C.POINTER(FrameView), C.POINTER(MapPoints), i32p, C.c_int, C.c_float, C.c_int]
     sigs.setdefault('ygz_search_by_projection_last', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), C.c_float, C.c_int, C.c_int]
     sigs.setdefault('ygz_search_by_projection_kf', {})['argtypes'] = [C.c_void_p, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), u8p, C.c_float, C.c_int]
@@ -535,6 +537,25 @@ class ORBmatcher:
                                                         _ptr(prev, f32p), _ptr(m12, i32p), window),
                    "ygz_search_for_initialization")
         return n, m12[:f1.struct.n], prev
+
+    def SearchByBoWKF(self, kf1, kf2, mps):
+        """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) :480-595.  Returns (nmatches, matches12[kf1.n])."""
+        out = np.zeros(max(kf1.struct.n, 1), np.int32)
+        n = self.L.ygz_search_by_bow_kf(self.h, self.nnratio, int(self.checkOri), kf1.ptr(), kf2.ptr(), mps.ptr(), _ptr(out, i32p))
+        if n < 0:
+            _check(n, "ygz_search_by_bow_kf")
+        return n, out[:kf1.struct.n]
+
+    def SearchForTriangulation(self, kf1, kf2, F12, epipole, level_sigma2, only_stereo=False):
+        """SearchForTriangulation :597-746.  Returns (nmatches, pairs[n, 2])."""
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(9)
+        ls2 = np.ascontiguousarray(level_sigma2, np.float32)
+        pairs = np.zeros((max(kf1.struct.n, 1), 2), np.int32)
+        n = self.L.ygz_search_for_triangulation(self.h, int(self.checkOri), kf1.ptr(), kf2.ptr(), _ptr(F12, f32p), float(epipole[0]),
+                                                float(epipole[1]), _ptr(ls2, f32p), int(only_stereo), _ptr(pairs, i32p))
+        if n < 0:
+            _check(n, "ygz_search_for_triangulation")
+        return n, pairs[:n].copy()
 
     def SearchByBoWBatch(self, extractor, kf_idx, f_idx, node_of_feature):
         """Device-resident SearchByBoW over frame pairs of an extractor batch (outputs already in HBM)."""

@@ -542,6 +542,144 @@ int ygz_search_by_bow(ygz_matcher* h, float nnratio, int check_ori, const ygz_fr
     return nmatches;
 }
 
+// ---- src/ORBmatcher.cc:480-595  SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12)
+int ygz_search_by_bow_kf(ygz_matcher* h, float nnratio, int check_ori, const ygz_frame_view* kf1, const ygz_frame_view* kf2,
+                         const ygz_map_points* mps, int* matches12) {
+    YGZ_ARG_CHECK(h && kf1 && kf2 && mps && matches12);
+    for (int i = 0; i < kf1->n; i++) matches12[i] = -1;
+    struct Job { int idx1, first, count; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt;
+    int i1n = 0, i2n = 0;
+    while (i1n < kf1->fv_nodes && i2n < kf2->fv_nodes) {
+        const uint32_t n1 = kf1->fv_node_id[i1n], n2 = kf2->fv_node_id[i2n];
+        if (n1 == n2) {
+            for (int a = kf1->fv_offset[i1n]; a < kf1->fv_offset[i1n + 1]; a++) {
+                const int idx1 = (int)kf1->fv_index[a];
+                const int pMP1 = kf1->map_point[idx1];
+                if (pMP1 < 0 || mp_bad(mps, pMP1)) continue;
+                Job j{idx1, (int)pq.size(), 0};
+                for (int b = kf2->fv_offset[i2n]; b < kf2->fv_offset[i2n + 1]; b++) {
+                    const int idx2 = (int)kf2->fv_index[b];
+                    const int pMP2 = kf2->map_point[idx2];
+                    if (pMP2 < 0 || mp_bad(mps, pMP2)) continue;            // state-independent part of :528-532
+                    pq.push_back(idx1); pt.push_back(idx2); j.count++;
+                }
+                jobs.push_back(j);
+            }
+            i1n++; i2n++;
+        } else if (n1 < n2) {
+            while (i1n < kf1->fv_nodes && kf1->fv_node_id[i1n] < n2) i1n++;
+        } else {
+            while (i2n < kf2->fv_nodes && kf2->fv_node_id[i2n] < n1) i2n++;
+        }
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, kf1->desc, kf1->n, kf2->desc, kf2->n, pq, pt, dist);
+    if (rc) return rc;
+    std::vector<char> vbMatched2(kf2->n, 0);
+    int nmatches = 0;
+    RotHist rh;
+    for (const Job& j : jobs) {
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int idx2 = pt[p];
+            if (vbMatched2[idx2]) continue;
+            const int d = dist[p];
+            if (d < bestDist1) { bestDist2 = bestDist1; bestDist1 = d; bestIdx2 = idx2; }
+            else if (d < bestDist2) bestDist2 = d;
+        }
+        if (bestDist1 < TH_LOW && static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+            matches12[j.idx1] = kf2->map_point[bestIdx2];
+            vbMatched2[bestIdx2] = 1;
+            if (check_ori) rh.add(rot_bin(kf1->keys[j.idx1].angle, kf2->keys[bestIdx2].angle), j.idx1);
+            nmatches++;
+        }
+    }
+    if (check_ori) rh.prune([&](int idx) { matches12[idx] = -1; nmatches--; });
+    return nmatches;
+}
+
+// ---- src/ORBmatcher.cc:597-746  SearchForTriangulation (+ CheckDistEpipolarLine :136-153)
+int ygz_search_for_triangulation(ygz_matcher* h, int check_ori, const ygz_frame_view* kf1, const ygz_frame_view* kf2,
+                                 const float* F12, float ex, float ey, const float* level_sigma2, int only_stereo, int* pairs) {
+    YGZ_ARG_CHECK(h && kf1 && kf2 && F12 && level_sigma2 && pairs);
+    struct Job { int idx1, first, count; };
+    std::vector<Job> jobs;
+    std::vector<int> pq, pt;
+    int i1n = 0, i2n = 0;
+    while (i1n < kf1->fv_nodes && i2n < kf2->fv_nodes) {
+        const uint32_t n1 = kf1->fv_node_id[i1n], n2 = kf2->fv_node_id[i2n];
+        if (n1 == n2) {
+            for (int a = kf1->fv_offset[i1n]; a < kf1->fv_offset[i1n + 1]; a++) {
+                const int idx1 = (int)kf1->fv_index[a];
+                if (kf1->map_point[idx1] >= 0) continue;
+                if (only_stereo && !(uright(kf1, idx1) >= 0)) continue;
+                Job j{idx1, (int)pq.size(), 0};
+                for (int b = kf2->fv_offset[i2n]; b < kf2->fv_offset[i2n + 1]; b++) {
+                    const int idx2 = (int)kf2->fv_index[b];
+                    if (kf2->map_point[idx2] >= 0) continue;
+                    if (only_stereo && !(uright(kf2, idx2) >= 0)) continue;
+                    pq.push_back(idx1); pt.push_back(idx2); j.count++;
+                }
+                jobs.push_back(j);
+            }
+            i1n++; i2n++;
+        } else if (n1 < n2) {
+            while (i1n < kf1->fv_nodes && kf1->fv_node_id[i1n] < n2) i1n++;
+        } else {
+            while (i2n < kf2->fv_nodes && kf2->fv_node_id[i2n] < n1) i2n++;
+        }
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, kf1->desc, kf1->n, kf2->desc, kf2->n, pq, pt, dist);
+    if (rc) return rc;
+    std::vector<char> vbMatched2(kf2->n, 0);
+    std::vector<int> vMatches12(kf1->n, -1);
+    int nmatches = 0;
+    RotHist rh;
+    for (const Job& j : jobs) {
+        const ygz_keypoint& kp1 = kf1->keys[j.idx1];
+        const bool bStereo1 = uright(kf1, j.idx1) >= 0;
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            const int idx2 = pt[p];
+            if (vbMatched2[idx2]) continue;
+            const int d = dist[p];
+            if (d > TH_LOW || d > bestDist) continue;
+            const ygz_keypoint& kp2 = kf2->keys[idx2];
+            const bool bStereo2 = uright(kf2, idx2) >= 0;
+            if (!bStereo1 && !bStereo2) {
+                const float distex = ex - kp2.x, distey = ey - kp2.y;
+                if (distex * distex + distey * distey < 100 * kf2->scale_factors[kp2.octave]) continue;
+            }
+            // CheckDistEpipolarLine: l = x1' F12, distance of kp2 to l against the chi-square bound of its level
+            const float a = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+            const float b = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+            const float c = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+            const float num = a * kp2.x + b * kp2.y + c;
+            const float den = a * a + b * b;
+            if (den == 0) continue;
+            const float dsqr = num * num / den;
+            if (dsqr < 3.84 * level_sigma2[kp2.octave]) { bestIdx2 = idx2; bestDist = d; }
+        }
+        if (bestIdx2 >= 0) {
+            vMatches12[j.idx1] = bestIdx2;
+            // (the reference never sets vbMatched2 in this function: a KF2 feature can be matched by several KF1 features)
+            nmatches++;
+            if (check_ori) rh.add(rot_bin(kp1.angle, kf2->keys[bestIdx2].angle), j.idx1);
+        }
+    }
+    if (check_ori) rh.prune([&](int idx) { vMatches12[idx] = -1; nmatches--; });
+    int np = 0;
+    for (int i = 0; i < kf1->n; i++) {
+        if (vMatches12[i] < 0) continue;
+        pairs[2 * np] = i; pairs[2 * np + 1] = vMatches12[i];
+        np++;
+    }
+    return nmatches;
+}
+
 // ---- src/ORBmatcher.cc:43-126
 int ygz_search_by_projection_points(ygz_matcher* h, float nnratio, ygz_frame_view* F, const ygz_map_points* mps,
                                     const int* query_ids, int nq, float th, int check_level) {
