@@ -372,16 +372,18 @@ int ygz_find_direct_projection(ygz_direct* h, int cur_slot, const float* K4, con
 int ygz_direct_time(ygz_direct* h, int iters, float* ms) {
     YGZ_ARG_CHECK(h && ms && iters >= 1 && h->last_n >= 1);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     YGZ_CUDA_TRY(cudaEventCreate(&e0));
-    YGZ_CUDA_TRY(cudaEventCreate(&e1));
-    YGZ_CUDA_TRY(cudaEventRecord(e0, h->stream));
-    for (int i = 0; i < iters; i++) { int rc = direct_launch(h, h->last_n); if (rc) return rc; }
-    YGZ_CUDA_TRY(cudaEventRecord(e1, h->stream));
-    YGZ_CUDA_TRY(cudaEventSynchronize(e1));
-    YGZ_CUDA_TRY(cudaEventElapsedTime(ms, e0, e1));
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); set_last_error("cudaEventCreate failed"); return YGZ_ERR_CUDA; }
+    int rc = YGZ_OK;
+    cudaError_t ce = cudaEventRecord(e0, h->stream);
+    for (int i = 0; i < iters && rc == YGZ_OK && ce == cudaSuccess; i++) rc = direct_launch(h, h->last_n);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e1, h->stream);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    return YGZ_OK;
+    if (rc == YGZ_OK && ce != cudaSuccess) { set_last_error(std::string("ygz_direct_time: ") + cudaGetErrorString(ce)); rc = YGZ_ERR_CUDA; }
+    return rc;
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -129,7 +130,8 @@ struct ygz_stereo {
     float *d_u = nullptr, *d_z = nullptr;
 };
 
-static ygz_stereo* g_stereo[16] = {};
+static ygz_stereo* g_stereo[16] = {};     // per-device scratch (buffers + stream), created on first use
+static std::mutex g_stereo_mutex;          // calls are serialised: the scratch is shared by every caller of a device
 
 template <class T>
 static int grow(T** p, int* cap, int need) {
@@ -201,6 +203,7 @@ int ygz_compute_stereo_matches(ygz_orb* left, ygz_orb* right, int frame, const y
         dev = at.device;
     }
     YGZ_CUDA_TRY(cudaSetDevice(dev));
+    std::lock_guard<std::mutex> lock(g_stereo_mutex);
     ygz_stereo*& S = g_stereo[dev & 15];
     if (!S) {
         S = new ygz_stereo();

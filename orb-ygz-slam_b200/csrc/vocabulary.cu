@@ -98,11 +98,10 @@ static int vocab_free(ygz_vocab* v) {
     return YGZ_OK;
 }
 
-static int vocab_scratch(ygz_vocab* v, int n, bool with_input) {
+static int vocab_scratch(ygz_vocab* v, int n) {
     if (n <= v->cap) return YGZ_OK;
     cudaFree(v->d_in); cudaFree(v->d_wid); cudaFree(v->d_nid); cudaFree(v->d_w);
     v->d_in = nullptr; v->d_wid = v->d_nid = nullptr; v->d_w = nullptr; v->cap = 0;
-    (void)with_input;
     YGZ_CUDA_TRY(cudaMalloc(&v->d_in, (size_t)n * 32));
     YGZ_CUDA_TRY(cudaMalloc(&v->d_wid, (size_t)n * 4));
     YGZ_CUDA_TRY(cudaMalloc(&v->d_nid, (size_t)n * 4));
@@ -197,7 +196,7 @@ int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, 
     YGZ_ARG_CHECK(v && n >= 0 && (n == 0 || (desc && word_id && weight && node_id)));
     if (n == 0) return YGZ_OK;
     YGZ_CUDA_TRY(cudaSetDevice(v->device));
-    int rc = vocab_scratch(v, n, true);
+    int rc = vocab_scratch(v, n);
     if (rc) return rc;
     YGZ_CUDA_TRY(cudaMemcpyAsync(v->d_in, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
     k_vocab_transform<<<ceil_div(n, 8), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n, levelsup,
@@ -222,7 +221,7 @@ int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levels
     int rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap);
     if (rc) return rc;
     const int n = n_frames * cap;
-    if ((rc = vocab_scratch(v, n, false))) return rc;
+    if ((rc = vocab_scratch(v, n))) return rc;
     YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
     YGZ_CUDA_TRY(cudaMemsetAsync(v->d_wid, 0xFF, (size_t)n * 4, v->stream));      // slots past a frame's count: word -1, node -1, weight 0
     YGZ_CUDA_TRY(cudaMemsetAsync(v->d_nid, 0xFF, (size_t)n * 4, v->stream));
