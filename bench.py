@@ -492,6 +492,11 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                          "limiter": "issue slots, not bytes: ncu smsp__issue_active 80 % (fast_cells; ALU pipe 61 %), 87 % (blur_levels, which streams 2 x SUM_P at 2.4 TB/s); see DESIGN.md §4",
                          "kernel_ms_per_launch": stages[dom],
+                         "other_kernels": {k: {"algorithmic_bytes_per_launch": alg[k] * B, "ms_per_launch": stages[k],
+                                               "achieved": alg[k] * B / (stages[k] / 1e3) / 1e9,
+                                               "frac": alg[k] * B / (stages[k] / 1e3) / 1e9 / peak,
+                                               "traffic": NCU_TRAFFIC_B256.get(k) if B == 256 else None}
+                                           for k in ("blur_levels", "pyramid(7 launches)", "orient_describe") if stages.get(k)},
                          "pyramid_plus_fast": {"strict_bytes_per_step": pf_bytes, "ms_per_step": pf_ms,
                                                "achieved": pf_bytes / (pf_ms / 1e3) / 1e9,
                                                "frac": pf_bytes / (pf_ms / 1e3) / 1e9 / peak}},
