@@ -490,7 +490,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                         "limiter": "issue slots, not bytes: ncu smsp__issue_active 80 % (fast_cells; ALU pipe 61 %), 87 % (blur_levels, which streams 2 x SUM_P at 2.4 TB/s); see DESIGN.md §4",
+                         "limiter": "issue slots, not bytes: ncu smsp__issue_active 80 % (fast_cells; ALU pipe 61 %), 87 % (blur_levels, which streams 2 x SUM_P at 2.6 TB/s); see DESIGN.md §4",
                          "kernel_ms_per_launch": stages[dom],
                          "other_kernels": {k: {"algorithmic_bytes_per_launch": alg[k] * B, "ms_per_launch": stages[k],
                                                "achieved": alg[k] * B / (stages[k] / 1e3) / 1e9,
