@@ -235,9 +235,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const 
     {   // ---- tile load (coalesced words) + score tile clear
         const int wpr = TP >> 2;
         const uint8_t* g0 = L.base + (size_t)frame * L.frame_stride + (size_t)cd.y0 * L.pitch + xa;
-        for (int i = lane; i < ch * wpr; i += 32) {
-            const int r = i / wpr, c = i - r * wpr;
+        // (row, word) of this lane's element advanced incrementally: wpr is a run-time 9..18, a division per element
+        // cost 13 % of the kernel's instructions in the round-1 profile
+        int r = 0, c = lane;
+        while (c >= wpr) { c -= wpr; r++; }
+        while (r < ch) {
             reinterpret_cast<uint32_t*>(tile + r * TP)[c] = __ldg(reinterpret_cast<const uint32_t*>(g0 + (size_t)r * L.pitch) + c);
+            c += 32;
+            while (c >= wpr) { c -= wpr; r++; }
         }
         const int nsw = round4(sw2 * (dh + 2)) >> 2;
         for (int i = lane; i < nsw; i += 32) reinterpret_cast<uint32_t*>(sc)[i] = 0u;
