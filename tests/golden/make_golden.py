@@ -157,6 +157,40 @@ def make_direct():
     np.savez_compressed(os.path.join(HERE, "direct_v1.npz"), **rec)
 
 
+def make_dso_stereo_vocab():
+    rec = {}
+    # DSO key-point selection over a 3-frame stream (adaptive grid carried across frames)
+    w, h, nf = 480, 360, 400
+    frames = synth.synth_stream(11, 3, w, h)
+    ox = O.Extractor(nf, 1.2, 8, 20, 7)
+    base, _ = ox.extract(frames[0])
+    existing = base[(base["octave"] == 0) & (base["x"] > 30) & (base["y"] > 30) & (base["x"] < w - 30) & (base["y"] < h - 30)][::5].copy()
+    g = -1
+    for i, f in enumerate(frames):
+        kps, desc, g = ox.extract_frame_dso(f, existing, g)
+        rec["dso_kps%d" % i], rec["dso_desc%d" % i], rec["dso_grid%d" % i] = kps, desc, g
+    rec["dso_frame_sha"] = np.array(sha(frames))
+    # stereo association on a synthetic rectified pair
+    left, right, band, disp = synth.synth_stereo_pair(7, w, h, disparities=(5, 11, 19))
+    oxL = O.Extractor(600, 1.2, 8, 20, 7); oxR = O.Extractor(600, 1.2, 8, 20, 7)
+    kL, dL = oxL.extract(left); kR, dR = oxR.extract(right)
+    t = oxL.tables()
+    pyrL = pkg.make_direct_frame([oxL.level(l).copy() for l in range(8)])
+    pyrR = pkg.make_direct_frame([oxR.level(l).copy() for l in range(8)])
+    u, z, n = O.compute_stereo_matches(pyrL, pyrR, kL, dL, kR, dR, t["scale"], t["inv_scale"], 0.5, 100.0)
+    rec["st_u"], rec["st_z"], rec["st_n"], rec["st_right_sha"] = u, z, n, np.array(sha(right))
+    # vocabulary transform on a synthetic tree
+    data = synth.synth_vocabulary(3, k=6, L=3)
+    v = O.Vocabulary(data=data)
+    q, tt, _ = synth.synth_descriptors(5, 400, 400)
+    wid, wgt, nid = v.transform_features(np.concatenate([q, tt]), 2)
+    ids, vals, fv = v.transform(q, 2)
+    rec["voc_sha"] = np.array(sha(np.frombuffer(data, np.uint8)))
+    rec["voc_wid"], rec["voc_w"], rec["voc_nid"], rec["voc_bow_ids"], rec["voc_bow_vals"] = wid, wgt, nid, ids, vals
+    np.savez_compressed(os.path.join(HERE, "f_rows_v1.npz"), **rec)
+    print("f rows", [len(rec["dso_kps%d" % i]) for i in range(3)], n, len(ids))
+
+
 if __name__ == "__main__":
     make_prims()
     make_extract("c1_752x480_seed1", 1, 752, 480, 1000, 1.2, 8)
@@ -166,3 +200,4 @@ if __name__ == "__main__":
     make_matcher()
     make_sia()
     make_direct()
+    make_dso_stereo_vocab()

@@ -82,3 +82,39 @@ def test_sia_fixture(oracle, pkg, synth):
         assert np.abs(q - g["q%d" % seed]).max() < 1e-6 and np.abs(t - g["t%d" % seed]).max() < 1e-6
         assert len(tr) == len(g["trace%d" % seed])
         assert T.pose_diff(q, t, s["q_true"], s["t_true"]) < 5e-3
+
+
+def test_f_rows_fixture(oracle, pkg, synth):
+    """Oracle regression pins of the SURVEY 8(f) rows without their own fixture file: DSO key points over a stream,
+    ComputeStereoMatches, vocabulary transform (tests/golden/f_rows_v1.npz, made by make_golden.py)."""
+    g = np.load(os.path.join(GOLD, "f_rows_v1.npz"))
+    w, h, nf = 480, 360, 400
+    frames = synth.synth_stream(11, 3, w, h)
+    assert sha(frames) == str(g["dso_frame_sha"])
+    ox = oracle.Extractor(nf, 1.2, 8, 20, 7)
+    base, _ = ox.extract(frames[0])
+    existing = base[(base["octave"] == 0) & (base["x"] > 30) & (base["y"] > 30) & (base["x"] < w - 30) & (base["y"] < h - 30)][::5].copy()
+    grid = -1
+    for i, f in enumerate(frames):
+        kps, desc, grid = ox.extract_frame_dso(f, existing, grid)
+        assert grid == int(g["dso_grid%d" % i]) and len(kps) == len(g["dso_kps%d" % i])
+        for fld in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+            assert (kps[fld] == g["dso_kps%d" % i][fld]).all(), (i, fld)
+        assert (desc == g["dso_desc%d" % i]).all()
+    left, right, band, disp = synth.synth_stereo_pair(7, w, h, disparities=(5, 11, 19))
+    assert sha(right) == str(g["st_right_sha"])
+    oxL = oracle.Extractor(600, 1.2, 8, 20, 7); oxR = oracle.Extractor(600, 1.2, 8, 20, 7)
+    kL, dL = oxL.extract(left); kR, dR = oxR.extract(right)
+    t = oxL.tables()
+    pyrL = pkg.make_direct_frame([oxL.level(l).copy() for l in range(8)])
+    pyrR = pkg.make_direct_frame([oxR.level(l).copy() for l in range(8)])
+    u, z, n = oracle.compute_stereo_matches(pyrL, pyrR, kL, dL, kR, dR, t["scale"], t["inv_scale"], 0.5, 100.0)
+    assert n == int(g["st_n"]) and (u.view(np.uint32) == g["st_u"].view(np.uint32)).all() and (z.view(np.uint32) == g["st_z"].view(np.uint32)).all()
+    data = synth.synth_vocabulary(3, k=6, L=3)
+    assert sha(np.frombuffer(data, np.uint8)) == str(g["voc_sha"])
+    v = oracle.Vocabulary(data=data)
+    q, tt, _ = synth.synth_descriptors(5, 400, 400)
+    wid, wgt, nid = v.transform_features(np.concatenate([q, tt]), 2)
+    ids, vals, fv = v.transform(q, 2)
+    assert (wid == g["voc_wid"]).all() and (nid == g["voc_nid"]).all() and (wgt.view(np.uint32) == g["voc_w"].view(np.uint32)).all()
+    assert (ids == g["voc_bow_ids"]).all() and (vals == g["voc_bow_vals"]).all()
