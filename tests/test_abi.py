@@ -61,6 +61,16 @@ def test_product_does_not_link_or_import_the_oracle():
                 assert "oracle_lib" not in txt and "libygz_oracle" not in txt and "ygz_oracle.h" not in txt, f
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/ygz_b200.h is a C ABI: it compiles as C99 with -pedantic (no C++ types, no default arguments)."""
+    import subprocess
+    src = tmp_path / "c_check.c"
+    src.write_text('#include "ygz_b200.h"\nint main(void) { return ygz_device_count() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "c_check.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_cpp_class_mirror_compiles_and_links(tmp_path):
     """include/ygz/*.h (the reference-named C++ classes) compile against the C ABI and link with the library."""
     import subprocess
