@@ -87,6 +87,7 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
  * ShiTomasiScore :1152-1186, three best corners per cell, cell size shrunk by 5 until nfeatures are found) on level 0,
  * then descriptors of the n_existing keys (angles refreshed by IC_Angle, :1377-1380) and of the new keys (size 7,
  * octave 0).  *grid_size carries mnGridSize from frame to frame (-1 before the first frame; NULL: kept in the handle).
+ * Like ygz_orb_extract_frame it may grow the handle's output capacity (ygz_orb_max_keypoints) to hold existing + new keys.
  * SURVEY.md §8(f) rank 2. */
 int ygz_orb_extract_frame_dso(ygz_orb* h, const uint8_t* image, int row_stride, int n_existing, ygz_keypoint* kps,
                               uint8_t* desc, int* count, int cap, int* grid_size);

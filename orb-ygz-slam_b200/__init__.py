@@ -225,7 +225,6 @@ class ORBextractor:
         self.h = C.c_void_p()
         _check(self.L.ygz_orb_create(C.byref(self.cfg), C.byref(self.h)), "ygz_orb_create")
         self.nlevels, self.width, self.height, self.max_batch = nlevels, width, height, max_batch
-        self.cap = self.L.ygz_orb_max_keypoints(self.h)
 
     def close(self):
         if getattr(self, "h", None):
@@ -282,6 +281,11 @@ class ORBextractor:
 
     def __call__(self, image, mask=None):
         return self.extract_batch(image)[0]
+
+    @property
+    def cap(self):
+        """Rows per frame of the device output arrays (ygz_orb_max_keypoints); extract_frame / extract_frame_dso may grow it."""
+        return self.L.ygz_orb_max_keypoints(self.h)
 
     def extract_frame(self, image, existing):
         image = self._imgs(image)[0]
