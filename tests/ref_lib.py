@@ -1,0 +1,107 @@
+"""ctypes binding of oracle/_ref/libextractor_ref.so: the REFERENCE's own ygz::ORBextractor (src/ORBextractor.cc compiled
+unmodified against oracle/ref_mock).  TEST INFRASTRUCTURE ONLY — the pin of the oracle restatement."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from oracle_lib import KP_DTYPE, ORACLE_DIR, _ptr, f32p, u8p
+
+class RefThrows(Exception):
+    """The reference raised a C++ exception (e.g. std::length_error from vpIniNodes.resize(nIni < 0), src/ORBextractor.cc:545)."""
+
+
+REF_SRC = "/root/reference/src/ORBextractor.cc"
+_LIBS = {}
+
+
+def _load(name):
+    if name in _LIBS:
+        return _LIBS[name]
+    path = os.path.join(ORACLE_DIR, "_ref", name)
+    if os.path.exists(REF_SRC):                 # build container: (re)build from the reference where it lies
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "_ref/" + name], check=True)
+    if not os.path.exists(path):
+        _LIBS[name] = None
+        return None
+    _LIBS[name] = C.CDLL(path)
+    return _LIBS[name]
+
+
+def extractor_lib():
+    L = _load("libextractor_ref.so")
+    if L is None:
+        return None
+    L.ref_orb_create.restype = C.c_void_p
+    L.ref_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.ref_orb_destroy.argtypes = [C.c_void_p]
+    L.ref_orb_tables.argtypes = [C.c_void_p, C.c_int, f32p]
+    L.ref_orb_extract.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.ref_orb_frame_pyramid.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, C.c_int]
+    L.ref_orb_level.argtypes = [C.c_void_p, C.c_int, C.c_int, u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.ref_orb_extract_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.ref_arena.argtypes = [C.c_int]
+    return L
+
+
+class RefExtractor:
+    """The reference's ygz::ORBextractor (include/ORBextractor.h:45-172)."""
+    ORBSLAM_KEYPOINT, FAST_KEYPOINT, DSO_KEYPOINT = 0, 1, 2
+
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, creation_order=True):
+        self.L = extractor_lib()
+        assert self.L is not None, "oracle/_ref/libextractor_ref.so is missing"
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.creation_order = creation_order
+        self.h = self.L.ref_orb_create(nfeatures, scale, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        try:
+            self.L.ref_orb_destroy(self.h)
+        except Exception:
+            pass
+
+    def tables(self):
+        out = {}
+        for i, k in enumerate(("scale", "inv_scale", "sigma2", "inv_sigma2")):
+            v = np.zeros(self.nlevels, np.float32)
+            self.L.ref_orb_tables(self.h, i, _ptr(v, f32p))
+            out[k] = v
+        return out
+
+    def extract(self, img, cap=None):
+        """operator()(image, mask, keypoints, descriptors)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = cap or (self.nfeatures * 2 + 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        self.L.ref_arena(int(self.creation_order))
+        n = self.L.ref_orb_extract(self.h, _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0],
+                                   kps.ctypes.data, _ptr(desc, u8p), cap)
+        if n == -2:
+            raise RefThrows()
+        assert 0 <= n <= cap, n
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, level, border=0):
+        w, h = C.c_int(), C.c_int()
+        assert self.L.ref_orb_level(self.h, level, border, None, C.byref(w), C.byref(h)) == 0
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.L.ref_orb_level(self.h, level, border, _ptr(out, u8p), C.byref(w), C.byref(h))
+        return out
+
+    def extract_frame(self, img, existing, method=0, cap=None):
+        """Frame ctor pyramid (src/Frame.cc:807-813) + operator()(Frame*, frame->mvKeys, desc, method, leftEye=true)"""
+        img = np.ascontiguousarray(img, np.uint8)
+        existing = np.ascontiguousarray(existing, KP_DTYPE)
+        ne = len(existing)
+        cap = cap or (3 * (img.shape[0] // 7) * (img.shape[1] // 7) + self.nfeatures * 2 + ne + 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        self.L.ref_arena(int(self.creation_order))
+        self.L.ref_orb_frame_pyramid(self.h, _ptr(img, u8p), img.shape[1], img.shape[0], img.strides[0])
+        n = self.L.ref_orb_extract_frame(self.h, method, existing.ctypes.data, ne, kps.ctypes.data, _ptr(desc, u8p), cap)
+        if n == -2:
+            raise RefThrows()
+        assert 0 <= n <= cap, n
+        return kps[:n].copy(), desc[:n].copy()
