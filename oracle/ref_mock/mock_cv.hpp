@@ -179,6 +179,19 @@ public:
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
     Mat row(int y) const { return rowRange(y, y + 1); }
+    Mat col(int x) const { return colRange(x, x + 1); }
+    // CV_32F matrix algebra of the back-end matcher variants (src/ORBmatcher.cc:274-278, 897-901, 1014-1024): OpenCV's
+    // generic 32F GEMM / dot / norm accumulate in double and round the result to float once.
+    Mat t() const {
+        Mat m(cols, rows, type());
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) m.at<float>(x, y) = at<float>(y, x);
+        return m;
+    }
+    double dot(const Mat& o) const {
+        double r = 0;
+        for (int y = 0; y < rows; y++) for (int x = 0; x < cols; x++) r += (double)at<float>(y, x) * o.at<float>(y, x);
+        return r;
+    }
 
     int type() const { return flags & 0xfff; }
     int depth() const { return flags & 7; }
@@ -199,6 +212,34 @@ public:
     template <class T> T& at(int i) { return rows == 1 ? ((T*)data)[i] : *(T*)(data + (size_t)i * step.buf[0]); }
     template <class T> const T& at(int i) const { return rows == 1 ? ((const T*)data)[i] : *(const T*)(data + (size_t)i * step.buf[0]); }
 };
+
+static inline Mat operator*(const Mat& a, const Mat& b) {
+    Mat m(a.rows, b.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++)
+        for (int j = 0; j < b.cols; j++) {
+            double s = 0;
+            for (int k = 0; k < a.cols; k++) s += (double)a.at<float>(i, k) * b.at<float>(k, j);
+            m.at<float>(i, j) = (float)s;
+        }
+    return m;
+}
+static inline Mat mock_ew(const Mat& a, const Mat& b, int sign) {
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) m.at<float>(i, j) = sign > 0 ? a.at<float>(i, j) + b.at<float>(i, j) : a.at<float>(i, j) - b.at<float>(i, j);
+    return m;
+}
+static inline Mat mock_scale(const Mat& a, double s) {
+    Mat m(a.rows, a.cols, CV_32F);
+    for (int i = 0; i < a.rows; i++) for (int j = 0; j < a.cols; j++) m.at<float>(i, j) = (float)(a.at<float>(i, j) * s);
+    return m;
+}
+static inline Mat operator+(const Mat& a, const Mat& b) { return mock_ew(a, b, 1); }
+static inline Mat operator-(const Mat& a, const Mat& b) { return mock_ew(a, b, -1); }
+static inline Mat operator-(const Mat& a) { return mock_scale(a, -1.0); }
+static inline Mat operator*(const Mat& a, double s) { return mock_scale(a, s); }
+static inline Mat operator*(double s, const Mat& a) { return mock_scale(a, s); }
+static inline Mat operator/(const Mat& a, double s) { return mock_scale(a, 1.0 / s); }
+static inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
 
 template <class T> class Mat_ : public Mat {
 public:

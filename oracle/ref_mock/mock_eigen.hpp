@@ -51,6 +51,17 @@ template <class T, int R, int C, int Opt = 0> struct Matrix {
     Matrix normalized() const { T n = norm(); Matrix m(*this); for (int i = 0; i < R * C; i++) m.d[i] /= n; return m; }
     Matrix<T, 1, C> row(int i) const { Matrix<T, 1, C> m; for (int j = 0; j < C; j++) m.d[j] = (*this)(i, j); return m; }
     Matrix<T, R, 1> col(int j) const { Matrix<T, R, 1> m; for (int i = 0; i < R; i++) m.d[i] = (*this)(i, j); return m; }
+    struct ColRef {
+        Matrix& m; int j;
+        ColRef& operator=(const Matrix<T, R, 1>& v) { for (int i = 0; i < R; i++) m(i, j) = v.d[i]; return *this; }
+        operator Matrix<T, R, 1>() const { return const_cast<const Matrix&>(m).col(j); }
+    };
+    ColRef col(int j) { return ColRef{*this, j}; }
+    struct CommaInit {
+        Matrix& m; int n;
+        CommaInit& operator,(T v) { m.d[n++] = v; return *this; }
+    };
+    CommaInit operator<<(T v) { d[0] = v; return CommaInit{*this, 1}; }
     template <class U> Matrix<U, R, C> cast() const { Matrix<U, R, C> m; for (int i = 0; i < R * C; i++) m.d[i] = (U)d[i]; return m; }
     T determinant() const {
         static_assert(R == C && (R == 2 || R == 3), "determinant: 2x2 / 3x3 only");
@@ -68,7 +79,9 @@ template <class T, int R, int C, int Opt = 0> struct Matrix {
             m(0, 0) = a(1, 1) * id; m(0, 1) = -a(0, 1) * id; m(1, 0) = -a(1, 0) * id; m(1, 1) = a(0, 0) * id;
             return m;
         }
-        T id = T(1) / determinant();
+        // Eigen's compute_inverse_size3: det = sum_k cofactor<k,0> * m(k,0), result(i,j) = cofactor<j,i> * (1/det)
+        T c0 = a(1, 1) * a(2, 2) - a(1, 2) * a(2, 1), c1 = a(2, 1) * a(0, 2) - a(2, 2) * a(0, 1), c2 = a(0, 1) * a(1, 2) - a(0, 2) * a(1, 1);
+        T id = T(1) / ((c0 * a(0, 0) + c1 * a(1, 0)) + c2 * a(2, 0));
         for (int i = 0; i < 3; i++)
             for (int j = 0; j < 3; j++) {
                 int i1 = (j + 1) % 3, i2 = (j + 2) % 3, j1 = (i + 1) % 3, j2 = (i + 2) % 3;

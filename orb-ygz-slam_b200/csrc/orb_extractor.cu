@@ -2,6 +2,7 @@
 // ORBextractor constructor and cell loop (src/ORBextractor.cc:412-470, 725-762, 1129-1133), device
 // buffers, kernel launches and the extern "C" entry points declared in include/ygz_b200.h.
 #include "orb_kernels.cuh"
+#include "fast_cells_v2.cuh"
 #include "dso_kernels.cuh"
 #include "trig_glibc.cuh"
 #include <algorithm>
@@ -58,6 +59,10 @@ struct ygz_orb {
     float4* d_pattern = nullptr;
     TmaMaps tma;
     PatchMaps patch;
+    FastMaps fastmaps;
+    int* d_fast_ids = nullptr;          // [narrow cells (k_fast_cells_v2)] ++ [the rest (k_fast_cells)]
+    int n_fast_narrow = 0, n_fast_wide = 0;
+    int fast_v2_grid = 0;
     BlurTile* d_blur_tiles = nullptr;
     int n_blur_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0;
@@ -108,7 +113,7 @@ static int orb_free(ygz_orb* h) {
     if (!h) return YGZ_OK;
     cudaSetDevice(h->device);
     for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_blur); cudaFree(L.d_tx); cudaFree(L.d_ty); }
-    cudaFree(h->d_blur_tiles);
+    cudaFree(h->d_blur_tiles); cudaFree(h->d_fast_ids);
     cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_pts);
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
@@ -354,6 +359,40 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         TRY_OR_FREE(cudaMemcpy(h->d_blur_tiles, tiles.data(), tiles.size() * sizeof(BlurTile), cudaMemcpyHostToDevice));
     }
     {
+        // FAST cells: k_fast_cells_v2 (TMA box per cell, one lane per detection column) takes the cells with a detection window
+        // of at most 32 columns and a cell image of at most F2_MAX_CH rows on levels that have a tensor map; k_fast_cells the rest.
+        std::memset(&h->fastmaps, 0, sizeof(h->fastmaps));
+        std::vector<int> narrow, wide;
+        unsigned ok = 0;
+        for (int l = 0; l < nl; l++) {
+            const LevelHost& L = h->lv[l];
+            int maxch = 0;
+            for (int c = h->P.lv[l].cell_begin; c < h->P.lv[l].cell_end; c++)
+                if (h->cells[c].cw - 6 <= F2_MAX_DW && h->cells[c].ch <= F2_MAX_CH) maxch = std::max(maxch, (int)h->cells[c].ch);
+            if (maxch > 6 && !getenv("YGZ_NO_TMA") && !getenv("YGZ_FAST_V1") && L.w >= F2_PITCH && L.h >= maxch + 1 &&
+                make_tensor_map_u8_3d(&h->fastmaps.level[l], L.d_base, L.w, L.h, B, L.pitch, L.frame_stride, F2_PITCH, maxch + 1) == 0) {
+                ok |= 1u << l;
+                h->fastmaps.boxh[l] = (unsigned char)(maxch + 1);
+            }
+        }
+        for (int c = 0; c < (int)h->cells.size(); c++) {
+            const CellDesc& cd = h->cells[c];
+            const bool v2 = ((ok >> cd.level) & 1u) && cd.cw > 6 && cd.ch > 6 && cd.cw - 6 <= F2_MAX_DW && cd.ch <= F2_MAX_CH;
+            (v2 ? narrow : wide).push_back(c);
+        }
+        h->n_fast_narrow = (int)narrow.size();
+        h->n_fast_wide = (int)wide.size();
+        narrow.insert(narrow.end(), wide.begin(), wide.end());
+        TRY_OR_FREE(cudaMalloc(&h->d_fast_ids, std::max<size_t>(narrow.size(), 1) * sizeof(int)));
+        if (!narrow.empty())
+            TRY_OR_FREE(cudaMemcpy(h->d_fast_ids, narrow.data(), narrow.size() * sizeof(int), cudaMemcpyHostToDevice));
+        TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_WARPS * F2_WARP_SMEM));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        h->fast_v2_grid = sms * 4;                       // persistent: 4 resident CTAs per SM (registers and shared memory)
+        if (const char* e = getenv("YGZ_FAST_V2_CTAS")) h->fast_v2_grid = sms * std::max(1, atoi(e));
+    }
+    {
         std::vector<float> fp(256 * 4);
         for (int t = 0; t < 256; t++)            // test t = 8 * byte + j  ->  slot j * 32 + byte
             for (int c = 0; c < 4; c++) fp[((t & 7) * 32 + (t >> 3)) * 4 + c] = (float)h_pattern[t * 4 + c];
@@ -412,6 +451,9 @@ int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride
     return YGZ_OK;
 }
 
+// kernels launch_detect issues: k_fast_cells_v2 for the narrow cells, k_fast_cells for the rest
+static inline int fast_launches(const ygz_orb* h) { return (h->n_fast_narrow > 0) + (h->n_fast_wide > 0); }
+
 static int launch_pyramid(ygz_orb* h, int n) {
     for (int l = 1; l < h->cfg.nlevels; l++) {
         const LevelHost& S = h->lv[l - 1];
@@ -426,9 +468,16 @@ static int launch_pyramid(ygz_orb* h, int n) {
 }
 
 static int launch_detect(ygz_orb* h, int n) {
-    if (h->P.n_cells > 0) {
-        dim3 grid(ceil_div(h->P.n_cells, FAST_WARPS), n);
-        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->fast_warp_smem);
+    if (h->n_fast_narrow > 0) {
+        const int items = h->n_fast_narrow * n;
+        const int grid = std::min(h->fast_v2_grid, ceil_div(items, F2_WARPS));
+        k_fast_cells_v2<<<grid, F2_THREADS, F2_WARPS * F2_WARP_SMEM, h->stream>>>(h->P, h->fastmaps, h->d_cells, h->d_fast_ids, h->n_fast_narrow, n,
+                                                                                  h->d_pool, h->d_cell_count);
+    }
+    if (h->n_fast_wide > 0) {
+        dim3 grid(ceil_div(h->n_fast_wide, FAST_WARPS), n);
+        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_fast_ids + h->n_fast_narrow, h->n_fast_wide,
+                                                                      h->d_pool, h->d_cell_count, h->fast_warp_smem);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     return YGZ_OK;
@@ -471,7 +520,7 @@ int ygz_orb_run(ygz_orb* h, int n) {
     if ((rc = launch_octree(h, n))) return rc;
     if ((rc = launch_blur(h, n))) return rc;
     if ((rc = launch_describe(h, n, 0))) return rc;
-    h->launches_per_run = (h->cfg.nlevels - 1) + 4;
+    h->launches_per_run = (h->cfg.nlevels - 1) + 3 + fast_launches(h);
     h->ctr.kernel_launches += h->launches_per_run;
     h->ctr.frames += n;
     h->last_n = n;
@@ -594,7 +643,7 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
     if ((rc = launch_octree(h, 1))) return rc;
     if ((rc = launch_blur(h, 1))) return rc;
     if ((rc = launch_describe(h, 1, n_existing))) return rc;
-    h->ctr.kernel_launches += (h->cfg.nlevels - 1) + 4 + (n_existing > 0);
+    h->ctr.kernel_launches += (h->cfg.nlevels - 1) + 3 + fast_launches(h) + (n_existing > 0);
     h->ctr.frames += 1;
     YGZ_CUDA_TRY(cudaMemcpyAsync(count, h->d_counts, 4, cudaMemcpyDeviceToHost, h->stream));
     YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -798,8 +847,8 @@ int ygz_orb_time(ygz_orb* h, int n, int iters, float* stage_ms, int* launches) {
         acc[5] += ms;
     }
     for (int s = 0; s < 6; s++) stage_ms[s] = acc[s];
-    if (launches) *launches = ((h->cfg.nlevels - 1) + 4) * iters;
-    h->ctr.kernel_launches += (uint64_t)((h->cfg.nlevels - 1) + 4) * iters;
+    if (launches) *launches = ((h->cfg.nlevels - 1) + 3 + fast_launches(h)) * iters;
+    h->ctr.kernel_launches += (uint64_t)((h->cfg.nlevels - 1) + 3 + fast_launches(h)) * iters;
     h->ctr.frames += (uint64_t)n * iters;
     return YGZ_OK;
 }

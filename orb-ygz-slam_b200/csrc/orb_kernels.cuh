@@ -209,13 +209,17 @@ __host__ __device__ inline int fast_warp_smem(int cw, int ch) {
 }
 
 // (A compile-time tile pitch for the common <= 37 px cells was measured: same 1.09 ms, so only this flavour is kept.)
+// `ids` (optional): the cells this launch covers — the generic kernel handles the cells k_fast_cells_v2 does not take
+// (detection window wider than 32 columns, cell image taller than its TMA box, or a level without a tensor map).
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(OrbParams P, const CellDesc* __restrict__ cells,
+                                                             const int* __restrict__ ids, int n_ids,
                                                              uint32_t* __restrict__ pool,
                                                              uint16_t* __restrict__ cell_count, int warp_smem) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cell = blockIdx.x * FAST_WARPS + warp;
-    if (cell >= P.n_cells) return;
+    const int slot = blockIdx.x * FAST_WARPS + warp;
+    if (slot >= n_ids) return;
+    const int cell = ids ? ids[slot] : slot;
     const int frame = blockIdx.y;
     const CellDesc cd = cells[cell];
     const LevelDev& L = P.lv[cd.level];

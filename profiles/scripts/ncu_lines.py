@@ -12,8 +12,8 @@ start=[i for i,l in enumerate(txt) if '.text.'+mangled in l and '.section' in l]
 cur=None; amap={}
 for l in txt[start+1:]:
     if l.startswith('//---------------------') and amap: break
-    m=re.search(r'//## File ".*?", line (\d+)',l)
-    if m: cur=int(m.group(1)); continue
+    m=re.search(r'//## File "(.*?)", line (\d+)',l)
+    if m: cur=(os.path.basename(m.group(1)),int(m.group(2))); continue
     m=re.match(r'\s+/\*([0-9a-f]{4,5})\*/',l)
     if m and cur is not None: amap[int(m.group(1),16)]=cur
 raw=subprocess.run(['ncu','-i',rep,'--page','source','--csv','--kernel-name','regex:'+kname],capture_output=True,text=True).stdout
@@ -27,11 +27,18 @@ for r in rows[hi+1:]:
     if 'Instructions Executed' in r: break   # second kernel instance
     a=int(r[ad],16) if r[ad].startswith('0x') else int(r[ad])
     if base is None: base=a
-    line=amap.get(a-base,-1)
+    line=amap.get(a-base,('?',-1))
     per[line]=per.get(line,0)+f(r[ie]); pers[line]=pers.get(line,0)+f(r[st])
 tot=sum(per.values()); tots=sum(pers.values())
-src=open('/root/repo/orb-ygz-slam_b200/csrc/orb_kernels.cuh').read().split('\n')
+srcs={}
+def srcline(fl):
+    f,l=fl
+    if f not in srcs:
+        try: srcs[f]=open('/root/repo/orb-ygz-slam_b200/csrc/'+f).read().split('\n')
+        except Exception: srcs[f]=None
+    return srcs[f][l-1].strip()[:95] if srcs[f] and 0<l<=len(srcs[f]) else '?'
+thr=float(sys.argv[4]) if len(sys.argv)>4 else 0.012
 print('total warp inst',tot,'samples',tots)
 for line in sorted(per):
-    if per[line]>tot*0.012 or pers[line]>tots*0.012:
-        print('%5d %5.1f%% inst %5.1f%% stall | %s'%(line,per[line]/tot*100,pers[line]/tots*100,src[line-1].strip()[:95] if line>0 else '?'))
+    if per[line]>tot*thr or pers[line]>tots*thr:
+        print('%-16s %5d %5.1f%% inst %5.1f%% stall | %s'%(line[0][:16],line[1],per[line]/tot*100,pers[line]/tots*100,srcline(line)))
