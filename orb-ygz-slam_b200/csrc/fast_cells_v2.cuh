@@ -30,8 +30,8 @@ constexpr int F2_MAX_CH = F2_BOXH_MAX - 1;      // 43 -> dh <= 37
 constexpr int F2_TILE_BYTES = F2_PITCH * F2_BOXH_MAX;   // 2816 = 22 * 128 (TMA destination alignment)
 constexpr int F2_SCP = 36;                      // score-map pitch (dw + 2 <= 34)
 constexpr int F2_SC_BYTES = F2_SCP * 40;        // (dh + 2 <= 39) rows
-constexpr int F2_ITEMS_BYTES = 2 * F2_MAX_DW * 38;      // u16 per pre-test survivor, worst case every pixel
-constexpr int F2_WARP_SMEM = 6784;              // 2816 + 1440 + 2432 + 8 (mbarrier), rounded to 128
+constexpr int F2_ITEMS_BYTES = 2 * F2_MAX_DW * 38;      // u16 per pre-test survivor, worst case every pixel of dh (rounded up to even) rows
+constexpr int F2_WARP_SMEM = 6784;              // 2816 + 1440 + 2432 + 8 (mbarrier), rounded to 128; 8 warps x 4 CTAs fit one SM
 
 struct FastMaps {                               // per level: raw u8 [frames][h][pitch], box F2_PITCH x boxh[l] x 1
     CUtensorMap level[MAX_LEVELS];
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                                                                 const __grid_constant__ FastMaps maps,
                                                                 const CellDesc* __restrict__ cells,
                                                                 const int* __restrict__ ids, int n_ids, int n_frames,
+                                                                int n_static, int* __restrict__ queue,
                                                                 uint32_t* __restrict__ pool,
                                                                 uint16_t* __restrict__ cell_count) {
     extern __shared__ __align__(128) uint8_t f2_smem[];
@@ -58,9 +59,21 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
     unsigned long long* const bar = reinterpret_cast<unsigned long long*>(sc + F2_SC_BYTES + F2_ITEMS_BYTES);
     constexpr int TP = F2_PITCH;
 
+    // Work items (frame, cell), frame-major.  The first n_static items are dealt to the warps round-robin; the rest are
+    // drawn from a global counter (one atomic per item) so that no warp is left with a long tail: cells differ in cost
+    // by the texture they cover, and a static deal left a quarter of the warp slots idle at the end of the launch.
     const int n_items = n_ids * n_frames;
     const int stride = gridDim.x * F2_WARPS;
     int item = blockIdx.x * F2_WARPS + warp;
+    auto next_item = [&](int cur) {
+        int nx = cur + stride;
+        if (nx >= n_static) {
+            if (lane == 0) nx = n_static + atomicAdd(queue, 1);
+            nx = __shfl_sync(0xffffffffu, nx, 0);
+        }
+        return nx;
+    };
+    if (item >= n_static) item = next_item(n_static);       // fewer static items than warps: this one starts on the queue
     if (item >= n_items) return;
 
     if (lane == 0) mbar_init(bar, 1);
@@ -85,13 +98,14 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                   o7 = -3 * TP + 1, o8 = -3 * TP, o9 = -3 * TP - 1, o10 = -2 * TP - 2, o11 = -TP - 3, o12 = -3,
                   o13 = TP - 3, o14 = 2 * TP - 2, o15 = 3 * TP - 1;
 
-    for (; item < n_items; item += stride) {
+    while (item < n_items) {
+        const int nxt = next_item(item);
         const int frame = item / n_ids;
         const int cell = ids[item - frame * n_ids];
         const CellDesc cd = cells[cell];
         const int dw = cd.cw - 6, dh = cd.ch - 6;
         const uint8_t* const t00 = tile + 3 * TP + 3 + (cd.x0 & 15);       // pixel (0,0) of the detection window
-        const bool has_next = item + stride < n_items;
+        const bool has_next = nxt < n_items;
         mbar_wait(bar, phase);
         phase ^= 1;
         bool prefetched = false;
@@ -120,7 +134,8 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                 unsigned q8a = F2_LD2(-3 * TP), q8b = F2_LD2(-TP), q8c = F2_LD2(TP);            // rows (-3,-2) (-1,0) (1,2), dx 0
                 unsigned q6a = F2_LD2(-2 * TP + 2), q6b = F2_LD2(2);                             // rows (-2,-1) (0,1), dx +2
                 unsigned q10a = F2_LD2(-2 * TP - 2), q10b = F2_LD2(-2);                          // rows (-2,-1) (0,1), dx -2
-                unsigned itv = (unsigned)lane;                                                   // lane | y << 6
+                unsigned itv = (unsigned)lane;                                                   // x | y << 6
+                int n1 = 0;
 #pragma unroll 6
                 for (int y = 0; y < dh; y += 2, p += 2 * TP, itv += 128u) {
                     const unsigned c2 = F2_LD2(0), A4 = F2_LD2(o4), A12 = F2_LD2(o12);
@@ -131,17 +146,19 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                     q10a = q10b; q10b = A14;
                     const unsigned bmin = __vminu2(__vminu2(__vmaxu2(A0, A8), __vmaxu2(A4, A12)), __vminu2(__vmaxu2(A2, A10), __vmaxu2(A6, A14)));
                     const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(A0, A8), __vminu2(A4, A12)), __vmaxu2(__vminu2(A2, A10), __vminu2(A6, A14)));
-                    unsigned z = ((bmin + K3 - c2) | (c2 + K3 - dmax)) & lane_mask;
-                    if (y + 1 >= dh) z &= 0xFFFFu;
-                    const unsigned p0 = z & 0x8000u, p1 = z >> 31;
+                    const unsigned z = ((bmin + K3 - c2) | (c2 + K3 - dmax)) & lane_mask;
+                    const bool p0 = (z & 0x8000u) != 0u, p1 = (int)z < 0;
                     const unsigned bal0 = __ballot_sync(0xffffffffu, p0);
                     const unsigned bal1 = __ballot_sync(0xffffffffu, p1);
                     const int n0 = __popc(bal0);
+                    n1 = __popc(bal1);
                     if (p0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)itv;
                     if (p1) items[total + n0 + __popc(bal1 & lanemask_lt())] = (uint16_t)(itv + 64u);
-                    total += n0 + __popc(bal1);
+                    total += n0 + n1;
                 }
 #undef F2_LD2
+                // odd dh: the last step also tested row dh, one past the window; its survivors are the tail of the list
+                if (dh & 1) total -= n1;
             }
             __syncwarp();
 
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
             }
             __syncwarp();
             // the tile is dead unless the minTh pass may still be needed (only when iniTh found no corner at all)
-            if (!prefetched && has_next && (pass == 1 || ncorn > 0)) { issue(item + stride); prefetched = true; }
+            if (!prefetched && has_next && (pass == 1 || ncorn > 0)) { issue(nxt); prefetched = true; }
 
             // ---- phase C+D: 3x3 non-max suppression inside the detection window (strict >, zeros outside) and ordered
             //      emission, coordinates relative to (16,16)
@@ -194,11 +211,12 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
             for (int g = lane; g < ncorn; g += 32) { const int it = items[g]; sc[((it >> 6) + 1) * F2_SCP + (it & 63) + 1] = 0; }
             __syncwarp();
         }
-        if (!prefetched && has_next) { __syncwarp(); issue(item + stride); }
+        if (!prefetched && has_next) { __syncwarp(); issue(nxt); }
         if (lane == 0) cell_count[(size_t)frame * P.n_cells + cell] = (uint16_t)min(nkeep, (int)cd.cap);
         // leave the score map clear for the next cell
         for (int g = lane; g < ncorn; g += 32) { const int it = items[g]; sc[((it >> 6) + 1) * F2_SCP + (it & 63) + 1] = 0; }
         __syncwarp();
+        item = nxt;
     }
 }
 

@@ -61,6 +61,9 @@ struct ygz_orb {
     PatchMaps patch;
     FastMaps fastmaps;
     int* d_fast_ids = nullptr;          // [narrow cells (k_fast_cells_v2)] ++ [the rest (k_fast_cells)]
+    int* d_fast_queue = nullptr;        // work counter of k_fast_cells_v2 (zeroed before every launch)
+    cudaStream_t aux_stream = nullptr;  // the generic FAST kernel (few, wide cells) runs beside k_fast_cells_v2
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int n_fast_narrow = 0, n_fast_wide = 0;
     int fast_v2_grid = 0;
     BlurTile* d_blur_tiles = nullptr;
@@ -113,7 +116,10 @@ static int orb_free(ygz_orb* h) {
     if (!h) return YGZ_OK;
     cudaSetDevice(h->device);
     for (auto& L : h->lv) { cudaFree(L.d_base); cudaFree(L.d_blur); cudaFree(L.d_tx); cudaFree(L.d_ty); }
-    cudaFree(h->d_blur_tiles); cudaFree(h->d_fast_ids);
+    cudaFree(h->d_blur_tiles); cudaFree(h->d_fast_ids); cudaFree(h->d_fast_queue);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_pts);
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
@@ -386,6 +392,10 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         TRY_OR_FREE(cudaMalloc(&h->d_fast_ids, std::max<size_t>(narrow.size(), 1) * sizeof(int)));
         if (!narrow.empty())
             TRY_OR_FREE(cudaMemcpy(h->d_fast_ids, narrow.data(), narrow.size() * sizeof(int), cudaMemcpyHostToDevice));
+        TRY_OR_FREE(cudaMalloc(&h->d_fast_queue, 64));
+        TRY_OR_FREE(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        TRY_OR_FREE(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        TRY_OR_FREE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_WARPS * F2_WARP_SMEM));
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -468,16 +478,31 @@ static int launch_pyramid(ygz_orb* h, int n) {
 }
 
 static int launch_detect(ygz_orb* h, int n) {
+    // the few cells the TMA kernel does not take go first, on the auxiliary stream: one cell per warp is a latency-bound
+    // launch (55 us for 1.5 % of the C1 cells when serialised) that hides completely beside the persistent kernel
+    const bool fork = h->n_fast_wide > 0 && h->n_fast_narrow > 0;
+    if (h->n_fast_wide > 0) {
+        cudaStream_t s = h->stream;
+        if (fork) {
+            YGZ_CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));
+            YGZ_CUDA_TRY(cudaStreamWaitEvent(h->aux_stream, h->ev_fork, 0));
+            s = h->aux_stream;
+        }
+        dim3 grid(ceil_div(h->n_fast_wide, FAST_WARPS), n);
+        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, s>>>(h->P, h->d_cells, h->d_fast_ids + h->n_fast_narrow, h->n_fast_wide,
+                                                              h->d_pool, h->d_cell_count, h->fast_warp_smem);
+        if (fork) YGZ_CUDA_TRY(cudaEventRecord(h->ev_join, h->aux_stream));
+    }
     if (h->n_fast_narrow > 0) {
         const int items = h->n_fast_narrow * n;
         const int grid = std::min(h->fast_v2_grid, ceil_div(items, F2_WARPS));
+        // 3/4 of the items are dealt statically, the last quarter is drawn from the queue (tail balancing)
+        static const int static_pct = getenv("YGZ_FAST_STATIC_PCT") ? atoi(getenv("YGZ_FAST_STATIC_PCT")) : 75;   // tuning knob
+        const int n_static = std::min(items, (int)((long long)items * static_pct / 100) / (grid * F2_WARPS) * (grid * F2_WARPS));
+        YGZ_CUDA_TRY(cudaMemsetAsync(h->d_fast_queue, 0, 4, h->stream));
         k_fast_cells_v2<<<grid, F2_THREADS, F2_WARPS * F2_WARP_SMEM, h->stream>>>(h->P, h->fastmaps, h->d_cells, h->d_fast_ids, h->n_fast_narrow, n,
-                                                                                  h->d_pool, h->d_cell_count);
-    }
-    if (h->n_fast_wide > 0) {
-        dim3 grid(ceil_div(h->n_fast_wide, FAST_WARPS), n);
-        k_fast_cells<<<grid, FAST_THREADS, h->fast_smem, h->stream>>>(h->P, h->d_cells, h->d_fast_ids + h->n_fast_narrow, h->n_fast_wide,
-                                                                      h->d_pool, h->d_cell_count, h->fast_warp_smem);
+                                                                                  n_static, h->d_fast_queue, h->d_pool, h->d_cell_count);
+        if (fork) YGZ_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     return YGZ_OK;
