@@ -148,8 +148,11 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                     const unsigned dmax = __vmaxu2(__vmaxu2(__vminu2(A0, A8), __vminu2(A4, A12)), __vmaxu2(__vminu2(A2, A10), __vminu2(A6, A14)));
                     const unsigned z = ((bmin + K3 - c2) | (c2 + K3 - dmax)) & lane_mask;
                     const bool p0 = (z & 0x8000u) != 0u, p1 = (int)z < 0;
-                    const unsigned bal0 = __ballot_sync(0xffffffffu, p0);
-                    const unsigned bal1 = __ballot_sync(0xffffffffu, p1);
+                    unsigned bal0, bal1;                        // the warp is converged here: two plain VOTEs, one predicate each
+                    asm volatile("{\n\t.reg .pred q0, q1;\n\t.reg .b32 t;\n\t"
+                                 "and.b32 t, %2, 0x8000;\n\tsetp.ne.u32 q0, t, 0;\n\tsetp.lt.s32 q1, %2, 0;\n\t"
+                                 "vote.sync.ballot.b32 %0, q0, 0xffffffff;\n\tvote.sync.ballot.b32 %1, q1, 0xffffffff;\n\t}"
+                                 : "=r"(bal0), "=r"(bal1) : "r"(z));
                     const int n0 = __popc(bal0);
                     n1 = __popc(bal1);
                     if (p0) items[total + __popc(bal0 & lanemask_lt())] = (uint16_t)itv;
