@@ -3,6 +3,7 @@
 // buffers, kernel launches and the extern "C" entry points declared in include/ygz_b200.h.
 #include "orb_kernels.cuh"
 #include "fast_cells_v2.cuh"
+#include "pyr_resize_v2.cuh"
 #include "dso_kernels.cuh"
 #include "trig_glibc.cuh"
 #include <algorithm>
@@ -27,6 +28,7 @@ struct LevelHost {
     uint8_t* d_blur = nullptr;     // GaussianBlur(level), written by k_blur_levels
     ResizeTabX* d_tx = nullptr;
     ResizeTabY* d_ty = nullptr;
+    int py2_pitch = 0, py2_smem = 0;   // k_pyr_resize_v2 staging window of this level (0: use k_pyr_resize)
 };
 
 }  // namespace ygz_b200
@@ -308,6 +310,7 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
 #define TRY_OR_FREE(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); orb_free(h); return YGZ_ERR_CUDA; } } while (0)
     TRY_OR_FREE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) TRY_OR_FREE(cudaEventCreate(&e));
+    int py2_max_smem = 0;
     for (int l = 0; l < nl; l++) {
         LevelHost& L = h->lv[l];
         TRY_OR_FREE(cudaMalloc(&L.d_base, L.frame_stride * B + 64));
@@ -325,8 +328,24 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
             TRY_OR_FREE(cudaMemcpy(L.d_ty, ty.data(), ty.size() * sizeof(ResizeTabY), cudaMemcpyHostToDevice));
             h->P.lv[l].tx = L.d_tx;
             h->P.lv[l].ty = L.d_ty;
+            // staging window of k_pyr_resize_v2: the largest source window any 256 x 16 output tile of this level needs
+            int max_rows = 0, max_vec = 0;
+            for (int y = 0; y < L.h; y += PY2_TILE_ROWS)
+                max_rows = std::max(max_rows, ty[std::min(y + PY2_TILE_ROWS, L.h) - 1].y1 - ty[y].y0 + 1);
+            for (int x = 0; x < L.w; x += PY2_COLS) {
+                const int lo = tx[x].ofs & ~15, hi = std::min(tx[std::min(x + PY2_COLS, L.w) - 1].ofs + 1, h->lv[l - 1].w - 1);
+                max_vec = std::max(max_vec, (hi - lo) / 16 + 1);
+            }
+            const int smem = max_rows * max_vec * 32;
+            if (smem <= 96 * 1024 && !getenv("YGZ_PYR_V1")) {
+                L.py2_pitch = max_vec * 32;
+                L.py2_smem = smem;
+                py2_max_smem = std::max(py2_max_smem, smem);
+            }
         }
     }
+    if (py2_max_smem > 0)
+        TRY_OR_FREE(cudaFuncSetAttribute(k_pyr_resize_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(py2_max_smem, 1024)));
     TRY_OR_FREE(cudaMalloc(&h->d_cells, std::max<size_t>(h->cells.size(), 1) * sizeof(CellDesc)));
     if (!h->cells.empty())
         TRY_OR_FREE(cudaMemcpy(h->d_cells, h->cells.data(), h->cells.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
@@ -468,6 +487,12 @@ static int launch_pyramid(ygz_orb* h, int n) {
     for (int l = 1; l < h->cfg.nlevels; l++) {
         const LevelHost& S = h->lv[l - 1];
         const LevelHost& D = h->lv[l];
+        if (D.py2_smem > 0) {
+            dim3 grid(ceil_div(D.w, PY2_COLS), ceil_div(D.h, PY2_TILE_ROWS), n);
+            k_pyr_resize_v2<<<grid, PY2_THREADS, D.py2_smem, h->stream>>>(S.d_base, S.pitch, S.frame_stride, S.w, S.h, D.d_base, D.pitch,
+                                                                          D.frame_stride, D.w, D.h, D.d_tx, D.d_ty, D.py2_pitch);
+            continue;
+        }
         dim3 block(PYR_THREADS);
         dim3 grid(ceil_div(ceil_div(D.w, 4), PYR_THREADS), ceil_div(D.h, PYR_ROWS), n);
         k_pyr_resize<<<grid, block, 0, h->stream>>>(S.d_base, S.pitch, S.frame_stride, S.w, S.h, D.d_base, D.pitch, D.frame_stride,
