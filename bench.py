@@ -4,10 +4,10 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B]
 
 Workload (BASELINE.json configs[1], "C2"): synthetic EuRoC-shape mono stream, 752x480 u8 frames,
-ORBextractor(1000, 1.2, 8, 20, 7) + ORBmatcher(0.7, checkOri).SearchByBoW of every frame against the previous
-one (synthetic bench vocabulary node = descriptor byte0 >> 2; DBoW2 transform is a "next" row).
-One "step" = one batch of B frames through the whole hot path (7 pyramid launches, FAST cells, octree,
-orientation+rBRIEF, batched SearchByBoW).  Inputs are B distinct frames (B*361 KB = 92 MB at B=256; pyramid working
+ORBextractor(1000, 1.2, 8, 20, 7) + Frame::ComputeBoW (DBoW2 transform, levelsup 4, through a synthetic vocabulary of
+ORBvoc.bin's shape: k = 10, L = 6, ~0.98 M nodes) + ORBmatcher(0.7, checkOri).SearchByBoW of every frame against the
+previous one.  One "step" = one batch of B frames through the whole hot path (7 pyramid launches, FAST cells, octree,
+blur, orientation+rBRIEF, vocabulary descent, batched SearchByBoW).  Inputs are B distinct frames (B*361 KB = 92 MB at B=256; pyramid working
 set 286 MB > the 126 MB L2, so no L2 flush is needed between steps).
 
   value  whole-job frames/s with inputs already resident in HBM (CUDA events on the launching stream)
@@ -15,6 +15,8 @@ set 286 MB > the 126 MB L2, so no L2 flush is needed between steps).
          keypoints + descriptors + match arrays inside the timed region
   roofline  for the dominant kernel (by device time) against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the oracle port (host-tuned build, all host threads) on a bounded sample of the same workload
+  cpu_baseline_opencv  the same step with OpenCV's own primitives (cv2.resize / cv2.FAST / cv2.GaussianBlur) and the port's
+         octree + orientation + rBRIEF + BoW + matcher, 1 thread per frame: the reference's "OpenCV path" 
 
 Multi-GPU (torchrun, one rank per GPU): frames are independent units, every rank runs its own batch (weak
 scaling, no data-path collective); the only exchange is one NCCL all-gather of throughput counters.
@@ -123,12 +125,121 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def csrc_sha():
+    """Identity of the kernel sources: sha1 over orb-ygz-slam_b200/csrc/* in name order (profiles/kernel_metrics.json carries the
+    value of the build its ncu captures were taken from)."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "orb-ygz-slam_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".inc")):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()
+
+
+def profiled_metrics(batch):
+    """Per-kernel ncu numbers (DRAM bytes per launch, issue / pipe utilisation) written by profiles/scripts/ncu_summary.py from
+    an `ncu --set full` capture of this command shape.  Only returned when the capture was taken from THIS build of the
+    kernels (csrc sha) and batch size; otherwise ({}, why)."""
+    p = os.path.join(ROOT, "profiles", "kernel_metrics.json")
+    try:
+        j = json.load(open(p))
+    except Exception:
+        return {}, "no profiles/kernel_metrics.json"
+    if j.get("csrc_sha") != csrc_sha():
+        return {}, "profiles/kernel_metrics.json was captured from another build of csrc/ (sha %s...)" % str(j.get("csrc_sha"))[:10]
+    if j.get("batch") != batch:
+        return {}, "profiles/kernel_metrics.json was captured at batch %s" % j.get("batch")
+    return j.get("kernels", {}), "profiles/kernel_metrics.json (%s)" % j.get("source", "ncu --set full")
+
+
 def make_frames(seed, n):
     import __graft_entry__ as g
     g.load_package()
     import importlib
     synth = importlib.import_module("orb_ygz_slam_b200.synth")
     return synth.synth_stream(seed, n, W, H)
+
+
+VOC_SEED, VOC_K, VOC_L, LEVELSUP = 7, 10, 6, 4
+_VOC_BYTES = None
+
+
+def vocabulary_bytes():
+    """Synthetic vocabulary in ORBvoc.bin's binary layout and shape (k = 10, L = 6; /root/reference/Vocabulary/ORBvoc.bin has
+    1 082 074 nodes, this one ~0.98 M): the reference's file does not travel to the GPU box."""
+    global _VOC_BYTES
+    if _VOC_BYTES is None:
+        import __graft_entry__ as g
+        g.load_package()
+        import importlib
+        _VOC_BYTES = importlib.import_module("orb_ygz_slam_b200.synth").synth_vocabulary(VOC_SEED, k=VOC_K, L=VOC_L)
+    return _VOC_BYTES
+
+
+def opencv_arm(frames, threads, min_seconds=6.0):
+    """The reference's OpenCV path (SURVEY.md §8d CPU baseline (1)): OpenCV's own resize / FAST / GaussianBlur (cv2 4.13, the
+    build OpenCV ships: IPP / AVX2) + the port's octree, IC_Angle, rBRIEF, ComputeBoW and SearchByBoW.  cv2.FAST runs once per
+    LEVEL at iniTh, not once per ~30x30 cell with the minTh retry as src/ORBextractor.cc:756-770 does (982 calls per frame, which
+    cannot be issued from Python without measuring the interpreter) — fewer, larger calls, i.e. a LOWER bound of the
+    reference's OpenCV time.  One frame per thread (cv2.setNumThreads(1)), `threads` frames in parallel.  Returns fps."""
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    cv2.setNumThreads(1)
+    try:
+        O.lib(native=True); native = True
+    except Exception:
+        native = False
+    voc = O.Vocabulary(data=vocabulary_bytes(), native=native)
+    sizes = LEVELS
+    local = threading.local()
+    conv_s = [0.0]
+    lock = threading.Lock()
+
+    def one(i):
+        if not hasattr(local, "ex"):
+            local.ex = O.Extractor(native=native, **_orb_kw())
+            local.fast = cv2.FastFeatureDetector_create(ORB["iniThFAST"], True)
+            local.prev = None
+        lv = [frames[i]]
+        for (w, h) in sizes[1:]:
+            lv.append(cv2.resize(lv[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+        cands = []
+        for im in lv:
+            kps = local.fast.detect(im[16:im.shape[0] - 16, 16:im.shape[1] - 16])
+            tc = time.perf_counter()                      # Python-binding cost (cv::KeyPoint objects -> array), not OpenCV's
+            a = np.zeros(len(kps), O.KP_DTYPE)
+            if kps:
+                pts = cv2.KeyPoint_convert(kps)
+                a["x"] = pts[:, 0]; a["y"] = pts[:, 1]
+                a["response"] = np.fromiter((k.response for k in kps), np.float32, len(kps))
+                a["size"] = 7; a["angle"] = -1; a["class_id"] = -1
+            cands.append(a)
+            tconv = time.perf_counter() - tc
+            with lock:
+                conv_s[0] += tconv
+        bl = [cv2.GaussianBlur(im, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101) for im in lv]
+        kps, desc = local.ex.extract_tail(lv, bl, cands)
+        cur = (kps, desc)
+        nm = O.bow_match_pair(local.prev, cur, voc, LEVELSUP, NNRATIO, CHECK_ORI) if local.prev is not None else 0
+        local.prev = cur
+        return nm
+
+    n = len(frames)
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(one, range(min(n, threads))))            # warm: per-thread extractors
+        conv_s[0] = 0.0
+        done, t0 = 0, time.perf_counter()
+        while True:
+            list(pool.map(one, range(n)))
+            done += n
+            dt = time.perf_counter() - t0
+            if dt >= min_seconds:
+                break
+    binding_share = min(0.9, conv_s[0] / max(threads * dt, 1e-9))      # share of the thread-seconds spent converting key points
+    return done / dt, done, dt, done / (dt * (1.0 - binding_share))
 
 
 def cpu_arm(frames, threads, min_seconds=8.0, max_frames=None):
@@ -141,13 +252,16 @@ def cpu_arm(frames, threads, min_seconds=8.0, max_frames=None):
     except Exception:
         native = False
     n = len(frames) if max_frames is None else min(len(frames), max_frames)
-    O.frontend_batch(frames[:min(n, max(threads, 8))], threads, nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, **_orb_kw())  # warm
+    voc = O.Vocabulary(data=vocabulary_bytes(), native=native)
+    O.frontend_batch(frames[:min(n, max(threads, 8))], threads, nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, vocab=voc,
+                     levelsup=LEVELSUP, **_orb_kw())  # warm
     # every thread keeps its chunk of the batch and re-processes it `repeat` times inside ONE call, so thread start-up and
     # first-touch page faults are amortised (a per-call spawn of 128 threads over 2 frames each measured 10x too slow)
     repeat = 4
     done, t0 = 0, time.perf_counter()
     while True:
-        O.frontend_batch(frames[:n], threads, nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, repeat=repeat, **_orb_kw())
+        O.frontend_batch(frames[:n], threads, nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, repeat=repeat, vocab=voc,
+                         levelsup=LEVELSUP, **_orb_kw())
         done += n * repeat
         dt = time.perf_counter() - t0
         if dt >= min_seconds:
@@ -168,15 +282,15 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads, cpu_note = host_threads()
-    sample = max(threads, 64)
-    frames = make_frames(1234, min(sample, 256))
+    frames = make_frames(1000, args.batch)            # the GPU arm's step: the same B frames (rank 0's stream)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     try:
         O.lib(native=True); native = True
     except Exception:
         native = False
-    kw = dict(nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, **_orb_kw())
+    voc = O.Vocabulary(data=vocabulary_bytes(), native=native)
+    kw = dict(nnratio=NNRATIO, check_ori=CHECK_ORI, native=native, vocab=voc, levelsup=LEVELSUP, **_orb_kw())
     O.frontend_batch(frames, threads, repeat=max(args.warmup, 1), **kw)
     t0 = time.perf_counter()
     O.frontend_batch(frames, threads, repeat=args.steps, **kw)      # K steps inside one call: worker threads persist across steps
@@ -188,7 +302,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(len(frames)),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d frames/step x %d steps, oracle port (%s build), %d threads (%s)" %
+                         "sample": "%d frames/step x %d steps (the GPU arm's batch), oracle port (%s build), %d threads (%s)" %
                                    (len(frames), args.steps, "-march=native" if native else "portable", threads, cpu_note)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -278,8 +392,9 @@ def aux_metrics(m, device):
 
 
 def workload_config(batch):
-    return {"workload": "C2 synthetic EuRoC-shape mono stream 752x480 u8: ORBextractor(1000,1.2,8,20,7) + "
-                        "ORBmatcher(0.7,checkOri).SearchByBoW vs previous frame (synthetic vocabulary byte0>>2)",
+    return {"workload": "C2 synthetic EuRoC-shape mono stream 752x480 u8: ORBextractor(1000,1.2,8,20,7) + Frame::ComputeBoW "
+                        "(DBoW2 transform, levelsup 4, synthetic vocabulary of ORBvoc.bin's shape k=10 L=6) + "
+                        "ORBmatcher(0.7,checkOri).SearchByBoW vs previous frame",
             "frames_per_step": batch, "l2_policy": "inputs larger than L2 (%d distinct frames/step, pyramid working set %.0f MB)"
                                                    % (batch, batch * (SUM_P + 361e3 * 0) / 1e6),
             "in_flight": "2 independent batches per GPU on 2 streams for the device-resident `value`; `e2e.pipeline` states its own depth",
@@ -367,6 +482,10 @@ def main():
         pairs.append((exn, mtn, bn))
     pairs = pairs[:max(1, args.inflight)]
     import ctypes as C
+    # Frame::ComputeBoW on the device: one resident vocabulary (read-only, shared by every handle pair), attached to the matchers
+    voc = m.ORBVocabulary(data=vocabulary_bytes(), device=local)
+    for mth in {id(p[1]): p[1] for p in pairs + [(ex2, mt2, None)]}.values():
+        mth.set_vocabulary(voc, LEVELSUP)
 
     def enqueue(exh, mth, b):
         m._check(m.lib().ygz_orb_extract_async(exh.h, b["img"].data_ptr(), B, W * H, W, b["kps"].data_ptr(), b["desc"].data_ptr(),
@@ -441,18 +560,23 @@ def main():
     # per-stage device times (same launches, separately timed) for the roofline of the dominant kernel
     it = max(3, min(args.steps, 10))
     st = ex.time(B, it)
-    bow_ms = mt.time_bow_batch(ex, B, it) / it
+    voc_ms = voc.transform_orb(ex, B, LEVELSUP, want=(), timed=True)["ms"]
+    bow_ms = mt.time_bow_batch(ex, B, it) / it - voc_ms          # the timed batch search includes the vocabulary descent
+    launches_per_step = st["launches"] // it + 2                # extractor kernels + k_vocab_transform + k_bow_match_batch
     stages = {"pyramid(7 launches)": st["pyramid"] / it, "fast_cells": st["fast_cells"] / it, "octree": st["octree"] / it,
-              "blur_levels": st["blur"] / it, "orient_describe": st["describe"] / it, "bow_match": bow_ms}
+              "blur_levels": st["blur"] / it, "orient_describe": st["describe"] / it, "vocab_transform": voc_ms,
+              "bow_match": bow_ms}
 
     # ---- max over ranks; the ONE collective: all-gather of throughput counters (orb-ygz-slam_b200/shard.py)
     import importlib
     shard = importlib.import_module("orb_ygz_slam_b200.shard")
     ctr = ex.counters()
     ctr["matches"] = n_match
-    t_dev, t_e = shard.max_over_ranks(dist, [ms_dev / 1e3, t_e2e], device="cuda" if dist is not None else None)
-    ctr["elapsed_ns"] = int(t_dev * 1e9)
-    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None)
+    ctr["elapsed_ns"] = int(ms_dev * 1e6)
+    # the ONE collective: counters and this rank's two timings in one all-gathered row; max over ranks taken from the table
+    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e])
+    t_dev, t_e = shard.timings_max(gathered, 2)
+    gathered = gathered[:, :len(shard.COUNTER_COLUMNS)]
 
     if rank == 0:
         total_frames = world * B * args.steps
@@ -461,21 +585,32 @@ def main():
         peak, peak_src = measured_peak_gbs()
         dom = max(stages, key=stages.get)
         alg = {"pyramid(7 launches)": PYR_CHAIN, "fast_cells": SUM_P, "octree": 0, "blur_levels": 2 * SUM_P,
-               "orient_describe": 0, "bow_match": 0}
+               "orient_describe": 0, "bow_match": 0, "vocab_transform": 0}
         # algorithmic bytes of gather-type kernels: keypoints * (31x31 raw patch + 512 blurred samples + 60 B out) ; BoW: descriptors of both frames
         kp_per_frame = n_kp / B
         alg["orient_describe"] = int(kp_per_frame * (31 * 31 + 512 + 28 + 32))
         alg["octree"] = int(4 * 16139 / 16)     # ~4 B per FAST candidate (read once); informative only
         alg["bow_match"] = int(2 * kp_per_frame * (32 + 28) + 4 * cap)
+        alg["vocab_transform"] = int(kp_per_frame * (32 + VOC_L * VOC_K * 32 + 4))     # descriptor + k node descriptors per level + node id
         dom_bytes = alg[dom] * B
         achieved = dom_bytes / (stages[dom] / 1e3) / 1e9
         pf_bytes = (SUM_P) * B
         pf_ms = stages["pyramid(7 launches)"] + stages["fast_cells"]
-        # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) from the ncu --set full capture of this very
-        # command shape (B=256), profiles/r1_full_B256_raw.csv; None for other shapes
-        NCU_TRAFFIC_B256 = {"fast_cells": 271616768 + 31951360, "orient_describe": 520987904 + 19014144,
-                            "octree": 70572544 + 53032448, "blur_levels": 290054656 + 252909568}
-        traffic = NCU_TRAFFIC_B256.get(dom) if B == 256 else None
+        # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) and the limiter come from the ncu --set full
+        # capture of this very command shape, but only if it was taken from this build of the kernels (see profiled_metrics)
+        prof, prof_src = profiled_metrics(B)
+
+        def traffic_of(stage):
+            k = prof.get(stage)
+            return int(k["dram_bytes_read"] + k["dram_bytes_write"]) if k else None
+
+        def limiter_of(stage):
+            k = prof.get(stage)
+            if not k:
+                return "not profiled for this build: " + prof_src
+            return ("ncu: issue slots active %.0f %%, ALU pipe %.0f %%, FMA pipe %.0f %%, LSU pipe %.0f %%, warps active %.0f %%"
+                    % (k.get("issue_active_pct", 0), k.get("alu_pct", 0), k.get("fma_pct", 0), k.get("lsu_pct", 0), k.get("warps_active_pct", 0)))
+        traffic = traffic_of(dom)
         out = {
             "metric": "front-end frames/sec (752x480, 1000 feat, 8-lvl pyr)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
@@ -486,16 +621,16 @@ def main():
                     "d2h_bytes_per_step": int(h_kps.numel() * 4 + h_desc.numel() + h_cnt.numel() * 4 + h_match.numel() * 4 + h_nm.numel() * 4),
                     "ms_per_step": t_e / args.steps * 1e3,
                     "pipeline": "%d batches in flight (one handle pair each, ygz_orb_extract_async + ygz_search_by_bow_batch_async + ygz_orb_wait)" % len(pairs)},
-            "gpu_launches": int(args.steps * ((ORB["nlevels"] - 1) + 4 + 1)),
+            "gpu_launches": int(args.steps * launches_per_step),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-                         "limiter": "issue slots, not bytes: ncu smsp__issue_active 80 % (fast_cells; ALU pipe 61 %), 87 % (blur_levels, which streams 2 x SUM_P at 2.6 TB/s); see DESIGN.md §4",
+                         "limiter": limiter_of(dom), "profile_source": prof_src,
                          "kernel_ms_per_launch": stages[dom],
                          "other_kernels": {k: {"algorithmic_bytes_per_launch": alg[k] * B, "ms_per_launch": stages[k],
                                                "achieved": alg[k] * B / (stages[k] / 1e3) / 1e9,
                                                "frac": alg[k] * B / (stages[k] / 1e3) / 1e9 / peak,
-                                               "traffic": NCU_TRAFFIC_B256.get(k) if B == 256 else None}
+                                               "traffic": traffic_of(k)}
                                            for k in ("blur_levels", "pyramid(7 launches)", "orient_describe") if stages.get(k)},
                          "pyramid_plus_fast": {"strict_bytes_per_step": pf_bytes, "ms_per_step": pf_ms,
                                                "achieved": pf_bytes / (pf_ms / 1e3) / 1e9,
@@ -513,6 +648,20 @@ def main():
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                    "sample": "%d frames of the same stream in %.1f s, oracle port (%s build), %d threads (%s)" %
                                              (done, dt, "-march=native" if native else "portable", threads, cpu_note)}
+            try:
+                f1, d1, t1, f1x = opencv_arm(frames[:32], 1, min_seconds=4.0)
+                fn, dn, tn, fnx = opencv_arm(frames[:max(64, 4 * threads)], threads, min_seconds=6.0)
+                out["cpu_baseline_opencv"] = {
+                    "value": fn, "unit": "frames/s", "cores": threads, "kind": "opencv-primitives + port tail",
+                    "value_1_thread": f1, "value_excluding_python_binding": fnx, "value_1_thread_excluding_python_binding": f1x,
+                    "sample": "%d frames in %.1f s on %d threads (1 frame per thread, cv2.setNumThreads(1)); %d frames in %.1f s on 1 thread"
+                              % (dn, tn, threads, d1, t1),
+                    "what": "cv2 %s resize + FAST(iniTh, once per level: a lower bound of the reference's 982 per-cell calls) + "
+                            "GaussianBlur, then the port's octree / IC_Angle / rBRIEF / ComputeBoW / SearchByBoW; "
+                            "'excluding_python_binding' removes the cv::KeyPoint -> array conversion of the cv2 module" %
+                            __import__("cv2").__version__}
+            except Exception as e:
+                out["cpu_baseline_opencv"] = {"error": str(e)[:200]}
         emit_json(out)
     if dist is not None:
         dist.barrier()

@@ -58,6 +58,7 @@ int ygz_orb_tables(ygz_orb* h, float* scale, float* inv_scale, float* sigma2, fl
                    int* features_per_level);
 int ygz_orb_level_size(ygz_orb* h, int level, int* w, int* hgt);
 int ygz_orb_max_keypoints(ygz_orb* h);    /* upper bound of keypoints per frame (caller buffer size) */
+int ygz_orb_max_batch(ygz_orb* h);        /* frames per call the handle was created for (ygz_orb_config.max_batch) */
 
 /* ORBextractor::operator()(InputArray image, mask, keypoints, descriptors), src/ORBextractor.cc:970-1028,
  * for a batch of n independent frames (n = 1 is the reference call).  HOST buffers:
@@ -124,6 +125,7 @@ int ygz_debug_cos_sin(int device, unsigned first_bits, unsigned n, float* cos_ou
 int ygz_descriptor_distance(const uint8_t* a, const uint8_t* b);
 
 typedef struct ygz_matcher ygz_matcher;
+typedef struct ygz_vocab ygz_vocab;      /* DBoW2 vocabulary on the device, see below */
 int ygz_matcher_create(int device, int max_queries, int max_targets, int max_pairs, ygz_matcher** out);
 int ygz_matcher_destroy(ygz_matcher* h);
 
@@ -213,7 +215,13 @@ int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_orien
 int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
                             const int* kf_idx, const int* f_idx, int n_pairs, const uint32_t* node_of_feature,
                             int* out_matches, int* out_nmatches);
-/* asynchronous form on the extractor's stream (synthetic vocabulary); results valid after ygz_orb_wait(orb) */
+/* Frame::ComputeBoW on the device (src/Frame.cc:495-501): attach a vocabulary and the batched searches below take the
+ * FeatureVector node ids (levelsup levels above the leaves; the reference uses 4) from a k_vocab_transform launch over the
+ * extractor's device-resident descriptors, on the same stream, instead of node_of_feature / the synthetic stand-in.
+ * vocab == NULL detaches.  The vocabulary handle must outlive the matcher's use of it and live on the same device. */
+int ygz_matcher_set_vocabulary(ygz_matcher* h, ygz_vocab* vocab, int levelsup);
+/* asynchronous form on the extractor's stream (attached vocabulary, else the synthetic stand-in node = byte0 >> 2);
+ * results valid after ygz_orb_wait(orb) */
 int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_orientation,
                                   const int* kf_idx, const int* f_idx, int n_pairs, int* out_matches, int* out_nmatches);
 /* same, results left on the device; timing variant for bench.py (ms over `iters` repeats) */
@@ -274,7 +282,6 @@ int ygz_sia_time(ygz_sia* h, int n_problems, int max_level, int min_level, int n
  * and transform(feature, word_id, weight, &nid, levelsup) (:1249-1282) for batches of descriptors.  The BowVector /
  * FeatureVector assembly (std::map inserts, :1151-1227) is a per-frame host step over these arrays (see the C++ and
  * Python mirrors). */
-typedef struct ygz_vocab ygz_vocab;
 int ygz_vocab_load(const char* path, int device, ygz_vocab** out);
 int ygz_vocab_from_memory(const uint8_t* buf, size_t bytes, int device, ygz_vocab** out);
 int ygz_vocab_destroy(ygz_vocab* v);

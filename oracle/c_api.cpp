@@ -3,6 +3,7 @@
 #include "cvprims.h"
 #include "orb_extractor.h"
 #include <atomic>
+#include <map>
 #include <cstring>
 #include <thread>
 
@@ -94,6 +95,63 @@ int orc_extract_frame_dso(orc_extractor* h, const uint8_t* img, int w, int hh, i
     return emit(k, d, kps, desc, cap);
 }
 
+int orc_extract_tail(orc_extractor* h, int nlevels, const uint8_t* const* levels, const uint8_t* const* blurred, const int* w,
+                     const int* hh, const orc_keypoint* const* cands, const int* ncand, orc_keypoint* kps, uint8_t* desc, int cap) {
+    if (nlevels != h->ex.nlevels) return -1;
+    h->ex.pyramid.resize(nlevels);
+    h->ex.blurred.resize(nlevels);
+    std::vector<std::vector<KeyPoint>> c(nlevels);
+    for (int l = 0; l < nlevels; l++) {
+        Image& P = h->ex.pyramid[l];
+        Image& B = h->ex.blurred[l];
+        P.w = B.w = w[l]; P.h = B.h = hh[l];
+        P.px.assign(levels[l], levels[l] + (size_t)w[l] * hh[l]);
+        B.px.assign(blurred[l], blurred[l] + (size_t)w[l] * hh[l]);
+        c[l].assign((const KeyPoint*)cands[l], (const KeyPoint*)cands[l] + ncand[l]);
+    }
+    std::vector<KeyPoint> k;
+    std::vector<uint8_t> d;
+    h->ex.extract_tail(c, k, d);
+    return emit(k, d, kps, desc, cap);
+}
+
+// Frame::ComputeBoW of two frames + SearchByBoW(KF = a, F = b): the matcher half of bench.py's OpenCV-path baseline
+int orc_bow_match_pair(const orc_vocab* voc, int levelsup, float nnratio, int check_ori, const orc_keypoint* ka, const uint8_t* da,
+                       int na, const orc_keypoint* kb, const uint8_t* db, int nb) {
+    struct FV { std::vector<uint32_t> node_id, index; std::vector<int> off, mp; };
+    auto build = [&](const uint8_t* d, int n, FV& F) {
+        std::vector<int> wid(n), nid(n);
+        std::vector<float> wt(n);
+        orc_vocab_transform(voc, d, n, levelsup, wid.data(), wt.data(), nid.data());
+        std::map<uint32_t, std::vector<uint32_t>> fv;
+        for (int i = 0; i < n; i++) fv[(uint32_t)nid[i]].push_back((uint32_t)i);
+        F.off.assign(1, 0);
+        for (auto& kv : fv) {
+            F.node_id.push_back(kv.first);
+            F.index.insert(F.index.end(), kv.second.begin(), kv.second.end());
+            F.off.push_back((int)F.index.size());
+        }
+        F.mp.resize(n);
+        for (int i = 0; i < n; i++) F.mp[i] = i;
+    };
+    FV A, B;
+    build(da, na, A);
+    build(db, nb, B);
+    auto view = [&](const orc_keypoint* k, const uint8_t* d, int n, FV& F) {
+        orc_frame_view v;
+        std::memset(&v, 0, sizeof(v));
+        v.n = n; v.keys = k; v.desc = d; v.map_point = F.mp.data();
+        v.fv_nodes = (int)F.node_id.size(); v.fv_node_id = F.node_id.data(); v.fv_offset = F.off.data(); v.fv_index = F.index.data();
+        return v;
+    };
+    orc_frame_view va = view(ka, da, na, A), vb = view(kb, db, nb, B);
+    orc_map_points mps;
+    std::memset(&mps, 0, sizeof(mps));
+    mps.m = na;
+    std::vector<int> out(nb + 1);
+    return orc_search_by_bow(nnratio, check_ori, &va, &mps, &vb, out.data());
+}
+
 int orc_fast10_detect_cell(const uint8_t* img, int w, int hh, int stride, int barrier, short* xy, int cap) {
     std::vector<std::pair<int, int>> c;
     orc::fast10_detect_cell(img, w, hh, stride, barrier, c);
@@ -163,8 +221,19 @@ long orc_extract_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t*
 // CPU front-end baseline (bench.py cpu_baseline / --impl reference): per frame ORBextractor::operator() and
 // SearchByBoW against the previous frame of the same thread's chunk (chunk wrap-around for the first frame), with the
 // synthetic bench vocabulary node = descriptor byte0 >> 2 (same stand-in as the device path).  Returns total matches.
+// voc != NULL: Frame::ComputeBoW (src/Frame.cc:495-501) with that vocabulary — transform(levelsup) of every descriptor, the
+// FeatureVector as the std::map<node, indices> DBoW2 builds — instead of the byte0 >> 2 stand-in.
+long orc_frontend_batch_voc(int nf, float sf, int nl, int ini, int mn, const uint8_t* imgs, int n_frames, int w, int hh,
+                            int threads, float nnratio, int check_ori, long* total_keypoints, int repeat,
+                            const orc_vocab* voc, int levelsup);
 long orc_frontend_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t* imgs, int n_frames, int w, int hh,
                         int threads, float nnratio, int check_ori, long* total_keypoints, int repeat) {
+    return orc_frontend_batch_voc(nf, sf, nl, ini, mn, imgs, n_frames, w, hh, threads, nnratio, check_ori, total_keypoints, repeat,
+                                  nullptr, 4);
+}
+long orc_frontend_batch_voc(int nf, float sf, int nl, int ini, int mn, const uint8_t* imgs, int n_frames, int w, int hh,
+                            int threads, float nnratio, int check_ori, long* total_keypoints, int repeat,
+                            const orc_vocab* voc, int levelsup) {
     if (repeat < 1) repeat = 1;
     if (threads < 1) threads = 1;
     if (threads > n_frames) threads = n_frames;
@@ -177,9 +246,24 @@ long orc_frontend_batch(int nf, float sf, int nl, int ini, int mn, const uint8_t
         std::vector<FrameData> fr(c1 - c0);
         auto build = [&](FrameData& F) {
             const int n = (int)F.k.size();
+            F.off.assign(1, 0);
+            if (voc) {
+                std::vector<int> wid(n), nid(n);
+                std::vector<float> wt(n);
+                orc_vocab_transform(voc, F.d.data(), n, levelsup, wid.data(), wt.data(), nid.data());
+                std::map<uint32_t, std::vector<uint32_t>> fv;               // DBoW2::FeatureVector::addFeature order
+                for (int i = 0; i < n; i++) fv[(uint32_t)nid[i]].push_back((uint32_t)i);
+                for (auto& kv : fv) {
+                    F.node_id.push_back(kv.first);
+                    F.index.insert(F.index.end(), kv.second.begin(), kv.second.end());
+                    F.off.push_back((int)F.index.size());
+                }
+                F.mp.resize(n);
+                for (int i = 0; i < n; i++) F.mp[i] = i;
+                return;
+            }
             std::vector<std::vector<uint32_t>> buckets(64);
             for (int i = 0; i < n; i++) buckets[F.d[(size_t)i * 32] >> 2].push_back((uint32_t)i);
-            F.off.assign(1, 0);
             for (uint32_t b = 0; b < 64; b++) {
                 if (buckets[b].empty()) continue;
                 F.node_id.push_back(b);

@@ -343,6 +343,40 @@ void Extractor::extract(const uint8_t* img, int w, int h, int stride,
     }
 }
 
+// ---- the in-tree tail of operator(): :782-803 (octree, border offset, octave, size, orientation) and :1012-1026
+void Extractor::extract_tail(const std::vector<std::vector<KeyPoint>>& cands, std::vector<KeyPoint>& keypoints,
+                             std::vector<uint8_t>& descriptors) {
+    keypoints.clear();
+    level_keys.assign(nlevels, {});
+    for (int level = 0; level < nlevels && level < (int)cands.size(); ++level) {
+        const Image& im = pyramid[level];
+        const int minB = EDGE_THRESHOLD - 3, maxBX = im.w - EDGE_THRESHOLD + 3, maxBY = im.h - EDGE_THRESHOLD + 3;
+        if (maxBX - minB < 30 || maxBY - minB < 30) continue;
+        std::vector<KeyPoint>& kps = level_keys[level];
+        kps = DistributeOctTree(cands[level], minB, maxBX, minB, maxBY, mnFeaturesPerLevel[level]);
+        const int scaledPatchSize = (int)(PATCH_SIZE * mvScaleFactor[level]);
+        for (KeyPoint& kp : kps) {
+            kp.x += minB; kp.y += minB; kp.octave = level; kp.size = (float)scaledPatchSize;
+            kp.angle = IC_Angle(im, kp.x, kp.y);
+        }
+    }
+    int n = 0;
+    for (auto& v : level_keys) n += (int)v.size();
+    descriptors.assign((size_t)n * 32, 0);
+    int offset = 0;
+    for (int level = 0; level < nlevels; ++level) {
+        std::vector<KeyPoint> kps = level_keys[level];
+        for (size_t i = 0; i < kps.size(); i++)
+            computeOrbDescriptor(kps[i], blurred[level], &descriptors[(size_t)(offset + i) * 32]);
+        offset += (int)kps.size();
+        if (level != 0) {
+            const float scale = mvScaleFactor[level];
+            for (KeyPoint& kp : kps) { kp.x *= scale; kp.y *= scale; }
+        }
+        keypoints.insert(keypoints.end(), kps.begin(), kps.end());
+    }
+}
+
 // ---- src/ORBextractor.cc:1031-1127 (method == ORBSLAM_KEYPOINT, left eye, pyramid already built)
 void Extractor::extract_frame(std::vector<KeyPoint>& keypoints, std::vector<uint8_t>& descriptors) {
     ComputeKeyPointsOctTree(level_keys);

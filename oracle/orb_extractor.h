@@ -39,6 +39,12 @@ public:
     // The pyramid must already have been built with ComputePyramid (Frame ctor does that).
     void extract_frame(std::vector<KeyPoint>& keypoints, std::vector<uint8_t>& descriptors);
 
+    // The in-tree part of operator() only — DistributeOctTree, IC_Angle, computeOrbDescriptor, scaling (:782-803, 1012-1026) — on
+    // a pyramid, blurred pyramid and per-level FAST candidates (relative to (16,16)) produced elsewhere: bench.py's OpenCV-path
+    // CPU baseline feeds it with cv2's own resize / FAST / GaussianBlur outputs.  `pyramid` / `blurred` must be filled first.
+    void extract_tail(const std::vector<std::vector<KeyPoint>>& cands, std::vector<KeyPoint>& keypoints,
+                      std::vector<uint8_t>& descriptors);
+
     // stage outputs kept for parity tests
     std::vector<Image> pyramid;                        // raw levels
     std::vector<Image> blurred;                        // 7x7 sigma-2 blurred levels

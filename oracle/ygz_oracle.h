@@ -182,6 +182,16 @@ int orc_vocab_transform_bow(const orc_vocab*, const uint8_t* desc, int n, int le
 long orc_frontend_batch(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs,
                         int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints,
                         int repeat);
+/* pieces of bench.py's OpenCV-path CPU baseline: the in-tree tail of ORBextractor::operator() on externally produced
+ * levels / blurred levels / FAST candidates (relative to (16,16)), and ComputeBoW x2 + SearchByBoW of one frame pair */
+int orc_extract_tail(orc_extractor*, int nlevels, const uint8_t* const* levels, const uint8_t* const* blurred, const int* w,
+                     const int* h, const orc_keypoint* const* cands, const int* ncand, orc_keypoint* kps, uint8_t* desc, int cap);
+int orc_bow_match_pair(const orc_vocab* voc, int levelsup, float nnratio, int check_ori, const orc_keypoint* ka, const uint8_t* da,
+                       int na, const orc_keypoint* kb, const uint8_t* db, int nb);
+/* the same with Frame::ComputeBoW through a vocabulary (NULL: the byte0 >> 2 stand-in) */
+long orc_frontend_batch_voc(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh, const uint8_t* imgs,
+                            int n_frames, int w, int h, int threads, float nnratio, int check_ori, long* total_keypoints,
+                            int repeat, const orc_vocab* voc, int levelsup);
 /* Sophus pieces exposed for unit tests */
 void orc_se3_exp(const float* x6, float* q, float* t);
 void orc_se3_mul(const float* qa, const float* ta, const float* qb, const float* tb, float* q, float* t);

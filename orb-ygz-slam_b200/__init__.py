@@ -85,7 +85,7 @@ class Counters(C.Structure):
 # every symbol include/ygz_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
     "ygz_last_error", "ygz_device_count", "ygz_device_info",
-    "ygz_orb_create", "ygz_orb_destroy", "ygz_orb_tables", "ygz_orb_level_size", "ygz_orb_max_keypoints",
+    "ygz_orb_create", "ygz_orb_destroy", "ygz_orb_tables", "ygz_orb_level_size", "ygz_orb_max_keypoints", "ygz_orb_max_batch",
     "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_extract_frame_dso",
     "ygz_orb_compute_pyramid", "ygz_orb_get_level",
     "ygz_orb_upload", "ygz_orb_run", "ygz_orb_download", "ygz_orb_sync", "ygz_orb_get_candidates",
@@ -93,7 +93,7 @@ ABI_SYMBOLS = [
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
     "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_bow_kf", "ygz_search_for_triangulation", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
-    "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
+    "ygz_matcher_set_vocabulary", "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
@@ -176,6 +176,8 @@ def lib():
     sigs.setdefault('ygz_orb_extract_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     sigs.setdefault('ygz_orb_wait', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_search_by_bow_batch_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, C.c_void_p, C.c_void_p]
+    sigs.setdefault('ygz_matcher_set_vocabulary', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int]
+    sigs.setdefault('ygz_orb_max_batch', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_debug_cos_sin', {})['argtypes'] = [C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
     sigs.setdefault('ygz_frontend_time2', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
     sigs.setdefault('ygz_frontend_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
@@ -489,6 +491,13 @@ class ORBmatcher:
             self.close()
         except Exception:
             pass
+
+    def set_vocabulary(self, vocab, levelsup=4):
+        """Frame::ComputeBoW on the device: the batched searches take their FeatureVector node ids from `vocab`
+        (an ORBVocabulary on the same device) instead of node_of_feature / the synthetic stand-in.  None detaches."""
+        self._vocab = vocab                     # keep the handle alive
+        _check(self.L.ygz_matcher_set_vocabulary(self.h, vocab.h if vocab is not None else None, levelsup),
+               "ygz_matcher_set_vocabulary")
 
     @staticmethod
     def DescriptorDistance(a, b):

@@ -11,6 +11,12 @@
 namespace ygz_b200 {
 
 void set_last_error(const std::string& s);
+#ifdef __CUDACC__
+// vocabulary.cu: node ids of an extractor's device-resident descriptors on the caller's stream (see there)
+int vocab_node_ids_async(ygz_vocab* v, const void* d_desc, const int* d_counts, int cap, int n_frames, int levelsup,
+                         uint32_t* d_node_out, cudaStream_t st);
+int vocab_device(const ygz_vocab* v);
+#endif
 
 #define YGZ_CUDA_TRY(expr)                                                                  \
     do {                                                                                    \

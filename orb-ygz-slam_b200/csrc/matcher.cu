@@ -384,6 +384,9 @@ struct ygz_matcher {
     // batch BoW
     int *d_kf_idx = nullptr, *d_f_idx = nullptr, *d_matches = nullptr, *d_nmatches = nullptr;
     uint32_t* d_node = nullptr;
+    size_t node_elems = 0;              // capacity of d_node in elements (frames x cap)
+    ygz_vocab* vocab = nullptr;         // attached vocabulary: node ids come from k_vocab_transform on the device
+    int levelsup = 4;
     int bow_pairs_cap = 0, bow_cap = 0, bow_frames = 0;
     BowBatchArgs last_args{};
     int last_pairs = 0;
@@ -931,31 +934,61 @@ static int bow_batch_prepare(ygz_matcher* h, ygz_orb* orb, int n_pairs, int* cap
     return YGZ_OK;
 }
 
+static int node_capacity(ygz_matcher* h, size_t elems) {
+    if (elems <= h->node_elems) return YGZ_OK;
+    cudaFree(h->d_node); h->d_node = nullptr; h->node_elems = 0;
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_node, elems * 4));
+    h->node_elems = elems;
+    return YGZ_OK;
+}
+
+static int frames_of_pairs(const int* kf_idx, const int* f_idx, int n_pairs) {
+    int max_frame = 0;
+    for (int i = 0; i < n_pairs; i++) max_frame = std::max(max_frame, std::max(kf_idx[i], f_idx[i]));
+    return max_frame + 1;
+}
+
+// node ids for the batched search: Frame::ComputeBoW (src/Frame.cc:495-501) of every frame the pairs reference, on stream st
+static int launch_node_ids(ygz_matcher* h, ygz_orb* orb, int frames, int cap, cudaStream_t st) {
+    void *d_kps, *d_desc, *d_counts;
+    int rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, nullptr);
+    if (rc) return rc;
+    return vocab_node_ids_async(h->vocab, d_desc, (const int*)d_counts, cap, frames, h->levelsup, h->d_node, st);
+}
+
+int ygz_matcher_set_vocabulary(ygz_matcher* h, ygz_vocab* vocab, int levelsup) {
+    YGZ_ARG_CHECK(h && levelsup >= 0);
+    if (vocab) YGZ_ARG_CHECK(vocab_device(vocab) == h->device);
+    h->vocab = vocab;
+    h->levelsup = levelsup;
+    h->last_pairs = 0;                 // cached launch arguments referred to the previous node source
+    return YGZ_OK;
+}
+
 int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, const int* kf_idx, const int* f_idx,
                             int n_pairs, const uint32_t* node_of_feature, int* out_matches, int* out_nmatches) {
     YGZ_ARG_CHECK(h && orb && kf_idx && f_idx && n_pairs >= 1 && out_matches && out_nmatches);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
     int cap = 0, rc;
     if ((rc = bow_batch_prepare(h, orb, n_pairs, &cap, nullptr))) return rc;
-    int max_frame = 0;
-    for (int i = 0; i < n_pairs; i++) max_frame = std::max(max_frame, std::max(kf_idx[i], f_idx[i]));
-    const int frames = max_frame + 1;
-    if (node_of_feature && frames > h->bow_frames) {
-        cudaFree(h->d_node); h->d_node = nullptr;
-        YGZ_CUDA_TRY(cudaMalloc(&h->d_node, (size_t)frames * cap * 4));
-        h->bow_frames = frames;
-    }
+    const int frames = frames_of_pairs(kf_idx, f_idx, n_pairs);
+    YGZ_ARG_CHECK(frames <= ygz_orb_max_batch(orb));
+    for (int i = 0; i < n_pairs; i++) YGZ_ARG_CHECK(kf_idx[i] >= 0 && f_idx[i] >= 0);
+    const bool use_nodes = node_of_feature || h->vocab;
+    if (use_nodes && (rc = node_capacity(h, (size_t)frames * cap))) return rc;
     void *d_kps, *d_desc, *d_counts;
     ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, nullptr);
     // the extractor's stream produced the inputs: order our stream after it
     YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
     if (node_of_feature)
         YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_node, node_of_feature, (size_t)frames * cap * 4, cudaMemcpyHostToDevice, h->stream));
+    else if (h->vocab && (rc = launch_node_ids(h, orb, frames, cap, h->stream))) return rc;
+    h->bow_frames = frames;
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_kf_idx, kf_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_f_idx, f_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     BowBatchArgs A;
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
-    A.node = node_of_feature ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
+    A.node = use_nodes ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
     k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -978,11 +1011,19 @@ int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, i
     cudaStream_t st = (cudaStream_t)ygz_orb_stream(orb);
     void *d_kps, *d_desc, *d_counts;
     ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, nullptr);
+    const int frames = frames_of_pairs(kf_idx, f_idx, n_pairs);
+    YGZ_ARG_CHECK(frames <= ygz_orb_max_batch(orb));
+    for (int i = 0; i < n_pairs; i++) YGZ_ARG_CHECK(kf_idx[i] >= 0 && f_idx[i] >= 0);
+    if (h->vocab) {                     // Frame::ComputeBoW of the batch, on the extractor's stream right after the descriptors
+        if ((rc = node_capacity(h, (size_t)frames * cap))) return rc;
+        if ((rc = launch_node_ids(h, orb, frames, cap, st))) return rc;
+    }
+    h->bow_frames = frames;
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_kf_idx, kf_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_f_idx, f_idx, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
     BowBatchArgs A;
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
-    A.node = nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
+    A.node = h->vocab ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
     k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), st>>>(A);
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -993,14 +1034,37 @@ int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, i
     return YGZ_OK;
 }
 
+// the cached launch arguments of the last batched search, re-pointed at the extractor's CURRENT output buffers
+// (ygz_orb_extract_frame / _dso may have re-allocated them since); a changed capacity invalidates the cache
+static int refreshed_args(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, BowBatchArgs* out) {
+    void *d_kps, *d_desc, *d_counts;
+    int cap = 0;
+    int rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap);
+    if (rc) return rc;
+    if (cap != h->last_args.cap) {
+        h->last_pairs = 0;
+        set_last_error("the extractor's output capacity changed since the last batched SearchByBoW: call it again first");
+        return YGZ_ERR_ARG;
+    }
+    BowBatchArgs A = h->last_args;
+    A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
+    A.nnratio = nnratio; A.check_ori = check_ori;
+    *out = A;
+    return YGZ_OK;
+}
+
 int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, int check_ori, int n_pairs, int iters, float* ms) {
     YGZ_ARG_CHECK(h && orb && ms && iters >= 1 && h->last_pairs >= 1 && n_pairs == h->last_pairs);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
-    BowBatchArgs A = h->last_args;
-    A.nnratio = nnratio; A.check_ori = check_ori;
+    BowBatchArgs A;
+    int rc;
+    if ((rc = refreshed_args(h, orb, nnratio, check_ori, &A))) return rc;
     YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
     YGZ_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    for (int i = 0; i < iters; i++) k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
+    for (int i = 0; i < iters; i++) {
+        if (h->vocab && (rc = launch_node_ids(h, orb, h->bow_frames, A.cap, h->stream))) return rc;
+        k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
+    }
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
     YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
@@ -1014,13 +1078,14 @@ int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, flo
     YGZ_ARG_CHECK(orb && h && ms && iters >= 1 && h->last_pairs >= 1);
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)ygz_orb_stream(orb);
-    BowBatchArgs A = h->last_args;
-    A.nnratio = nnratio; A.check_ori = check_ori;
+    BowBatchArgs A;
+    int rc;
+    if ((rc = refreshed_args(h, orb, nnratio, check_ori, &A))) return rc;
     YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
     YGZ_CUDA_TRY(cudaEventRecord(h->ev0, st));
     for (int i = 0; i < iters; i++) {
-        int rc = ygz_orb_run(orb, n_frames);
-        if (rc) return rc;
+        if ((rc = ygz_orb_run(orb, n_frames))) return rc;
+        if (h->vocab && (rc = launch_node_ids(h, orb, h->bow_frames, A.cap, st))) return rc;
         k_bow_match_batch<<<h->last_pairs, BOW_THREADS, bow_smem_bytes(A.cap), st>>>(A);
     }
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -1040,8 +1105,10 @@ int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matche
     YGZ_ARG_CHECK(orbA && hA && orbB && hB && ms && iters >= 1 && hA->last_pairs >= 1 && hB->last_pairs >= 1);
     YGZ_CUDA_TRY(cudaSetDevice(hA->device));
     cudaStream_t sA = (cudaStream_t)ygz_orb_stream(orbA), sB = (cudaStream_t)ygz_orb_stream(orbB);
-    BowBatchArgs A = hA->last_args, B = hB->last_args;
-    A.nnratio = B.nnratio = nnratio; A.check_ori = B.check_ori = check_ori;
+    BowBatchArgs A, B;
+    int rc;
+    if ((rc = refreshed_args(hA, orbA, nnratio, check_ori, &A))) return rc;
+    if ((rc = refreshed_args(hB, orbB, nnratio, check_ori, &B))) return rc;
     YGZ_CUDA_TRY(cudaStreamSynchronize(hA->stream));
     YGZ_CUDA_TRY(cudaStreamSynchronize(hB->stream));
     YGZ_CUDA_TRY(cudaStreamSynchronize(sA));
@@ -1052,8 +1119,8 @@ int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matche
         ygz_orb* orb = (i & 1) ? orbB : orbA;
         ygz_matcher* h = (i & 1) ? hB : hA;
         cudaStream_t st = (i & 1) ? sB : sA;
-        int rc = ygz_orb_run(orb, n_frames);
-        if (rc) return rc;
+        if ((rc = ygz_orb_run(orb, n_frames))) return rc;
+        if (h->vocab && (rc = launch_node_ids(h, orb, h->bow_frames, (i & 1) ? B.cap : A.cap, st))) return rc;
         k_bow_match_batch<<<h->last_pairs, BOW_THREADS, bow_smem_bytes((i & 1) ? B.cap : A.cap), st>>>((i & 1) ? B : A);
     }
     YGZ_CUDA_TRY(cudaGetLastError());

@@ -458,6 +458,7 @@ int ygz_orb_level_size(ygz_orb* h, int level, int* w, int* hgt) {
 }
 
 int ygz_orb_max_keypoints(ygz_orb* h) { return h ? h->P.out_cap : YGZ_ERR_ARG; }
+int ygz_orb_max_batch(ygz_orb* h) { return h ? h->cfg.max_batch : YGZ_ERR_ARG; }
 void* ygz_orb_stream(ygz_orb* h) { return h ? (void*)h->stream : nullptr; }
 
 int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride) {

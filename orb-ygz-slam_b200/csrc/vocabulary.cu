@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(256) k_vocab_transform(VocabDev V, const uint4
         if (V.word_id[cur] >= 0) break;               // isLeaf()
     }
     if (lane == 0) {
-        word_id[f] = V.word_id[cur];
-        weight[f] = V.weight[cur];
+        if (word_id) word_id[f] = V.word_id[cur];
+        if (weight) weight[f] = V.weight[cur];
         node_id[f] = nid;
     }
 }
@@ -109,6 +109,20 @@ static int vocab_scratch(ygz_vocab* v, int n) {
     v->cap = n;
     return YGZ_OK;
 }
+
+namespace ygz_b200 {
+// Frame::ComputeBoW's FeatureVector node ids (levelsup levels above the leaves) of the descriptors an extractor holds on the
+// device, written to d_node_out[n_frames][cap] on the CALLER's stream (no host round trip): what the batched SearchByBoW
+// consumes when a vocabulary is attached to the matcher (ygz_matcher_set_vocabulary).  Slots past a frame's count are not written.
+int vocab_node_ids_async(ygz_vocab* v, const void* d_desc, const int* d_counts, int cap, int n_frames, int levelsup,
+                         uint32_t* d_node_out, cudaStream_t st) {
+    const int n = n_frames * cap;
+    k_vocab_transform<<<ceil_div(n, 8), 256, 0, st>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, d_counts, cap, n, levelsup,
+                                                     nullptr, nullptr, reinterpret_cast<int*>(d_node_out));
+    return cudaGetLastError() == cudaSuccess ? YGZ_OK : YGZ_ERR_CUDA;
+}
+int vocab_device(const ygz_vocab* v) { return v->device; }
+}  // namespace ygz_b200
 
 extern "C" {
 

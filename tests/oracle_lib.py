@@ -179,6 +179,26 @@ class Extractor:
         assert n >= 0, n
         return kps[:n].copy(), desc[:n].copy(), g.value
 
+    def extract_tail(self, levels, blurred, cands, cap=None):
+        """octree + IC_Angle + rBRIEF + scaling on externally produced levels / blurred levels / FAST candidates"""
+        n = self.nlevels
+        assert len(levels) == len(blurred) == len(cands) == n
+        lv = [np.ascontiguousarray(x, np.uint8) for x in levels]
+        bl = [np.ascontiguousarray(x, np.uint8) for x in blurred]
+        cs = [np.ascontiguousarray(x, KP_DTYPE) for x in cands]
+        PP = u8p * n
+        w = (C.c_int * n)(*[x.shape[1] for x in lv]); h = (C.c_int * n)(*[x.shape[0] for x in lv])
+        nc = (C.c_int * n)(*[len(x) for x in cs])
+        cp = (C.c_void_p * n)(*[x.ctypes.data for x in cs])
+        cap = cap or (self.nfeatures * 2 + 64)
+        kps = np.zeros(cap, KP_DTYPE); desc = np.zeros((cap, 32), np.uint8)
+        self.L.orc_extract_tail.argtypes = [C.c_void_p, C.c_int, PP, PP, C.c_int * n, C.c_int * n, C.c_void_p * n, C.c_int * n,
+                                            C.c_void_p, u8p, C.c_int]
+        k = self.L.orc_extract_tail(self.h, n, PP(*[_ptr(x, u8p) for x in lv]), PP(*[_ptr(x, u8p) for x in bl]), w, h, cp, nc,
+                                    kps.ctypes.data, _ptr(desc, u8p), cap)
+        assert k >= 0, k
+        return kps[:k].copy(), desc[:k].copy()
+
     def level_size(self, level):
         w, h = C.c_int(), C.c_int()
         self.L.orc_level_size(self.h, level, C.byref(w), C.byref(h))
@@ -288,14 +308,28 @@ def se3_exp(x6):
 
 
 def frontend_batch(imgs, threads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, nnratio=0.7, check_ori=True,
-                   native=True, repeat=1):
-    """CPU baseline: extract + SearchByBoW(prev frame) over imgs[n,h,w]; returns (matches, keypoints)."""
+                   native=True, repeat=1, vocab=None, levelsup=4):
+    """CPU baseline: extract (+ Frame::ComputeBoW through `vocab`, a Vocabulary of the SAME library build) + SearchByBoW(prev
+    frame) over imgs[n,h,w]; returns (matches, keypoints)."""
     imgs = np.ascontiguousarray(imgs, np.uint8)
     n, h, w = imgs.shape
     kp = C.c_long()
-    m = lib(native).orc_frontend_batch(nfeatures, scale, nlevels, ini_th, min_th, _ptr(imgs, u8p), n, w, h, threads,
-                                       nnratio, int(check_ori), C.byref(kp), repeat)
+    L = lib(native)
+    L.orc_frontend_batch_voc.restype = C.c_long
+    L.orc_frontend_batch_voc.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_int, C.POINTER(C.c_long), C.c_int, C.c_void_p, C.c_int]
+    m = L.orc_frontend_batch_voc(nfeatures, scale, nlevels, ini_th, min_th, _ptr(imgs, u8p), n, w, h, threads,
+                                 nnratio, int(check_ori), C.byref(kp), repeat, vocab.h if vocab is not None else None, levelsup)
     return m, kp.value
+
+
+def bow_match_pair(a, b, vocab, levelsup=4, nnratio=0.7, check_ori=True):
+    """Frame::ComputeBoW of both frames + SearchByBoW(KF = a, F = b); a, b = (keypoints, descriptors); returns nmatches"""
+    (ka, da), (kb, db) = a, b
+    L = vocab.L_
+    L.orc_bow_match_pair.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, u8p, C.c_int, C.c_void_p, u8p, C.c_int]
+    return L.orc_bow_match_pair(vocab.h, levelsup, nnratio, int(check_ori), ka.ctypes.data, _ptr(da, u8p), len(ka),
+                                kb.ctypes.data, _ptr(db, u8p), len(kb))
 
 
 def find_direct_projection(ref_frames, cur_frame, K, scale, inv_scale, inv_level_sigma2_1, items):
@@ -338,8 +372,8 @@ def compute_stereo_matches(pyrL, pyrR, keysL, descL, keysR, descR, scale, inv_sc
 class Vocabulary:
     """Oracle DBoW2 vocabulary (oracle/vocabulary.cpp)."""
 
-    def __init__(self, path=None, data=None):
-        self.L_ = lib()
+    def __init__(self, path=None, data=None, native=False):
+        self.L_ = lib(native)
         L = self.L_
         L.orc_vocab_load.restype = C.c_void_p; L.orc_vocab_load.argtypes = [C.c_char_p]
         L.orc_vocab_from_memory.restype = C.c_void_p; L.orc_vocab_from_memory.argtypes = [C.c_void_p, C.c_size_t]

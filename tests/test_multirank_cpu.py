@@ -19,8 +19,9 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 b, e = shard.shard_range(1001, rank, world)
 ctr = {"frames": e - b, "keypoints": (e - b) * 1000 + rank, "matches": 7 * (rank + 1), "kernel_launches": 11, "elapsed_ns": 5 + rank}
-gathered = shard.gather_counters(dist, ctr)
-tmax = shard.max_over_ranks(dist, [1.0 + rank, 3.0 - rank])
+gathered = shard.gather_counters(dist, ctr, timings_s=[1.0 + rank, 3.0 - rank])     # the one collective
+tmax = shard.timings_max(gathered, 2)
+assert tmax == shard.max_over_ranks(dist, [1.0 + rank, 3.0 - rank])
 if rank == 0:
     print("RESULT " + json.dumps({"gathered": gathered.tolist(), "tmax": tmax, "fps": shard.job_throughput(gathered, tmax[0]),
                                   "streams": [shard.stream_of_rank(8, r, world) for r in range(world)]}))
@@ -40,7 +41,7 @@ def test_two_rank_gloo(tmp_path):
     import json
     res = json.loads(line[7:])
     g = np.array(res["gathered"])
-    assert g.shape == (2, 8)
+    assert g.shape == (2, 10)                                                  # 8 counters + 2 timing columns (ns)
     assert g[:, 0].sum() == 1001 and g[0, 0] == 500 and g[1, 0] == 501        # every unit owned exactly once
     assert g[1, 1] == 501 * 1000 + 1 and list(g[:, 2]) == [7, 14]
     assert res["tmax"] == [2.0, 3.0]

@@ -54,3 +54,47 @@ def test_transform_orb_feeds_search_by_bow(gpu, oracle, synth):
         o = np.zeros(len(kb), np.int32)
         n_bow = oracle.lib().orc_search_by_bow(0.7, 1, kf.ptr(), mps.ptr(), fr.ptr(), o.ctypes.data_as(oracle.i32p))
         assert nm[p] == n_bow and (matches[p, :len(kb)] == o).all()
+
+
+def test_transform_real_vocabulary_shape(gpu, oracle, synth):
+    """k = 10, L = 6: the shape of the reference's ORBvoc.bin (1 082 074 nodes there, ~0.98 M here; 32 MB of node descriptors,
+    larger than L1 and than any synthetic tree of the other tests) — word, weight and level-2 node (levelsup = 4) identical."""
+    data = synth.synth_vocabulary(2, k=10, L=6)
+    gv = gpu.ORBVocabulary(data=data)
+    ov = oracle.Vocabulary(data=data)
+    assert (gv.k, gv.L) == (10, 6) and gv.n_nodes == ov.n_nodes > 900000 and gv.n_words == ov.n_words
+    q, t, _ = synth.synth_descriptors(9, 2000, 2000)
+    desc = np.concatenate([q, t])
+    wid, w, nid = gv.transform_features(desc, 4)
+    owid, ow, onid = ov.transform_features(desc, 4)
+    assert (wid == owid).all() and (nid == onid).all() and (w.view(np.uint32) == ow.view(np.uint32)).all()
+    assert len(np.unique(nid)) > 50                    # level-2 nodes: up to 100 buckets, as SearchByBoW sees them
+
+
+def test_attached_vocabulary_equals_explicit_nodes(gpu, synth):
+    """ygz_matcher_set_vocabulary: Frame::ComputeBoW inside the batched SearchByBoW (node ids never leave the device) gives the
+    matches of the same search fed with the node ids of ygz_vocab_transform_orb; sync and async entry points."""
+    import ctypes as C
+    w, h, B = 480, 360, 4
+    frames = synth.synth_stream(23, B, w, h)
+    gv = gpu.ORBVocabulary(data=synth.synth_vocabulary(6, k=10, L=4))
+    ex = gpu.ORBextractor(600, 1.2, 8, 20, 7, width=w, height=h, max_batch=B)
+    ex.extract_batch(frames)
+    node = gv.transform_orb(ex, B, levelsup=2, want=("node",))["node"].astype(np.uint32)
+    kf_idx = np.array([3, 0, 1, 2], np.int32); f_idx = np.arange(4, dtype=np.int32)
+    mt = gpu.ORBmatcher(0.7, True)
+    nm0, m0 = mt.SearchByBoWBatch(ex, kf_idx, f_idx, node)
+    nm_syn, _ = mt.SearchByBoWBatch(ex, kf_idx, f_idx, None)             # synthetic stand-in: different buckets
+    mt.set_vocabulary(gv, 2)
+    nm1, m1 = mt.SearchByBoWBatch(ex, kf_idx, f_idx, None)
+    assert (nm1 == nm0).all() and (m1 == m0).all() and nm0.sum() > 100 and (nm_syn != nm0).any()
+    cap = ex.cap
+    out_m = np.zeros((4, cap), np.int32); out_n = np.zeros(4, np.int32)
+    gpu._check(gpu.lib().ygz_search_by_bow_batch_async(mt.h, ex.h, C.c_float(0.7), 1, kf_idx.ctypes.data_as(gpu.i32p),
+                                                       f_idx.ctypes.data_as(gpu.i32p), 4, out_m.ctypes.data_as(gpu.i32p),
+                                                       out_n.ctypes.data_as(gpu.i32p)), "async")
+    gpu._check(gpu.lib().ygz_orb_wait(ex.h), "wait")
+    assert (out_n == nm0).all() and (out_m == m0).all()
+    mt.set_vocabulary(None)
+    nm2, _ = mt.SearchByBoWBatch(ex, kf_idx, f_idx, None)
+    assert (nm2 == nm_syn).all()
