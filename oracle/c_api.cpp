@@ -124,7 +124,8 @@ int orc_bow_match_pair(const orc_vocab* voc, int levelsup, float nnratio, int ch
         std::vector<float> wt(n);
         orc_vocab_transform(voc, d, n, levelsup, wid.data(), wt.data(), nid.data());
         std::map<uint32_t, std::vector<uint32_t>> fv;
-        for (int i = 0; i < n; i++) fv[(uint32_t)nid[i]].push_back((uint32_t)i);
+        for (int i = 0; i < n; i++)
+            if (wt[i] > 0) fv[(uint32_t)nid[i]].push_back((uint32_t)i);               // TemplatedVocabulary.h:1186-1190
         F.off.assign(1, 0);
         for (auto& kv : fv) {
             F.node_id.push_back(kv.first);
@@ -252,7 +253,8 @@ long orc_frontend_batch_voc(int nf, float sf, int nl, int ini, int mn, const uin
                 std::vector<float> wt(n);
                 orc_vocab_transform(voc, F.d.data(), n, levelsup, wid.data(), wt.data(), nid.data());
                 std::map<uint32_t, std::vector<uint32_t>> fv;               // DBoW2::FeatureVector::addFeature order
-                for (int i = 0; i < n; i++) fv[(uint32_t)nid[i]].push_back((uint32_t)i);
+                for (int i = 0; i < n; i++)
+                    if (wt[i] > 0) fv[(uint32_t)nid[i]].push_back((uint32_t)i);       // TemplatedVocabulary.h:1186-1190
                 for (auto& kv : fv) {
                     F.node_id.push_back(kv.first);
                     F.index.insert(F.index.end(), kv.second.begin(), kv.second.end());

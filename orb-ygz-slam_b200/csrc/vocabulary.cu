@@ -15,58 +15,65 @@
 namespace {
 using namespace ygz_b200;
 
+// Device layout: nodes re-indexed breadth first so that the children of a node are CONTIGUOUS and in the reference's
+// insertion order (ascending original id): a level of the descent is two dependent loads — the node's 16-byte record
+// {first child, child count, word id, original id} and the children's descriptors (k x 32 contiguous bytes) — instead of
+// the five of a CSR (count, begin, child id, descriptor, leaf flag).
 struct VocabDev {
-    const uint4* desc;          // 2 x uint4 per node
-    const int* child_begin;     // CSR of children in the reference's insertion order (ascending node id)
-    const uint8_t* child_count;
-    const int* children;
+    const uint4* desc;          // 2 x uint4 per node, BFS order
+    const int4* meta;           // {first_child, child_count, word_id (-1: inner node), original node id}
     const float* weight;
-    const int* word_id;         // -1 for inner nodes
     int L;
 };
 
+constexpr int VOC_GROUP = 16;   // lanes per descriptor: two descents per warp, up to 16 children per step (k = 10 for ORBvoc)
+
+// mask_stopped: node id 0xFFFFFFFF for words of weight 0 — TemplatedVocabulary::transform adds a feature to the FeatureVector
+// only `if (w > 0)` (TemplatedVocabulary.h:1186-1190), so SearchByBoW never sees the features of stopped words.
 __global__ void __launch_bounds__(256) k_vocab_transform(VocabDev V, const uint4* __restrict__ desc, size_t desc_stride_u4,
                                                          const int* __restrict__ counts, int cap, int n_total, int levelsup,
-                                                         int* __restrict__ word_id, float* __restrict__ weight,
+                                                         int mask_stopped, int* __restrict__ word_id, float* __restrict__ weight,
                                                          int* __restrict__ node_id) {
     // feature f = (frame, slot): frame = f / cap, slot = f % cap (cap = n_total and counts = NULL for a flat list)
-    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= n_total) return;
-    if (counts) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) / VOC_GROUP;
+    const int gl = threadIdx.x & (VOC_GROUP - 1);
+    bool live = f < n_total;
+    if (live && counts) {
         const int frame = f / cap, slot = f - frame * cap;
-        if (slot >= counts[frame]) return;
+        live = slot < __ldg(counts + frame);
     }
+    const unsigned gmask = __ballot_sync(0xffffffffu, live) & (0xFFFFu << ((threadIdx.x & 16)));     // this group's lanes, if live
+    if (!live) return;
     const uint4* d = desc + (size_t)f * desc_stride_u4;
-    const uint4 a0 = d[0], a1 = d[1];
+    const uint4 a0 = __ldg(d), a1 = __ldg(d + 1);
     const int nid_level = V.L - levelsup;
-    int nid = 0, cur = 0, level = 0;
-    while (true) {
-        const int cnt = V.child_count[cur];
-        if (cnt == 0) break;
-        const int cb = V.child_begin[cur];
+    int cur = 0, level = 0, nid_node = 0;
+    int4 m = __ldg(V.meta);
+    while (m.y > 0) {
         ++level;
         int best = INT_MAX, bestc = INT_MAX;
-        for (int c = lane; c < cnt; c += 32) {
-            const int id = V.children[cb + c];
-            const uint4 b0 = V.desc[2 * (size_t)id], b1 = V.desc[2 * (size_t)id + 1];
+        for (int c = gl; c < m.y; c += VOC_GROUP) {
+            const uint4* b = V.desc + 2 * (size_t)(m.x + c);
+            const uint4 b0 = __ldg(b), b1 = __ldg(b + 1);
             const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-            if (dist < best) { best = dist; bestc = c; }
+            if (dist < best) { best = dist; bestc = c; }       // first minimum in child order (the reference's strict <)
         }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            const int ob = __shfl_xor_sync(0xffffffffu, best, o), oc = __shfl_xor_sync(0xffffffffu, bestc, o);
+        for (int o = VOC_GROUP / 2; o; o >>= 1) {
+            const int ob = __shfl_xor_sync(gmask, best, o), oc = __shfl_xor_sync(gmask, bestc, o);
             if (ob < best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
         }
-        cur = V.children[cb + bestc];
-        if (level == nid_level) nid = cur;
-        if (V.word_id[cur] >= 0) break;               // isLeaf()
+        cur = m.x + bestc;
+        m = __ldg(V.meta + cur);
+        if (level == nid_level) nid_node = m.w;
+        if (m.z >= 0) break;                                   // isLeaf()
     }
-    if (lane == 0) {
-        if (word_id) word_id[f] = V.word_id[cur];
-        if (weight) weight[f] = V.weight[cur];
-        node_id[f] = nid;
+    if (gl == 0) {
+        const float w = __ldg(V.weight + cur);
+        if (word_id) word_id[f] = m.z;
+        if (weight) weight[f] = w;
+        node_id[f] = (mask_stopped && !(w > 0.f)) ? -1 : nid_node;
     }
 }
 
@@ -77,22 +84,20 @@ struct ygz_vocab {
     cudaStream_t stream = nullptr;
     int k = 0, L = 0, scoring = 0, weighting = 0, n_nodes = 0, n_words = 0;
     uint4* d_desc = nullptr;
-    int *d_child_begin = nullptr, *d_children = nullptr, *d_word = nullptr;
-    uint8_t* d_child_count = nullptr;
+    int4* d_meta = nullptr;
     float* d_weight = nullptr;
     // scratch for transforms
     int cap = 0;
     uint8_t* d_in = nullptr;
     int *d_wid = nullptr, *d_nid = nullptr;
     float* d_w = nullptr;
-    VocabDev dev() const { return VocabDev{d_desc, d_child_begin, d_child_count, d_children, d_weight, d_word, L}; }
+    VocabDev dev() const { return VocabDev{d_desc, d_meta, d_weight, L}; }
 };
 
 static int vocab_free(ygz_vocab* v) {
     if (!v) return YGZ_OK;
     cudaSetDevice(v->device);
-    cudaFree(v->d_desc); cudaFree(v->d_child_begin); cudaFree(v->d_children); cudaFree(v->d_word); cudaFree(v->d_child_count);
-    cudaFree(v->d_weight); cudaFree(v->d_in); cudaFree(v->d_wid); cudaFree(v->d_nid); cudaFree(v->d_w);
+    cudaFree(v->d_desc); cudaFree(v->d_meta); cudaFree(v->d_weight); cudaFree(v->d_in); cudaFree(v->d_wid); cudaFree(v->d_nid); cudaFree(v->d_w);
     if (v->stream) cudaStreamDestroy(v->stream);
     delete v;
     return YGZ_OK;
@@ -117,8 +122,8 @@ namespace ygz_b200 {
 int vocab_node_ids_async(ygz_vocab* v, const void* d_desc, const int* d_counts, int cap, int n_frames, int levelsup,
                          uint32_t* d_node_out, cudaStream_t st) {
     const int n = n_frames * cap;
-    k_vocab_transform<<<ceil_div(n, 8), 256, 0, st>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, d_counts, cap, n, levelsup,
-                                                     nullptr, nullptr, reinterpret_cast<int*>(d_node_out));
+    k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, st>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, d_counts, cap, n,
+                                                                   levelsup, 1, nullptr, nullptr, reinterpret_cast<int*>(d_node_out));
     return cudaGetLastError() == cudaSuccess ? YGZ_OK : YGZ_ERR_CUDA;
 }
 int vocab_device(const ygz_vocab* v) { return v->device; }
@@ -156,23 +161,36 @@ int ygz_vocab_from_memory(const uint8_t* buf, size_t bytes, int device, ygz_voca
     for (size_t i = 0; i < n; i++) { cbegin[i] = off; off += cnt[i]; ccount[i] = (uint8_t)cnt[i]; }
     std::vector<int> fill(cbegin);
     for (size_t nid = 1; nid < n; nid++) children[fill[parent[nid]]++] = (int)nid;      // ascending node id = insertion order
+    // breadth-first re-indexing: children of a node contiguous, in insertion order (nodes unreachable from the root are dropped)
+    std::vector<int> order;
+    order.reserve(n);
+    order.push_back(0);
+    std::vector<int4> meta;
+    meta.reserve(n);
+    for (size_t q = 0; q < order.size(); q++) {
+        const int id = order[q];
+        const int first = (int)order.size();
+        for (int c = 0; c < cnt[id]; c++) order.push_back(children[cbegin[id] + c]);
+        meta.push_back(make_int4(first, cnt[id], word[id], id));
+    }
+    const size_t nn = order.size();
+    std::vector<uint8_t> desc2(nn * 32);
+    std::vector<float> weight2(nn);
+    for (size_t q = 0; q < nn; q++) {
+        std::memcpy(&desc2[q * 32], &desc[(size_t)order[q] * 32], 32);
+        weight2[q] = weight[order[q]];
+    }
     YGZ_CUDA_TRY(cudaSetDevice(device));
     ygz_vocab* v = new ygz_vocab();
     v->device = device; v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->n_nodes = (int)n; v->n_words = n_words;
 #define TRY_OR_FREE(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); vocab_free(v); return YGZ_ERR_CUDA; } } while (0)
     TRY_OR_FREE(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-    TRY_OR_FREE(cudaMalloc(&v->d_desc, n * 32));
-    TRY_OR_FREE(cudaMalloc(&v->d_child_begin, n * 4));
-    TRY_OR_FREE(cudaMalloc(&v->d_children, children.size() * 4));
-    TRY_OR_FREE(cudaMalloc(&v->d_word, n * 4));
-    TRY_OR_FREE(cudaMalloc(&v->d_child_count, n));
-    TRY_OR_FREE(cudaMalloc(&v->d_weight, n * 4));
-    TRY_OR_FREE(cudaMemcpy(v->d_desc, desc.data(), n * 32, cudaMemcpyHostToDevice));
-    TRY_OR_FREE(cudaMemcpy(v->d_child_begin, cbegin.data(), n * 4, cudaMemcpyHostToDevice));
-    TRY_OR_FREE(cudaMemcpy(v->d_children, children.data(), children.size() * 4, cudaMemcpyHostToDevice));
-    TRY_OR_FREE(cudaMemcpy(v->d_word, word.data(), n * 4, cudaMemcpyHostToDevice));
-    TRY_OR_FREE(cudaMemcpy(v->d_child_count, ccount.data(), n, cudaMemcpyHostToDevice));
-    TRY_OR_FREE(cudaMemcpy(v->d_weight, weight.data(), n * 4, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMalloc(&v->d_desc, nn * 32));
+    TRY_OR_FREE(cudaMalloc(&v->d_meta, nn * sizeof(int4)));
+    TRY_OR_FREE(cudaMalloc(&v->d_weight, nn * 4));
+    TRY_OR_FREE(cudaMemcpy(v->d_desc, desc2.data(), nn * 32, cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_meta, meta.data(), nn * sizeof(int4), cudaMemcpyHostToDevice));
+    TRY_OR_FREE(cudaMemcpy(v->d_weight, weight2.data(), nn * 4, cudaMemcpyHostToDevice));
 #undef TRY_OR_FREE
     (void)nb_nodes;
     *out = v;
@@ -213,8 +231,8 @@ int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, 
     int rc = vocab_scratch(v, n);
     if (rc) return rc;
     YGZ_CUDA_TRY(cudaMemcpyAsync(v->d_in, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
-    k_vocab_transform<<<ceil_div(n, 8), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n, levelsup,
-                                                            v->d_wid, v->d_w, v->d_nid);
+    k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n,
+                                                                          levelsup, 0, v->d_wid, v->d_w, v->d_nid);
     YGZ_CUDA_TRY(cudaGetLastError());
     YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(weight, v->d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -242,8 +260,9 @@ int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levels
     YGZ_CUDA_TRY(cudaMemsetAsync(v->d_w, 0, (size_t)n * 4, v->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms) { YGZ_CUDA_TRY(cudaEventCreate(&e0)); YGZ_CUDA_TRY(cudaEventCreate(&e1)); YGZ_CUDA_TRY(cudaEventRecord(e0, v->stream)); }
-    k_vocab_transform<<<ceil_div(n, 8), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2,
-                                                            reinterpret_cast<const int*>(d_counts), cap, n, levelsup, v->d_wid, v->d_w, v->d_nid);
+    k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2,
+                                                                          reinterpret_cast<const int*>(d_counts), cap, n, levelsup, 0,
+                                                                          v->d_wid, v->d_w, v->d_nid);
     YGZ_CUDA_TRY(cudaGetLastError());
     if (ms) { YGZ_CUDA_TRY(cudaEventRecord(e1, v->stream)); }
     if (word_id) YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));

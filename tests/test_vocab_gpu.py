@@ -80,7 +80,9 @@ def test_attached_vocabulary_equals_explicit_nodes(gpu, synth):
     gv = gpu.ORBVocabulary(data=synth.synth_vocabulary(6, k=10, L=4))
     ex = gpu.ORBextractor(600, 1.2, 8, 20, 7, width=w, height=h, max_batch=B)
     ex.extract_batch(frames)
-    node = gv.transform_orb(ex, B, levelsup=2, want=("node",))["node"].astype(np.uint32)
+    tr = gv.transform_orb(ex, B, levelsup=2, want=("node", "weight"))
+    node = np.where(tr["weight"] > 0, tr["node"], -1).astype(np.uint32)     # stopped words are not in the FeatureVector
+    assert (tr["weight"] == 0).sum() > (tr["node"] >= 0).sum() * 0.01       # the synthetic vocabulary stops ~5 % of its words
     kf_idx = np.array([3, 0, 1, 2], np.int32); f_idx = np.arange(4, dtype=np.int32)
     mt = gpu.ORBmatcher(0.7, True)
     nm0, m0 = mt.SearchByBoWBatch(ex, kf_idx, f_idx, node)
@@ -98,3 +100,20 @@ def test_attached_vocabulary_equals_explicit_nodes(gpu, synth):
     mt.set_vocabulary(None)
     nm2, _ = mt.SearchByBoWBatch(ex, kf_idx, f_idx, None)
     assert (nm2 == nm_syn).all()
+
+
+def test_attached_vocabulary_equals_oracle_frontend(gpu, oracle, synth):
+    """The bench step end to end against the CPU arm: extractor + ComputeBoW (stopped words excluded) + SearchByBoW vs the
+    previous frame — total matches and key points of the device path == oracle.frontend_batch with the same vocabulary."""
+    w, h, B = 480, 360, 6
+    frames = synth.synth_stream(29, B, w, h)
+    data = synth.synth_vocabulary(8, k=10, L=4)
+    gv = gpu.ORBVocabulary(data=data)
+    ex = gpu.ORBextractor(600, 1.2, 8, 20, 7, width=w, height=h, max_batch=B)
+    res = ex.extract_batch(frames)
+    mt = gpu.ORBmatcher(0.7, True)
+    mt.set_vocabulary(gv, 2)
+    kf_idx = np.array([(i - 1) % B for i in range(B)], np.int32); f_idx = np.arange(B, dtype=np.int32)
+    nm, _ = mt.SearchByBoWBatch(ex, kf_idx, f_idx, None)
+    om, ok = oracle.frontend_batch(frames, 1, nfeatures=600, native=False, vocab=oracle.Vocabulary(data=data), levelsup=2)
+    assert ok == sum(len(k) for k, _ in res) and om == int(nm.sum())
