@@ -22,6 +22,9 @@
 #include <cstring>
 #include <memory>
 #include <vector>
+#if defined(__SSE4_2__) || defined(__POPCNT__)
+#include <nmmintrin.h>      // OpenCV's cvdef.h pulls the SSE intrinsics in; src/ORBmatcher.cc:1515 relies on it for _mm_popcnt_u64
+#endif
 
 #include "../cvprims.h"
 

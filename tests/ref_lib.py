@@ -105,3 +105,46 @@ class RefExtractor:
             raise RefThrows()
         assert 0 <= n <= cap, n
         return kps[:n].copy(), desc[:n].copy()
+
+
+def matcher_lib():
+    """oracle/_ref/libmatcher_ref.so: the reference's own ygz::ORBmatcher (src/ORBmatcher.cc + src/Align.cc compiled unmodified
+    against oracle/ref_mock; oracle/ref_matcher_shim.cpp).  Entry points mirror the oracle's orc_* matcher signatures."""
+    L = _load("libmatcher_ref.so")
+    if L is None:
+        return None
+    i32p = C.POINTER(C.c_int)
+    L.refm_hamming256.argtypes = [u8p, u8p]
+    L.refm_three_maxima.argtypes = [i32p, C.c_int, i32p, i32p, i32p]
+    L.refm_search_by_bow.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, i32p]
+    L.refm_search_by_projection_points.argtypes = [C.c_float, C.c_void_p, C.c_void_p, i32p, C.c_int, C.c_float, C.c_int]
+    L.refm_search_by_projection_last.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    L.refm_search_by_projection_kf.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_float, C.c_int]
+    L.refm_search_for_initialization.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, f32p, i32p, C.c_int]
+    L.refm_search_by_bow_kf.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, i32p]
+    L.refm_search_for_triangulation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, f32p, C.POINTER(C.c_float), C.POINTER(C.c_float), f32p,
+                                                C.c_int, i32p]
+    return L
+
+
+def find_direct_projection(ref_frames, cur_frame, K, scale, inv_scale, inv_level_sigma2_1, items):
+    """The reference's ORBmatcher::FindDirectProjection per item (refm_find_direct_projection); arguments as
+    oracle_lib.find_direct_projection."""
+    L = matcher_lib()
+    i32p = C.POINTER(C.c_int)
+    n = len(items)
+    items = np.ascontiguousarray(items)
+    Frame = type(cur_frame.struct)
+    refs = (Frame * len(ref_frames))(*[f.struct for f in ref_frames])
+    K = np.ascontiguousarray(K, np.float32)
+    scale = np.ascontiguousarray(scale, np.float32)
+    inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    px = np.zeros((n, 2), np.float32); lvl = np.zeros(n, np.int32); ok = np.zeros(n, np.uint8)
+    L.refm_find_direct_projection.argtypes = [C.c_void_p, C.c_int, C.c_void_p, f32p, f32p, f32p, C.c_float, C.c_int, C.c_void_p, C.c_int,
+                                              f32p, i32p, u8p]
+    rc = L.refm_find_direct_projection(C.cast(refs, C.c_void_p), len(ref_frames), C.cast(C.pointer(cur_frame.struct), C.c_void_p),
+                                       K.ctypes.data_as(f32p), scale.ctypes.data_as(f32p), inv_scale.ctypes.data_as(f32p),
+                                       float(inv_level_sigma2_1), len(scale), items.ctypes.data, n,
+                                       px.ctypes.data_as(f32p), lvl.ctypes.data_as(i32p), ok.ctypes.data_as(u8p))
+    assert rc == 0, rc
+    return px, lvl, ok
