@@ -21,6 +21,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <iostream>
+#include <sstream>
+#include <string>
 #include <vector>
 #if defined(__SSE4_2__) || defined(__POPCNT__)
 #include <nmmintrin.h>      // OpenCV's cvdef.h pulls the SSE intrinsics in; src/ORBmatcher.cc:1515 relies on it for _mm_popcnt_u64
@@ -346,5 +349,29 @@ struct KeyPointsFilter {
         k.resize(e - k.begin());
     }
 };
+
+// cv::FileStorage / cv::FileNode: the YAML persistence of DBoW2's TemplatedVocabulary (save / load are virtual, so they are
+// instantiated with the class although the hot path only uses loadFromBinaryFile / loadFromTextFile).  Inert stand-ins: a
+// storage that never opens, nodes that read as empty.
+struct FileNode {
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator float() const { return 0.f; }
+    operator double() const { return 0.0; }
+    operator std::string() const { return std::string(); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](const std::string&) const { return FileNode(); }
+};
+template <class T> static inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 
 }  // namespace cv

@@ -148,3 +148,59 @@ def find_direct_projection(ref_frames, cur_frame, K, scale, inv_scale, inv_level
                                        px.ctypes.data_as(f32p), lvl.ctypes.data_as(i32p), ok.ctypes.data_as(u8p))
     assert rc == 0, rc
     return px, lvl, ok
+
+
+class RefVocabulary:
+    """The reference's ygz::ORBVocabulary (DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>), oracle/ref_vocab_shim.cpp.
+    Same methods as oracle_lib.Vocabulary.  loadFromBinaryFile only reads files: `data` goes through a temporary file."""
+
+    def __init__(self, path=None, data=None):
+        import tempfile
+        self.L_ = _load("libvocab_ref.so")
+        assert self.L_ is not None, "oracle/_ref/libvocab_ref.so is missing"
+        L = self.L_
+        i32p = C.POINTER(C.c_int)
+        L.refv_load.restype = C.c_void_p; L.refv_load.argtypes = [C.c_char_p]
+        L.refv_destroy.argtypes = [C.c_void_p]
+        L.refv_info.argtypes = [C.c_void_p] + [i32p] * 6
+        L.refv_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, f32p, i32p]
+        L.refv_transform_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, C.POINTER(C.c_double), i32p, i32p, i32p, i32p]
+        if path is None:
+            with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+                f.write(bytes(data))
+                tmp = f.name
+            try:
+                self.h = L.refv_load(tmp.encode())
+            finally:
+                os.unlink(tmp)
+        else:
+            self.h = L.refv_load(str(path).encode())
+        assert self.h, "vocabulary did not load"
+        v = [C.c_int() for _ in range(6)]
+        L.refv_info(self.h, *[C.byref(x) for x in v])
+        self.k, self.L, self.scoring, self.weighting, self.n_nodes, self.n_words = [x.value for x in v]
+
+    def __del__(self):
+        try:
+            self.L_.refv_destroy(self.h)
+        except Exception:
+            pass
+
+    def transform_features(self, desc, levelsup=4):
+        i32p = C.POINTER(C.c_int)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid = np.zeros(n, np.int32); w = np.zeros(n, np.float32); nid = np.zeros(n, np.int32)
+        self.L_.refv_transform(self.h, desc.ctypes.data, n, levelsup, wid.ctypes.data_as(i32p), w.ctypes.data_as(f32p), nid.ctypes.data_as(i32p))
+        return wid, w, nid
+
+    def transform(self, desc, levelsup=4):
+        i32p = C.POINTER(C.c_int)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        ids = np.zeros(max(n, 1), np.int32); vals = np.zeros(max(n, 1), np.float64)
+        fvn = C.c_int(); node = np.zeros(max(n, 1), np.int32); off = np.zeros(n + 2, np.int32); idx = np.zeros(max(n, 1), np.int32)
+        nb = self.L_.refv_transform_bow(self.h, desc.ctypes.data, n, levelsup, ids.ctypes.data_as(i32p), vals.ctypes.data_as(C.POINTER(C.c_double)),
+                                        C.byref(fvn), node.ctypes.data_as(i32p), off.ctypes.data_as(i32p), idx.ctypes.data_as(i32p))
+        fv = {int(node[j]): [int(x) for x in idx[off[j]:off[j + 1]]] for j in range(fvn.value)}
+        return ids[:nb].copy(), vals[:nb].copy(), fv
