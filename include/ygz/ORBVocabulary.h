@@ -13,7 +13,14 @@
 #include <vector>
 #include "../ygz_b200.h"
 
-namespace ygz {
+// The classes live in namespace ygz (the reference's) unless ygz/adapters.h moved them to ygz::flat to free the reference's
+// class names for the literal-signature adapters.
+#ifndef YGZ_MIRROR_BEGIN
+#define YGZ_MIRROR_BEGIN namespace ygz {
+#define YGZ_MIRROR_END }
+#define YGZ_MIRROR_NS ygz
+#endif
+YGZ_MIRROR_BEGIN
 
 typedef unsigned int WordId;
 typedef double WordValue;
@@ -69,4 +76,4 @@ private:
     ygz_vocab* v_ = nullptr;
 };
 
-}  // namespace ygz
+YGZ_MIRROR_END  // namespace

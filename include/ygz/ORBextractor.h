@@ -10,7 +10,14 @@
 #include <opencv2/core/core.hpp>
 #endif
 
-namespace ygz {
+// The classes live in namespace ygz (the reference's) unless ygz/adapters.h moved them to ygz::flat to free the reference's
+// class names for the literal-signature adapters.
+#ifndef YGZ_MIRROR_BEGIN
+#define YGZ_MIRROR_BEGIN namespace ygz {
+#define YGZ_MIRROR_END }
+#define YGZ_MIRROR_NS ygz
+#endif
+YGZ_MIRROR_BEGIN
 
 typedef ygz_keypoint KeyPoint;      // == cv::KeyPoint: pt.x, pt.y, size, angle, response, octave, class_id
 
@@ -174,4 +181,4 @@ public:   // literal reference signatures (include/ORBextractor.h:69-73)
 #endif
 };
 
-}  // namespace ygz
+YGZ_MIRROR_END  // namespace

@@ -8,7 +8,14 @@
 #include <vector>
 #include "../ygz_b200.h"
 
-namespace ygz {
+// The classes live in namespace ygz (the reference's) unless ygz/adapters.h moved them to ygz::flat to free the reference's
+// class names for the literal-signature adapters.
+#ifndef YGZ_MIRROR_BEGIN
+#define YGZ_MIRROR_BEGIN namespace ygz {
+#define YGZ_MIRROR_END }
+#define YGZ_MIRROR_NS ygz
+#endif
+YGZ_MIRROR_BEGIN
 
 class ORBmatcher {
 public:
@@ -118,4 +125,4 @@ protected:
     ygz_direct* d_ = nullptr;
 };
 
-}  // namespace ygz
+YGZ_MIRROR_END  // namespace

@@ -6,7 +6,14 @@
 #include <cstring>
 #include "../ygz_b200.h"
 
-namespace ygz {
+// The classes live in namespace ygz (the reference's) unless ygz/adapters.h moved them to ygz::flat to free the reference's
+// class names for the literal-signature adapters.
+#ifndef YGZ_MIRROR_BEGIN
+#define YGZ_MIRROR_BEGIN namespace ygz {
+#define YGZ_MIRROR_END }
+#define YGZ_MIRROR_NS ygz
+#endif
+YGZ_MIRROR_BEGIN
 
 struct SE3fPOD { float q[4]; float t[3]; };     // Sophus::SE3f: unit quaternion (x,y,z,w) + translation
 
@@ -55,4 +62,4 @@ protected:
     ygz_sia* h_ = nullptr;
 };
 
-}  // namespace ygz
+YGZ_MIRROR_END  // namespace

@@ -12,12 +12,30 @@
 // What stays mocked (stated, not hidden): Frame::GetFeaturesInArea / AssignFeaturesToGrid / PosInGrid live in
 // src/Frame.cc, which needs the whole SLAM system to compile — ref_mock/Frame.h restates them (48 lines); Eigen and
 // Sophus are absent third-party dependencies — ref_mock/mock_eigen.hpp evaluates fixed-size products left to right.
+//
+// Second use (-DSHIM_USE_ADAPTERS, oracle/Makefile target _ref/libadapters_e2e.so): the SAME caller code below is compiled
+// against include/ygz/adapters.h instead of the reference's ORBmatcher.h — ygz::ORBmatcher is then the product's
+// literal-signature adapter over libygz_b200.so and the entry points are named adp_* instead of refm_*.  That the calls
+// `m.SearchByBoW(K, F, vp)` ... compile unchanged against both is the drop-in claim of INTEGRATION.md;
+// tests/test_adapters_gpu.py runs both libraries on the same scenes on a B200.
+#ifdef SHIM_USE_ADAPTERS
+#include <opencv2/core/core.hpp>
+#include "Common.h"
+#include "MapPoint.h"
+#include "KeyFrame.h"
+#include "Frame.h"
+#define YGZ_B200_REFERENCE_NAMES
+#include <ygz/adapters.h>
+#define REFM(name) adp_##name
+#else
 #define protected public          // ComputeThreeMaxima, RadiusByViewingCos and CheckDistEpipolarLine are protected upstream
 #define private public
 #include <opencv2/core/core.hpp>
 #include "ORBmatcher.h"
 #undef protected
 #undef private
+#define REFM(name) refm_##name
+#endif
 #include <cstring>
 #include <map>
 #include <set>
@@ -164,19 +182,21 @@ void store_map_points(const std::vector<MapPoint *> &v, const Points &P, int *ou
 
 extern "C" {
 
-int refm_hamming256(const uint8_t *a, const uint8_t *b) {
+int REFM(hamming256)(const uint8_t *a, const uint8_t *b) {
     cv::Mat ma(1, 32, CV_8U, (void *) a), mb(1, 32, CV_8U, (void *) b);
     return ORBmatcher::DescriptorDistance(ma, mb);                              // src/ORBmatcher.cc:1507
 }
 
-void refm_three_maxima(const int *hist_sizes, int L, int *ind1, int *ind2, int *ind3) {
+#ifndef SHIM_USE_ADAPTERS
+void REFM(three_maxima)(const int *hist_sizes, int L, int *ind1, int *ind2, int *ind3) {
     std::vector<std::vector<int> > histo(L);
     for (int i = 0; i < L; i++) histo[i].assign(hist_sizes[i], 0);
     ORBmatcher m;
     m.ComputeThreeMaxima(histo.data(), L, *ind1, *ind2, *ind3);                 // :1471
 }
+#endif
 
-int refm_search_by_bow(float nnratio, int check_ori, const orc_frame_view *kf, const orc_map_points *mps,
+int REFM(search_by_bow)(float nnratio, int check_ori, const orc_frame_view *kf, const orc_map_points *mps,
                        const orc_frame_view *f, int *out_matches) {
     Points P(mps);
     KeyFrame *K = make_keyframe(kf, P);
@@ -190,7 +210,7 @@ int refm_search_by_bow(float nnratio, int check_ori, const orc_frame_view *kf, c
     return n;
 }
 
-int refm_search_by_projection_points(float nnratio, orc_frame_view *f, const orc_map_points *mps, const int *query_ids, int nq,
+int REFM(search_by_projection_points)(float nnratio, orc_frame_view *f, const orc_map_points *mps, const int *query_ids, int nq,
                                      float th, int check_level) {
     Points P(mps);
     Frame F;
@@ -203,7 +223,7 @@ int refm_search_by_projection_points(float nnratio, orc_frame_view *f, const orc
     return n;
 }
 
-int refm_search_by_projection_last(int check_ori, orc_frame_view *cur, const orc_frame_view *last, const orc_map_points *mps,
+int REFM(search_by_projection_last)(int check_ori, orc_frame_view *cur, const orc_frame_view *last, const orc_map_points *mps,
                                    float th, int mono, int check_level) {
     Points P(mps);
     Frame L, Cf;
@@ -215,7 +235,7 @@ int refm_search_by_projection_last(int check_ori, orc_frame_view *cur, const orc
     return n;
 }
 
-int refm_search_by_projection_kf(int check_ori, orc_frame_view *cur, const orc_frame_view *kf, const orc_map_points *mps,
+int REFM(search_by_projection_kf)(int check_ori, orc_frame_view *cur, const orc_frame_view *kf, const orc_map_points *mps,
                                  const uint8_t *already_found, float th, int orb_dist) {
     Points P(mps);
     KeyFrame *K = make_keyframe(kf, P);
@@ -231,7 +251,7 @@ int refm_search_by_projection_kf(int check_ori, orc_frame_view *cur, const orc_f
     return n;
 }
 
-int refm_search_for_initialization(float nnratio, int check_ori, const orc_frame_view *f1, const orc_frame_view *f2,
+int REFM(search_for_initialization)(float nnratio, int check_ori, const orc_frame_view *f1, const orc_frame_view *f2,
                                    float *prev_matched_xy, int *matches12, int window) {
     Points P(nullptr);
     Frame F1, F2;
@@ -246,7 +266,7 @@ int refm_search_for_initialization(float nnratio, int check_ori, const orc_frame
     return n;
 }
 
-int refm_search_by_bow_kf(float nnratio, int check_ori, const orc_frame_view *kf1, const orc_frame_view *kf2,
+int REFM(search_by_bow_kf)(float nnratio, int check_ori, const orc_frame_view *kf1, const orc_frame_view *kf2,
                           const orc_map_points *mps, int *matches12) {
     Points P(mps);
     KeyFrame *K1 = make_keyframe(kf1, P), *K2 = make_keyframe(kf2, P);
@@ -260,7 +280,7 @@ int refm_search_by_bow_kf(float nnratio, int check_ori, const orc_frame_view *kf
 
 /* (ex, ey) of the oracle's signature are OUTPUTS here: the reference computes the epipole itself from the two poses
  * (:603-609); the test feeds them to the oracle. */
-int refm_search_for_triangulation(int check_ori, const orc_frame_view *kf1, const orc_frame_view *kf2, const float *F12,
+int REFM(search_for_triangulation)(int check_ori, const orc_frame_view *kf1, const orc_frame_view *kf2, const float *F12,
                                   float *ex, float *ey, const float *level_sigma2, int only_stereo, int *pairs) {
     int npts = 0;
     for (int i = 0; i < kf1->n; i++) if (kf1->map_point && kf1->map_point[i] >= npts) npts = kf1->map_point[i] + 1;
@@ -287,6 +307,7 @@ int refm_search_for_triangulation(int check_ori, const orc_frame_view *kf1, cons
 
 }  // extern "C"
 
+#ifndef SHIM_USE_ADAPTERS      // the batched device form of FindDirectProjection has its own tests (tests/test_direct_gpu.py)
 namespace {
 // Unit quaternion (x, y, z, w) -> rotation matrix with Eigen's QuaternionBase::toRotationMatrix arithmetic
 // (tx = 2x, twx = tx*w, ...; m(0,0) = 1 - (tyy + tzz), ...), which is what Sophus' SE3::rotationMatrix() returns.
@@ -310,7 +331,7 @@ void fill_pyramid(std::vector<cv::Mat> &pyr, const orc_direct_frame *f, int nlev
  * include/ORBmatcher.h:185-197, ygz::Align2D src/Align.cc:8-103) per item; same arguments as orc_find_direct_projection.
  * The mock SE3 holds a rotation MATRIX where Sophus holds a quaternion, so poses are converted once and the float results can
  * differ from a Sophus build in the last bits: the test compares levels / success flags exactly and pixels to 1e-3. */
-extern "C" int refm_find_direct_projection(const orc_direct_frame *refs, int n_refs, const orc_direct_frame *cur, const float *K4,
+extern "C" int REFM(find_direct_projection)(const orc_direct_frame *refs, int n_refs, const orc_direct_frame *cur, const float *K4,
                                            const float *scale, const float *inv_scale, float inv_level_sigma2_1, int nlevels,
                                            const orc_direct_item *items, int n_items, float *out_px, int *out_level, uint8_t *out_ok) {
     Frame::fx = K4[0]; Frame::fy = K4[1]; Frame::cx = K4[2]; Frame::cy = K4[3];
@@ -348,3 +369,89 @@ extern "C" int refm_find_direct_projection(const orc_direct_frame *refs, int n_r
     for (KeyFrame *k : kfs) delete k;
     return 0;
 }
+#endif
+
+#ifdef SHIM_USE_ADAPTERS
+// ---- the extractor and aligner adapters, driven the way Frame.cc / Tracking.cc drive the reference classes ---------------
+namespace {
+SE3f pose_from_q(const float *q, const float *t) { return ygz::b200::qt_to_pose<SE3f>(q, t); }
+}
+
+extern "C" {
+
+/* ORBextractor::operator()(InputArray image, InputArray mask, vector<KeyPoint>&, OutputArray), called as Frame's mono constructor does */
+int adp_extract_image(int nfeatures, float scale, int nlevels, int ini_th, int min_th, const uint8_t *img, int w, int h, int stride,
+                      orc_keypoint *kps, uint8_t *desc, int cap) {
+    ygz::ORBextractor ext(nfeatures, scale, nlevels, ini_th, min_th);
+    cv::Mat im(h, w, CV_8U, (void *) img, (size_t) stride), descriptors;
+    std::vector<cv::KeyPoint> keys;
+    ext(im, cv::Mat(), keys, descriptors);
+    const int n = (int) keys.size();
+    if (n > cap) return -n;
+    for (int i = 0; i < n; i++) {
+        std::memcpy(&kps[i], &keys[i], sizeof(orc_keypoint));
+        std::memcpy(desc + 32 * (size_t) i, descriptors.data + (size_t) i * descriptors.step, 32);
+    }
+    return n;
+}
+
+/* Frame::ExtractORB (src/Frame.cc:332-348): ComputePyramid into frame->mvImagePyramid, then operator()(Frame*, mvKeys, mDescriptors, method);
+ * method 0 = ORBSLAM_KEYPOINT, 2 = DSO_KEYPOINT.  kps holds the n_existing direct-tracked keys on entry.  Also returns level
+ * `probe_level` of the extractor's public mvImagePyramid (probe may be NULL). */
+int adp_extract_frame(int nfeatures, float scale, int nlevels, int ini_th, int min_th, const uint8_t *img, int w, int h, int stride,
+                      int method, int n_existing, orc_keypoint *kps, uint8_t *desc, int cap, int probe_level, uint8_t *probe) {
+    ygz::ORBextractor ext(nfeatures, scale, nlevels, ini_th, min_th);
+    cv::Mat im(h, w, CV_8U, (void *) img, (size_t) stride);
+    ext.ComputePyramid(im);                                                   // src/Frame.cc:807-813
+    Frame F;
+    F.mvImagePyramid.resize(nlevels);
+    for (int l = 0; l < nlevels; l++) F.mvImagePyramid[l] = ext.mvImagePyramid[l].clone();
+    if (probe) {
+        const cv::Mat &L = ext.mvImagePyramid[probe_level];
+        for (int y = 0; y < L.rows; y++) std::memcpy(probe + (size_t) y * L.cols, L.data + (size_t) y * L.step, L.cols);
+    }
+    F.mvKeys.resize(n_existing);
+    for (int i = 0; i < n_existing; i++) F.mvKeys[i] = to_cv(kps[i]);
+    F.N = n_existing;
+    ext(&F, F.mvKeys, F.mDescriptors, (ygz::ORBextractor::KeyPointMethod) method, true);
+    const int n = (int) F.mvKeys.size();
+    if (n > cap) return -n;
+    for (int i = 0; i < n; i++) {
+        std::memcpy(&kps[i], &F.mvKeys[i], sizeof(orc_keypoint));
+        std::memcpy(desc + 32 * (size_t) i, F.mDescriptors.data + (size_t) i * F.mDescriptors.step, 32);
+    }
+    return n;
+}
+
+/* SparseImgAlign::run(Frame* ref, Frame* cur, SE3f& TCR) as Tracking::TrackWithSparseAlignment calls it (src/Tracking.cc:2087) */
+int adp_sia_run(const orc_sia_problem *p, int max_level, int min_level, int n_iter, float *out_q, float *out_t) {
+    Frame::fx = p->fx; Frame::fy = p->fy; Frame::cx = p->cx; Frame::cy = p->cy;
+    Frame R, Cf;
+    std::vector<MapPoint> pts(p->n);
+    R.N = p->n;
+    R.mvKeys.resize(p->n);
+    R.mvpMapPoints.assign(p->n, nullptr);
+    R.mvbOutlier.assign(p->n, false);
+    for (int i = 0; i < p->n; i++) {
+        R.mvKeys[i] = cv::KeyPoint(p->ref_px[2 * i], p->ref_px[2 * i + 1], 31.f);
+        pts[i].mWorldPos = Vector3f(p->world_xyz[3 * i], p->world_xyz[3 * i + 1], p->world_xyz[3 * i + 2]);
+        if (p->valid[i]) R.mvpMapPoints[i] = &pts[i];
+    }
+    R.mvInvScaleFactors.assign(p->inv_scale_factors, p->inv_scale_factors + p->n_levels);
+    R.mvImagePyramid.resize(p->n_levels);
+    Cf.mvImagePyramid.resize(p->n_levels);
+    for (int l = 0; l < p->n_levels; l++) {
+        R.mvImagePyramid[l] = cv::Mat(p->level_h[l], p->level_w[l], CV_8U, (void *) p->ref_levels[l]);
+        Cf.mvImagePyramid[l] = cv::Mat(p->level_h[l], p->level_w[l], CV_8U, (void *) p->cur_levels[l]);
+    }
+    R.mTcw = pose_from_q(p->ref_q, p->ref_t);
+    Cf.mTcw = pose_from_q(p->cur_q, p->cur_t);
+    ygz::SparseImgAlign align(max_level, min_level, n_iter);
+    SE3f TCR;
+    const size_t n = align.run(&R, &Cf, TCR);
+    ygz::b200::pose_to_qt(TCR, out_q, out_t);
+    return (int) n;
+}
+
+}  // extern "C"
+#endif

@@ -204,3 +204,31 @@ class RefVocabulary:
                                         C.byref(fvn), node.ctypes.data_as(i32p), off.ctypes.data_as(i32p), idx.ctypes.data_as(i32p))
         fv = {int(node[j]): [int(x) for x in idx[off[j]:off[j + 1]]] for j in range(fvn.value)}
         return ids[:nb].copy(), vals[:nb].copy(), fv
+
+
+def adapters_lib():
+    """oracle/_ref/libadapters_e2e.so: oracle/ref_matcher_shim.cpp compiled with -DSHIM_USE_ADAPTERS — the same caller code as
+    libmatcher_ref.so, but ygz::ORBmatcher / ORBextractor / SparseImgAlign are the product's literal-signature adapters
+    (include/ygz/adapters.h) over libygz_b200.so.  Needs a GPU at run time.  Built in the build container only (it needs the
+    reference's Common.h to compile); travels prebuilt."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libadapters_e2e.so")
+    if os.path.exists(REF_SRC):
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "_ref/libadapters_e2e.so"], check=True)
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    i32p = C.POINTER(C.c_int)
+    L.adp_hamming256.argtypes = [u8p, u8p]
+    L.adp_search_by_bow.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, i32p]
+    L.adp_search_by_projection_points.argtypes = [C.c_float, C.c_void_p, C.c_void_p, i32p, C.c_int, C.c_float, C.c_int]
+    L.adp_search_by_projection_last.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int]
+    L.adp_search_by_projection_kf.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, u8p, C.c_float, C.c_int]
+    L.adp_search_for_initialization.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, f32p, i32p, C.c_int]
+    L.adp_search_by_bow_kf.argtypes = [C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, i32p]
+    L.adp_search_for_triangulation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, f32p, C.POINTER(C.c_float), C.POINTER(C.c_float), f32p,
+                                               C.c_int, i32p]
+    L.adp_extract_image.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_void_p, u8p, C.c_int]
+    L.adp_extract_frame.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, u8p, C.c_int, C.c_int, u8p]
+    L.adp_sia_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p]
+    return L

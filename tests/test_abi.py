@@ -85,3 +85,23 @@ def test_cpp_class_mirror_compiles_and_links(tmp_path):
                         "-L" + libdir, "-lygz_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_adapters_compile_against_reference_types():
+    """include/ygz/adapters.h (the reference's literal signatures over Frame* / KeyFrame* / MapPoint*) compiles behind the same
+    caller code that drives the reference's own ORBmatcher.cc (oracle/ref_matcher_shim.cpp, -DSHIM_USE_ADAPTERS), against the
+    reference's Common.h + the stand-in Frame / KeyFrame / MapPoint of oracle/ref_mock, and links to the product library.
+    Build container only (needs /root/reference/include/Common.h); the run is tests/test_adapters_gpu.py."""
+    import subprocess
+    if not os.path.exists("/root/reference/include/Common.h"):
+        pytest.skip("reference headers not present on this box")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["make", "-s", "-B", "-C", odir, "_ref/libadapters_e2e.so"], check=True)
+    so = os.path.join(odir, "_ref", "libadapters_e2e.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    for name in ("adp_search_by_bow", "adp_search_by_bow_kf", "adp_search_by_projection_points", "adp_search_by_projection_last",
+                 "adp_search_by_projection_kf", "adp_search_for_initialization", "adp_search_for_triangulation", "adp_extract_image",
+                 "adp_extract_frame", "adp_sia_run"):
+        assert (" T " + name) in syms, name
+    undef = subprocess.run(["nm", "-D", "--undefined-only", so], capture_output=True, text=True, check=True).stdout
+    assert "ygz_search_by_bow" in undef and "orc_" not in undef          # product entry points, never the oracle
