@@ -419,12 +419,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=None, help="units per step: frames (c2, default 256), stereo pairs (c5, 128), alignment problems (c3, 592)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = the headline (BASELINE.json metric); c3 / c5 = the SparseImgAlign and stereo configurations (bench_c3c5.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--inflight", type=int, default=3, help="batches in flight on the end-to-end (host buffer) path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.batch is None:
+        args.batch = {"c2": 256, "c3": 592, "c5": 128}[args.workload]
     # The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner there) share fd 1, so
     # everything except the final line goes to stderr: fd 1 is pointed at fd 2 for the whole run and the JSON line is
     # written to the saved descriptor.
@@ -433,6 +437,12 @@ def main():
     _JSON_FD = os.dup(1)
     os.dup2(2, 1)
     if args.impl == "reference":
+        if args.workload != "c2":
+            if env_int("RANK", 0) == 0:
+                import bench_c3c5
+                ctx = dict(host_threads=host_threads, emit_json=emit_json)
+                (bench_c3c5.run_c5_reference if args.workload == "c5" else bench_c3c5.run_c3_reference)(args, args.batch, ctx)
+            return 0
         return run_reference(args)
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -448,6 +458,16 @@ def main():
     if m.device_count() <= local:
         raise SystemExit("bench.py needs a CUDA device (product path has no CPU fallback)")
     B = args.batch
+    if args.workload != "c2":
+        import importlib
+        import bench_c3c5
+        ctx = dict(m=m, torch=torch, dist=dist, rank=rank, world=world, local=local, ClockSampler=ClockSampler, host_threads=host_threads,
+                   measured_peak_gbs=measured_peak_gbs, emit_json=emit_json, shard=importlib.import_module("orb_ygz_slam_b200.shard"))
+        (bench_c3c5.run_c5 if args.workload == "c5" else bench_c3c5.run_c3)(args, B, ctx)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     frames = make_frames(1000 + rank, B)
 
     ex = m.ORBextractor(width=W, height=H, max_batch=B, device=local, **ORB)

@@ -303,6 +303,24 @@ int ygz_compute_stereo_matches(ygz_orb* left, ygz_orb* right, int frame, const y
                                const ygz_keypoint* keysR, const uint8_t* descR, int Nr, float mb, float mbf,
                                float* mvuRight, float* mvDepth);
 
+/* Batched, device-resident form (BASELINE C5: many stereo pairs per call): frame f of the left handle's last batch with frame f of
+ * the right handle's, both extractors' key points / descriptors / pyramids read in place on the device (zero copy): the row-band
+ * association and sub-pixel refinement of ComputeStereoMatches for every left key, the median cut (:668-681) per frame on the
+ * device, and — when any bf_* pointer is given — C5's dense brute-force matcher (best / second-best right descriptor of every
+ * left descriptor, first index wins ties).  Host outputs, each [n_frames][capL] with capL = ygz_orb_max_keypoints(left) (NULL to
+ * skip); slots past a frame's key count hold -1.  n_matches[n_frames] = the return value of ComputeStereoMatches' counting per
+ * frame.  The _async form enqueues on the left extractor's stream (ordered after the right one's); outputs (pinned) are valid
+ * after ygz_orb_wait(left).  At most 4096 left key slots per frame. */
+int ygz_stereo_batch(ygz_orb* left, ygz_orb* right, int n_frames, float mb, float mbf, float* mvuRight, float* mvDepth,
+                     int* n_matches, int* bf_best, int* bf_dist, int* bf_second);
+int ygz_stereo_batch_async(ygz_orb* left, ygz_orb* right, int n_frames, float mb, float mbf, float* mvuRight, float* mvDepth,
+                           int* n_matches, int* bf_best, int* bf_dist, int* bf_second);
+/* device-timed repeats of one whole C5 step, inputs resident: both extractors (each on its own stream) + the batched
+ * association + median cut (+ brute force).  ms = total over `iters`; stage_ms[4] (optional, last iteration) =
+ * {extractors L || R, association, median cut, brute force}. */
+int ygz_stereo_frontend_time(ygz_orb* left, ygz_orb* right, int n_frames, int iters, float mb, float mbf, int with_bf, float* ms,
+                             float* stage_ms);
+
 /* ------------------------------------------------------------------ direct (patch) projection search
  * ORBmatcher::FindDirectProjection(KeyFrame* ref, Frame* curr, MapPoint* mp,
  * Vector2f& px_curr, int& search_level), /root/reference/src/ORBmatcher.cc:1575-1602, with GetWarpAffineMatrix

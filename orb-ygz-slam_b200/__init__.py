@@ -97,6 +97,7 @@ ABI_SYMBOLS = [
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
+    "ygz_stereo_batch", "ygz_stereo_batch_async", "ygz_stereo_frontend_time",
     "ygz_vocab_load", "ygz_vocab_from_memory", "ygz_vocab_destroy", "ygz_vocab_info", "ygz_vocab_transform", "ygz_vocab_transform_orb",
 ]
 
@@ -156,6 +157,9 @@ def lib():
     sigs.setdefault('ygz_search_for_initialization', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, i32p, C.c_int]
     sigs.setdefault('ygz_search_by_bow_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, u32p, i32p, i32p]
     sigs.setdefault('ygz_compute_stereo_matches', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p]
+    sigs.setdefault('ygz_stereo_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p, i32p, i32p, i32p, i32p]
+    sigs.setdefault('ygz_stereo_batch_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    sigs.setdefault('ygz_stereo_frontend_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, f32p, f32p]
     sigs.setdefault('ygz_vocab_load', {})['argtypes'] = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     sigs.setdefault('ygz_vocab_from_memory', {})['argtypes'] = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
     sigs.setdefault('ygz_vocab_destroy', {})['argtypes'] = [C.c_void_p]
@@ -717,6 +721,28 @@ def ComputeStereoMatches(ex_left, ex_right, keysL, descL, keysR, descR, mb, mbf,
     if n < 0:
         _check(n, "ygz_compute_stereo_matches")
     return u, z, n
+
+
+def StereoBatch(ex_left, ex_right, n_frames, mb, mbf, brute_force=False):
+    """Batched, device-resident Frame::ComputeStereoMatches over the n_frames stereo pairs the two extractor handles hold (their last
+    batch), median cut included, plus (brute_force) the dense best / second-best right descriptor of every left key (BASELINE C5).
+    Returns dict(u_right[n, cap], depth[n, cap], n_matches[n], bf_best / bf_dist / bf_second [n, cap] or None)."""
+    cap = ex_left.cap
+    u = np.zeros((n_frames, cap), np.float32); z = np.zeros((n_frames, cap), np.float32); nm = np.zeros(n_frames, np.int32)
+    bf = [np.zeros((n_frames, cap), np.int32) for _ in range(3)] if brute_force else [None] * 3
+    _check(lib().ygz_stereo_batch(ex_left.h, ex_right.h, n_frames, float(mb), float(mbf), _ptr(u, f32p), _ptr(z, f32p), _ptr(nm, i32p),
+                                  _ptr(bf[0], i32p), _ptr(bf[1], i32p), _ptr(bf[2], i32p)), "ygz_stereo_batch")
+    return dict(u_right=u, depth=z, n_matches=nm, bf_best=bf[0], bf_dist=bf[1], bf_second=bf[2])
+
+
+def time_stereo_frontend(ex_left, ex_right, n_frames, iters, mb, mbf, brute_force=True):
+    """Device-timed C5 steps (both extractors + batched stereo association + median cut + brute force), inputs resident.
+    Returns (total ms over iters, stage ms of the last iteration {extract, match, median_cut, brute_force})."""
+    ms = C.c_float()
+    st = np.zeros(4, np.float32)
+    _check(lib().ygz_stereo_frontend_time(ex_left.h, ex_right.h, n_frames, iters, float(mb), float(mbf), int(brute_force), C.byref(ms),
+                                          _ptr(st, f32p)), "ygz_stereo_frontend_time")
+    return ms.value, dict(zip(("extract", "match", "median_cut", "brute_force"), [float(x) for x in st]))
 
 
 def make_direct_frame(levels, q=(0, 0, 0, 1), t=(0, 0, 0), cls=None):

@@ -246,12 +246,17 @@ int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, 
  * word -1, node -1, weight 0).  The node ids are what ygz_search_by_bow_batch takes as `node_of_feature`. */
 int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levelsup, int* word_id, float* weight, int* node_id,
                             float* ms) {
-    YGZ_ARG_CHECK(v && orb && n_frames >= 1);
+    YGZ_ARG_CHECK(v && orb && n_frames >= 1 && n_frames <= ygz_orb_max_batch(orb));
     YGZ_CUDA_TRY(cudaSetDevice(v->device));
     void *d_kps = nullptr, *d_desc = nullptr, *d_counts = nullptr;
     int cap = 0;
     int rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap);
     if (rc) return rc;
+    {   // the vocabulary and the extractor must live on the same device (the kernel dereferences both)
+        cudaPointerAttributes at;
+        YGZ_CUDA_TRY(cudaPointerGetAttributes(&at, d_desc));
+        if (at.device != v->device) { set_last_error("vocabulary and extractor are on different devices"); return YGZ_ERR_ARG; }
+    }
     const int n = n_frames * cap;
     if ((rc = vocab_scratch(v, n))) return rc;
     YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));

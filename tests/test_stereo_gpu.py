@@ -41,3 +41,42 @@ def test_stereo_edge_cases(gpu, synth):
     assert n == 0 and (u == -1).all() and (z == -1).all()
     u, z, n = gpu.ComputeStereoMatches(exL, exR, kL, dL, kR, dR, 0.5, 1.0)                # maxD = 2 px: disparities of 6+ are out of range
     assert n == 0 and (u == -1).all()
+
+
+@pytest.mark.parametrize("w,h,nf,B", [(1242, 375, 2000, 5), (640, 360, 700, 3)])
+def test_stereo_batch_device_resident(gpu, oracle, synth, w, h, nf, B):
+    """ygz_stereo_batch: B stereo pairs straight from the two extractors' device outputs (association without the host row table,
+    median cut on the device, dense brute force) against the oracle run pair by pair — bit-exact, counts included."""
+    pairs = [synth.synth_stereo_pair(10 + i, w, h) for i in range(B)]
+    left = np.stack([p[0] for p in pairs]); right = np.stack([p[1] for p in pairs])
+    if B > 2:
+        right[2] = 128                              # a textureless right image: no right keys for that pair -> no matches
+    exL = gpu.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=B)
+    exR = gpu.ORBextractor(nf, 1.2, 8, 20, 7, width=w, height=h, max_batch=B)
+    resL = exL.extract_batch(left)
+    resR = exR.extract_batch(right)
+    t = exL.tables()
+    mbf, mb = 386.1448, 0.54
+    out = gpu.StereoBatch(exL, exR, B, mb, mbf, brute_force=True)
+    for f in range(B):
+        (kL, dL), (kR, dR) = resL[f], resR[f]
+        n = len(kL)
+        pyrL = gpu.make_direct_frame([exL.level(f, l) for l in range(8)])
+        pyrR = gpu.make_direct_frame([exR.level(f, l) for l in range(8)])
+        ou, oz, on = oracle.compute_stereo_matches(pyrL, pyrR, kL, dL, kR, dR, t["scale"], t["inv_scale"], mb, mbf)
+        assert out["n_matches"][f] == on, (f, out["n_matches"][f], on)
+        assert (out["u_right"][f, :n].view(np.uint32) == ou.view(np.uint32)).all()
+        assert (out["depth"][f, :n].view(np.uint32) == oz.view(np.uint32)).all()
+        assert (out["u_right"][f, n:] == -1).all() and (out["depth"][f, n:] == -1).all()
+        if len(kR):
+            bi, bd, sd = oracle.bf_top2(dL, dR)
+            assert (out["bf_best"][f, :n] == bi).all() and (out["bf_dist"][f, :n] == bd).all() and (out["bf_second"][f, :n] == sd).all()
+        assert (out["bf_best"][f, n:] == -1).all()
+        if f == 2:
+            assert on == 0 and len(kR) == 0
+    assert out["n_matches"][0] > 0.3 * len(resL[0][0])
+    # the per-frame entry point on the same handles gives the same answer
+    u, z, n1 = gpu.ComputeStereoMatches(exL, exR, resL[1][0], resL[1][1], resR[1][0], resR[1][1], mb, mbf, frame=1)
+    assert n1 == out["n_matches"][1] and (u.view(np.uint32) == out["u_right"][1, :len(u)].view(np.uint32)).all()
+    ms, stages = gpu.time_stereo_frontend(exL, exR, B, 2, mb, mbf)
+    assert ms > 0 and stages["match"] > 0
