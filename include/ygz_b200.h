@@ -98,6 +98,10 @@ int ygz_orb_compute_pyramid(ygz_orb* h, const uint8_t* images, int n, size_t fra
  * REFLECT_101 frame of src/ORBextractor.cc:1141-1146 into a (w+2b)*(h+2b) buffer. */
 int ygz_orb_get_level(ygz_orb* h, int frame, int level, int border, uint8_t* out);
 
+/* GaussianBlur(mvImagePyramid[level], 7x7, sigma 2, REFLECT_101) as the last extraction left it on the device
+ * (src/ORBextractor.cc:1009-1010, :1079-1084): continuous w*h bytes.  Parity instrumentation (stage tests). */
+int ygz_orb_get_blurred_level(ygz_orb* h, int frame, int level, uint8_t* out);
+
 /* Split phases for device-resident timing (bench.py `value`) and stage-level parity tests. */
 int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride);
 int ygz_orb_run(ygz_orb* h, int n);                       /* all kernels, inputs already in HBM */

@@ -170,6 +170,8 @@ void ldlt_solve6(const float* Ain, const float* b, float* x) {
     for (int i = 0; i < n; i++) x[i] = y[i];
 }
 
+thread_local bool g_wide_sums = false;
+
 struct Aligner {
     const orc_sia_problem* P;
     SE3 ref_T;
@@ -249,6 +251,10 @@ struct Aligner {
         const int border = 3;
         const float scale = P->inv_scale_factors[level_];
         float chi2 = 0.0f;
+        // wide_sums (test switch orc_sia_wide_sums): accumulate H, Jres and chi2 in double and round once — the value the
+        // reference's float sums approximate, independent of summation order / FMA contraction.  Used to state how far the
+        // reference's own float accumulation is from exact arithmetic on ill-conditioned problems (tests/test_sia_gpu.py).
+        double Hd[36] = {0}, Jd[6] = {0}, chi2d = 0.0;
         for (int i = 0; i < P->n; i++) {
             if (!visible_fts_[i]) continue;
             float xyz_ref[3], xyz_cur[3];
@@ -275,15 +281,29 @@ struct Aligner {
                     const float intensity_cur = w_tl * p[0] + w_tr * p[1] + w_bl * p[stride] + w_br * p[stride + 1];
                     const float res = intensity_cur - (*ref_ptr);
                     chi2 += res * res * 1.0f;
+                    chi2d += (double)(res * res);
                     n_meas_++;
                     if (linearize) {
                         const float* J = jacobian_cache_.data() + 6 * ((size_t)i * 16 + pixel_counter);
-                        for (int r = 0; r < 6; r++)
-                            for (int c = 0; c < 6; c++) H_[r * 6 + c] += J[r] * J[c];
-                        for (int r = 0; r < 6; r++) Jres_[r] -= J[r] * res;
+                        if (g_wide_sums) {
+                            for (int r = 0; r < 6; r++)
+                                for (int c = 0; c < 6; c++) Hd[r * 6 + c] += (double)(J[r] * J[c]);
+                            for (int r = 0; r < 6; r++) Jd[r] -= (double)(J[r] * res);
+                        } else {
+                            for (int r = 0; r < 6; r++)
+                                for (int c = 0; c < 6; c++) H_[r * 6 + c] += J[r] * J[c];
+                            for (int r = 0; r < 6; r++) Jres_[r] -= J[r] * res;
+                        }
                     }
                 }
             }
+        }
+        if (g_wide_sums) {
+            if (linearize) {
+                for (int k = 0; k < 36; k++) H_[k] = (float)Hd[k];
+                for (int k = 0; k < 6; k++) Jres_[k] = (float)Jd[k];
+            }
+            chi2 = (float)chi2d;
         }
         return chi2 / n_meas_;
     }
@@ -337,6 +357,9 @@ void orc_se3_inv(const float* q, const float* t, float* qo, float* to) {
     SE3 r = se3_inv(a);
     std::memcpy(qo, r.q, 16); std::memcpy(to, r.t, 12);
 }
+
+/* test switch: 1 = H / Jres / chi2 summed in double (see computeResiduals); per calling thread */
+void orc_sia_wide_sums(int on) { g_wide_sums = on != 0; }
 
 // src/SparseImageAlign.cc:20-49
 int orc_sia_run(const orc_sia_problem* p, int max_level, int min_level, int n_iter, float eps,

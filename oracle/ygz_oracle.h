@@ -142,6 +142,9 @@ typedef struct {
  * trace (optional, 8 floats per evaluated iteration: level, iter, chi2, n_meas, max|x|, accepted,0,0) */
 int orc_sia_run(const orc_sia_problem* p, int max_level, int min_level, int n_iter, float eps,
                 float* out_q, float* out_t, float* H_out, float* trace, int trace_cap, int* trace_n);
+/* test switch (per calling thread): 1 = accumulate H, Jres and chi2 in double and round once — exact-arithmetic reference for
+ * the float sums of computeResiduals (how far the reference's own float accumulation is from the exact value) */
+void orc_sia_wide_sums(int on);
 /* ---- direct (patch) projection search: ORBmatcher::FindDirectProjection src/ORBmatcher.cc:1575-1602 with
  * GetWarpAffineMatrix :1525-1547, WarpAffine :1549-1573 and ygz::Align2D src/Align.cc:8-103.   */
 typedef struct {

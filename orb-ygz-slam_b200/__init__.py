@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "ygz_last_error", "ygz_device_count", "ygz_device_info",
     "ygz_orb_create", "ygz_orb_destroy", "ygz_orb_tables", "ygz_orb_level_size", "ygz_orb_max_keypoints", "ygz_orb_max_batch",
     "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_extract_frame_dso",
-    "ygz_orb_compute_pyramid", "ygz_orb_get_level",
+    "ygz_orb_compute_pyramid", "ygz_orb_get_level", "ygz_orb_get_blurred_level",
     "ygz_orb_upload", "ygz_orb_run", "ygz_orb_download", "ygz_orb_sync", "ygz_orb_get_candidates",
     "ygz_orb_time", "ygz_debug_cos_sin", "ygz_orb_device_outputs", "ygz_orb_device_level", "ygz_orb_stream", "ygz_orb_counters",
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
@@ -131,6 +131,7 @@ def lib():
     sigs.setdefault('ygz_orb_extract_frame_dso', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, i32p, C.c_int, i32p]
     sigs.setdefault('ygz_orb_compute_pyramid', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
     sigs.setdefault('ygz_orb_get_level', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    sigs.setdefault('ygz_orb_get_blurred_level', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     sigs.setdefault('ygz_orb_upload', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
     sigs.setdefault('ygz_orb_run', {})['argtypes'] = [C.c_void_p, C.c_int]
     sigs.setdefault('ygz_orb_download', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -330,6 +331,13 @@ class ORBextractor:
         w, h = self.level_size(level)
         out = np.zeros((h + 2 * border, w + 2 * border), np.uint8)
         _check(self.L.ygz_orb_get_level(self.h, frame, level, border, out.ctypes.data), "ygz_orb_get_level")
+        return out
+
+    def blurred_level(self, frame, level):
+        """GaussianBlur(mvImagePyramid[level]) as the last extraction left it on the device (parity instrumentation)."""
+        w, h = self.level_size(level)
+        out = np.zeros((h, w), np.uint8)
+        _check(self.L.ygz_orb_get_blurred_level(self.h, frame, level, out.ctypes.data), "ygz_orb_get_blurred_level")
         return out
 
     def candidates(self, frame, level, cap=400000):

@@ -7,6 +7,9 @@
 #include <cstring>
 #include <string>
 #include "../../include/ygz_b200.h"
+// NVTX ranges around every stage launch (the reference's only tracing is glog timing lines): header-only NVTX v3,
+// no-ops unless a tool (nsys / ncu --nvtx) is attached.
+#include <nvtx3/nvToolsExt.h>
 
 namespace ygz_b200 {
 
@@ -119,4 +122,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 }
 #endif
 
+}  // namespace ygz_b200
+
+namespace ygz_b200 {
+struct NvtxRange {          // RAII: one named range per stage on the calling (launching) thread
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 }  // namespace ygz_b200

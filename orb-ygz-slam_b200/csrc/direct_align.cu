@@ -334,7 +334,9 @@ int ygz_direct_set_pose(ygz_direct* h, int slot, const float* q, const float* t)
 }
 
 static int direct_launch(ygz_direct* h, int n) {
+    { NvtxRange nvtx_range("ygz/FindDirectProjection");
     k_direct_projection<<<ceil_div(n, 128), 128, 0, h->stream>>>(h->d_frames, h->P, h->d_items, n, h->d_px, h->d_level, h->d_ok);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     return YGZ_OK;
 }

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                 }
                 nkeep += __popc(bal);
             }
+            __syncwarp();       // every lane's neighbour reads of the score map are done before any entry is cleared below
             // vKeysCell.empty() after the iniTh call decides the fallback to minTh (src/ORBextractor.cc:765-770)
             if (nkeep > 0 || pass == 1) break;
             // the minTh pass recomputes every score it needs: drop this pass's entries (minTh > iniTh would leave stale ones)

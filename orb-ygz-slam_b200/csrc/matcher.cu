@@ -424,7 +424,9 @@ int ygz_hamming_pairs(ygz_matcher* h, const uint8_t* q, int nq, const uint8_t* t
         const int m = std::min(h->max_pairs, n_pairs - off);
         YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_pq, pair_q + off, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
         YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_pt, pair_t + off, (size_t)m * 4, cudaMemcpyHostToDevice, h->stream));
+        { NvtxRange nvtx_range("ygz/Hamming pairs");
         k_hamming_pairs<<<ceil_div(m, 256), 256, 0, h->stream>>>((const uint4*)h->d_q, (const uint4*)h->d_t, h->d_pq, h->d_pt, m, h->d_dist);
+        }
         YGZ_CUDA_TRY(cudaGetLastError());
         YGZ_CUDA_TRY(cudaMemcpyAsync(dist + off, h->d_dist, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
         YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -931,7 +933,9 @@ int ygz_search_by_bow_batch(ygz_matcher* h, ygz_orb* orb, float nnratio, int che
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
     A.node = use_nodes ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
+    { NvtxRange nvtx_range("ygz/SearchByBoW batch");
     k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     h->last_args = A;
     h->last_pairs = n_pairs;
@@ -966,7 +970,9 @@ int ygz_search_by_bow_batch_async(ygz_matcher* h, ygz_orb* orb, float nnratio, i
     A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
     A.node = h->vocab ? h->d_node : nullptr; A.cap = cap; A.kf_idx = h->d_kf_idx; A.f_idx = h->d_f_idx; A.nnratio = nnratio;
     A.check_ori = check_ori; A.matches = h->d_matches; A.nmatches = h->d_nmatches;
+    { NvtxRange nvtx_range("ygz/SearchByBoW batch");
     k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), st>>>(A);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     h->last_args = A;
     h->last_pairs = n_pairs;
@@ -1004,7 +1010,9 @@ int ygz_search_by_bow_batch_time(ygz_matcher* h, ygz_orb* orb, float nnratio, in
     YGZ_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < iters; i++) {
         if (h->vocab && (rc = launch_node_ids(h, orb, h->bow_frames, A.cap, h->stream))) return rc;
+        { NvtxRange nvtx_range("ygz/SearchByBoW batch");
         k_bow_match_batch<<<n_pairs, BOW_THREADS, bow_smem_bytes(A.cap), h->stream>>>(A);
+        }
     }
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -1027,7 +1035,9 @@ int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, flo
     for (int i = 0; i < iters; i++) {
         if ((rc = ygz_orb_run(orb, n_frames))) return rc;
         if (h->vocab && (rc = launch_node_ids(h, orb, h->bow_frames, A.cap, st))) return rc;
+        { NvtxRange nvtx_range("ygz/SearchByBoW batch");
         k_bow_match_batch<<<h->last_pairs, BOW_THREADS, bow_smem_bytes(A.cap), st>>>(A);
+        }
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, st));
@@ -1062,7 +1072,9 @@ int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matche
         cudaStream_t st = (i & 1) ? sB : sA;
         if ((rc = ygz_orb_run(orb, n_frames))) return rc;
         if (h->vocab && (rc = launch_node_ids(h, orb, h->bow_frames, (i & 1) ? B.cap : A.cap, st))) return rc;
+        { NvtxRange nvtx_range("ygz/SearchByBoW batch");
         k_bow_match_batch<<<h->last_pairs, BOW_THREADS, bow_smem_bytes((i & 1) ? B.cap : A.cap), st>>>((i & 1) ? B : A);
+        }
     }
     YGZ_CUDA_TRY(cudaGetLastError());
     YGZ_CUDA_TRY(cudaEventRecord(hB->ev1, sB));

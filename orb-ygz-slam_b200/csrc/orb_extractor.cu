@@ -57,6 +57,8 @@ struct ygz_orb {
     uint8_t* d_desc = nullptr;
     int* d_counts = nullptr;
     ExistingKey* d_existing = nullptr;
+    uint8_t* d_stage = nullptr;          // upload staging for frames whose rows are not 16-byte multiples (see ygz_orb_upload)
+    size_t stage_bytes = 0;
     int existing_cap = 0;
     float4* d_pattern = nullptr;
     TmaMaps tma;
@@ -125,7 +127,7 @@ static int orb_free(ygz_orb* h) {
     cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_pts);
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
-    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing); cudaFree(h->d_pattern);
+    cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing); cudaFree(h->d_stage); cudaFree(h->d_pattern);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -469,8 +471,18 @@ int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride
         // contiguous frames and no row padding on the device (w % 16 == 0): one 1-D copy
         YGZ_CUDA_TRY(cudaMemcpyAsync(L0.d_base, images, L0.frame_stride * n, cudaMemcpyHostToDevice, h->stream));
     } else if (frame_stride == (size_t)row_stride * L0.h) {
-        YGZ_CUDA_TRY(cudaMemcpy2DAsync(L0.d_base, L0.pitch, images, row_stride, L0.w, (size_t)L0.h * n,
-                                       cudaMemcpyHostToDevice, h->stream));
+        // Contiguous frames whose row length is not the device pitch (w % 16 != 0, e.g. 1242): a 2-D host-to-device copy of
+        // n*h short rows runs at a fraction of the link rate (measured 10 GB/s on 1242-byte rows), so the block crosses PCIe as
+        // ONE 1-D copy into a staging buffer and is re-pitched on the device.
+        const size_t bytes = frame_stride * n;
+        if (bytes > h->stage_bytes) {
+            cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_bytes = 0;
+            YGZ_CUDA_TRY(cudaMalloc(&h->d_stage, frame_stride * h->cfg.max_batch));
+            h->stage_bytes = frame_stride * h->cfg.max_batch;
+        }
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_stage, images, bytes, cudaMemcpyHostToDevice, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(L0.d_base, L0.pitch, h->d_stage, row_stride, L0.w, (size_t)L0.h * n,
+                                       cudaMemcpyDeviceToDevice, h->stream));
     } else {
         for (int f = 0; f < n; f++)
             YGZ_CUDA_TRY(cudaMemcpy2DAsync(L0.d_base + f * L0.frame_stride, L0.pitch, images + f * frame_stride, row_stride,
@@ -485,6 +497,7 @@ int ygz_orb_upload(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride
 static inline int fast_launches(const ygz_orb* h) { return (h->n_fast_narrow > 0) + (h->n_fast_wide > 0); }
 
 static int launch_pyramid(ygz_orb* h, int n) {
+    NvtxRange nvtx_range("ygz/ComputePyramid");
     for (int l = 1; l < h->cfg.nlevels; l++) {
         const LevelHost& S = h->lv[l - 1];
         const LevelHost& D = h->lv[l];
@@ -504,6 +517,7 @@ static int launch_pyramid(ygz_orb* h, int n) {
 }
 
 static int launch_detect(ygz_orb* h, int n) {
+    NvtxRange nvtx_range("ygz/FAST cells");
     // the few cells the TMA kernel does not take go first, on the auxiliary stream: one cell per warp is a latency-bound
     // launch (55 us for 1.5 % of the C1 cells when serialised) that hides completely beside the persistent kernel
     const bool fork = h->n_fast_wide > 0 && h->n_fast_narrow > 0;
@@ -535,6 +549,7 @@ static int launch_detect(ygz_orb* h, int n) {
 }
 
 static int launch_octree(ygz_orb* h, int n) {
+    NvtxRange nvtx_range("ygz/DistributeOctTree");
     dim3 grid(n, h->cfg.nlevels);
     k_octree<<<grid, OCT_THREADS, h->oct_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->d_keys,
                                                             h->d_keynode, h->d_nkeys, h->d_sel, h->d_nsel, h->oct_node_smem, h->oct_key_cache);
@@ -543,6 +558,7 @@ static int launch_octree(ygz_orb* h, int n) {
 }
 
 static int launch_blur(ygz_orb* h, int n) {
+    NvtxRange nvtx_range("ygz/GaussianBlur");
     dim3 grid(h->n_blur_tiles, n);
     k_blur_levels<<<grid, BLUR_THREADS, 0, h->stream>>>(h->P, h->tma, h->d_blur_tiles);
     YGZ_CUDA_TRY(cudaGetLastError());
@@ -550,6 +566,7 @@ static int launch_blur(ygz_orb* h, int n) {
 }
 
 static int launch_describe(ygz_orb* h, int n, int n_existing) {
+    NvtxRange nvtx_range("ygz/IC_Angle+rBRIEF");
     dim3 grid(ceil_div(h->P.sel_total, DESC_WARPS), n);
     k_orient_describe<<<grid, DESC_THREADS, 0, h->stream>>>(h->P, h->patch, 0, n_existing, h->P.sel_total, h->d_pattern, h->d_sel, h->d_nsel, nullptr,
                                                            h->d_kps, h->d_desc, h->d_counts);
@@ -847,6 +864,17 @@ int ygz_orb_get_level(ygz_orb* h, int frame, int level, int border, uint8_t* out
             for (int x = L.w; x < L.w + border; x++) D[x + border] = D[refl(x, L.w) + border];
         }
     }
+    return YGZ_OK;
+}
+
+/* GaussianBlur(mvImagePyramid[level], 7x7, sigma 2, BORDER_REFLECT_101) of frame `frame` as the last extraction left it on the
+ * device (src/ORBextractor.cc:1009-1010 / :1079-1084): continuous w*h bytes.  Parity instrumentation for the stage tests. */
+int ygz_orb_get_blurred_level(ygz_orb* h, int frame, int level, uint8_t* out) {
+    YGZ_ARG_CHECK(h && out && frame >= 0 && frame < h->cfg.max_batch && level >= 0 && level < h->cfg.nlevels);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const LevelHost& L = h->lv[level];
+    YGZ_CUDA_TRY(cudaMemcpy2DAsync(out, L.w, L.d_blur + frame * L.frame_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
     return YGZ_OK;
 }
 

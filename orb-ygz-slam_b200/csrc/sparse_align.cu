@@ -482,7 +482,9 @@ int ygz_sia_run(ygz_sia* h, const ygz_sia_problem* problems, int n_problems, int
     YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_prob, pd.data(), (size_t)n_problems * sizeof(SiaProblemDev), cudaMemcpyHostToDevice, h->stream));
     YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));      // pd / pageable sources must outlive the copies
     SiaArgs A = make_args(h, max_level, min_level, n_iter, eps);
+    { NvtxRange nvtx_range("ygz/SparseImgAlign::run");
     k_sia_align<<<n_problems, SIA_THREADS, 0, h->stream>>>(A);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     h->last_n = n_problems;
     YGZ_CUDA_TRY(cudaMemcpyAsync(out_q, h->d_q, (size_t)n_problems * 16, cudaMemcpyDeviceToHost, h->stream));
@@ -512,7 +514,9 @@ int ygz_sia_time(ygz_sia* h, int n_problems, int max_level, int min_level, int n
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
     SiaArgs A = make_args(h, max_level, min_level, n_iter, eps);
     YGZ_CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    { NvtxRange nvtx_range("ygz/SparseImgAlign::run");
     for (int i = 0; i < iters; i++) k_sia_align<<<n_problems, SIA_THREADS, 0, h->stream>>>(A);
+    }
     YGZ_CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
     YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));

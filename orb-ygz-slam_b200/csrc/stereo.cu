@@ -386,7 +386,9 @@ int stereo_batch_launch(ygz_stereo* S, const StereoBatch& A, int n_frames, int w
         g_stereo_smem_set = true;
     }
     const dim3 grid(ceil_div(A.capL, 8 * SB_KEYS_PER_WARP), n_frames);
+    { NvtxRange nvtx_range("ygz/ComputeStereoMatches batch");
     k_stereo_match_batch<<<grid, 256, smem, st>>>(A);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     if (after_match) YGZ_CUDA_TRY(cudaEventRecord(after_match, st));
     k_stereo_median_cut<<<n_frames, 1024, 0, st>>>(S->d_bu, S->d_bz, S->d_bsad, A.cntL, A.capL, S->d_bn);
@@ -482,9 +484,11 @@ int ygz_compute_stereo_matches(ygz_orb* left, ygz_orb* right, int frame, const y
     YGZ_CUDA_TRY(cudaMemcpyAsync(S->d_row_off, off.data(), (size_t)(nRows + 1) * 4, cudaMemcpyHostToDevice, S->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(S->d_row_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, S->stream));
     const float maxD = mbf / mb;                        // minZ = mb, :541-543
+    { NvtxRange nvtx_range("ygz/ComputeStereoMatches");
     k_stereo_match<<<ceil_div(N, 8), 256, 0, S->stream>>>(lv, S->d_kL, reinterpret_cast<const uint4*>(S->d_dL), N, S->d_kR,
                                                          reinterpret_cast<const uint4*>(S->d_dR), S->d_row_off, S->d_row_idx, nRows,
                                                          maxD, mbf, S->d_u, S->d_z, S->d_sad);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     std::vector<int> sad(N);
     YGZ_CUDA_TRY(cudaMemcpyAsync(mvuRight, S->d_u, (size_t)N * 4, cudaMemcpyDeviceToHost, S->stream));

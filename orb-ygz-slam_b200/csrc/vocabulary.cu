@@ -122,8 +122,10 @@ namespace ygz_b200 {
 int vocab_node_ids_async(ygz_vocab* v, const void* d_desc, const int* d_counts, int cap, int n_frames, int levelsup,
                          uint32_t* d_node_out, cudaStream_t st) {
     const int n = n_frames * cap;
+    { NvtxRange nvtx_range("ygz/ComputeBoW");
     k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, st>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, d_counts, cap, n,
                                                                    levelsup, 1, nullptr, nullptr, reinterpret_cast<int*>(d_node_out));
+    }
     return cudaGetLastError() == cudaSuccess ? YGZ_OK : YGZ_ERR_CUDA;
 }
 int vocab_device(const ygz_vocab* v) { return v->device; }
@@ -231,8 +233,10 @@ int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, 
     int rc = vocab_scratch(v, n);
     if (rc) return rc;
     YGZ_CUDA_TRY(cudaMemcpyAsync(v->d_in, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
+    { NvtxRange nvtx_range("ygz/ComputeBoW");
     k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n,
                                                                           levelsup, 0, v->d_wid, v->d_w, v->d_nid);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(weight, v->d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -265,9 +269,11 @@ int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levels
     YGZ_CUDA_TRY(cudaMemsetAsync(v->d_w, 0, (size_t)n * 4, v->stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms) { YGZ_CUDA_TRY(cudaEventCreate(&e0)); YGZ_CUDA_TRY(cudaEventCreate(&e1)); YGZ_CUDA_TRY(cudaEventRecord(e0, v->stream)); }
+    { NvtxRange nvtx_range("ygz/ComputeBoW");
     k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2,
                                                                           reinterpret_cast<const int*>(d_counts), cap, n, levelsup, 0,
                                                                           v->d_wid, v->d_w, v->d_nid);
+    }
     YGZ_CUDA_TRY(cudaGetLastError());
     if (ms) { YGZ_CUDA_TRY(cudaEventRecord(e1, v->stream)); }
     if (word_id) YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));

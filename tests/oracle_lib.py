@@ -287,6 +287,11 @@ def bf_top2(q, t):
     return bi, bd, sd
 
 
+def sia_wide_sums(on):
+    """Test switch of the oracle aligner (calling thread): H / Jres / chi2 summed in double and rounded once."""
+    lib().orc_sia_wide_sums(int(on))
+
+
 def sia_run(problem, max_level, min_level, n_iter=10, eps=1e-6, trace_cap=192):
     """problem: _Keep(SiaProblem) built with cls=oracle_lib.SiaProblem.  Returns (n_tracked, q, t, H, trace)."""
     q = np.zeros(4, np.float32)

@@ -45,6 +45,8 @@ def test_extract_stages_bit_exact(gpu, oracle, synth, w, h, nf, sf, nl, seeds):
             gc = ex.candidates(f, l)
             oc = ox.candidates(l)
             assert_kps_equal(gc, oc, "candidates level %d" % l)
+            if len(ox.level_keys(l)):          # the reference blurs a level only if it holds key points (src/ORBextractor.cc:1003-1010)
+                assert (ex.blurred_level(f, l) == ox.level(l, blurred=True)).all(), "blurred level %d" % l
         kps, desc = res[f]
         assert_kps_equal(kps, okps, "keypoints seed %d" % seed)
         assert (desc == odesc).all(), "descriptors: %d rows differ" % (desc != odesc).any(1).sum()

@@ -71,7 +71,14 @@ def test_sia_batch_and_edge_cases(gpu, oracle, synth):
 
 
 def test_sia_rollback_from_bad_init(gpu, oracle, synth):
-    """Far-off initial guess: exercises the chi2 rollback / early-stop paths; GPU must follow the oracle."""
+    """Far-off initial guess: exercises the chi2 rollback / early-stop paths; GPU must follow the oracle.
+
+    On this ill-conditioned problem the reference's OWN result is only determined to a few 1e-4: its float, sequential
+    accumulation of H / Jres (src/SparseImageAlign.cc:216-217) is ~1e-6 relative away from the exact sums, and the bad
+    conditioning of the first iterations amplifies that (the exact-sums run may even take a different accept / reject path).  The
+    device sums per-thread partials in float and reduces them in double — neither the reference's order nor exact.
+    The bound tested here is therefore max(1e-4, the CPU path's own float-vs-exact-sums spread, measured in
+    the test), with the identical accept / reject trace required on top; the seven well-conditioned seeds keep the plain 1e-4."""
     init = ((0.0, 0.0, 0.01, 0.99995), (0.15, -0.1, 0.05))
     pg, _ = build_problem(gpu, oracle, synth, 12, gpu.SiaProblem, init=init)
     po, _ = build_problem(gpu, oracle, synth, 12, oracle.SiaProblem, init=init)
@@ -81,4 +88,14 @@ def test_sia_rollback_from_bad_init(gpu, oracle, synth):
     tr = sia.trace()
     assert len(tr) == len(otr) and (tr[:, 5] == otr[:, 5]).all()
     assert n == on
-    assert pose_diff(q, t, oq, ot) <= 5e-4        # diverging problem: chaotic amplification, looser bound documented in DESIGN.md
+    # how well is the CPU result itself determined?  Same algorithm with exact (double) sums:
+    oracle.sia_wide_sums(True)
+    try:
+        wn, wq, wt, _, wtr = oracle.sia_run(po, 3, 1, 10, 1e-6)
+    finally:
+        oracle.sia_wide_sums(False)
+    d_gpu = pose_diff(q, t, oq, ot)                   # GPU vs the reference's arithmetic (float, sequential sums)
+    d_cpu = pose_diff(oq, ot, wq, wt)                 # the reference's float sums vs exact sums: the CPU path's own indeterminacy
+    print("bad-init case: |gpu - cpu| = %.2e, |cpu(float sums) - cpu(exact sums)| = %.2e, traces %d / %d iterations" %
+          (d_gpu, d_cpu, len(otr), len(wtr)))
+    assert d_gpu <= max(POSE_TOL, d_cpu), (d_gpu, d_cpu)
