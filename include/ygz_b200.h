@@ -209,6 +209,39 @@ int ygz_search_by_projection_kf(ygz_matcher* h, int check_orientation, ygz_frame
 int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_orientation, const ygz_frame_view* f1,
                                   const ygz_frame_view* f2, float* prev_matched_xy, int* matches12, int window);
 
+/* Batched, device-resident projection searches over the extractor's resident outputs (one CTA per pair; the sequential occupancy
+ * semantics of the reference loops are resolved exactly by ordered reservation rounds, csrc/projection_batch.cuh).  Assumption: every
+ * query map point has Observations() > 0 (a feature it takes blocks later queries); the per-call entry points above handle the
+ * general case. */
+typedef struct {
+    float fx, fy, cx, cy, mb, mbf;          /* Frame statics, include/Frame.h:231-236; mb / mbf of the current frame */
+    float min_x, min_y, max_x, max_y;       /* mnMinX .. mnMaxY */
+} ygz_projection_camera;
+/* ORBmatcher::SearchByProjection(Frame& Current, const Frame& Last, th, bMono, checkLevel), src/ORBmatcher.cc:1218-1350, for
+ * n_pairs (last, current) frame pairs of the extractor batch.  Per-frame host arrays, indexed by frame of the batch
+ * (B = ygz_orb_max_batch, cap = ygz_orb_max_keypoints): world_pos [B][cap][3] and valid [B][cap] = LastFrame.mvpMapPoints[i]'s
+ * GetWorldPos() and (non-null && !mvbOutlier[i]); pose [B][12] = mTcw of each frame (R row-major, t); mp_desc [B][cap][32] =
+ * pMP->GetDescriptor() (NULL: the last frame's own descriptor of the feature); u_right [B][cap] = mvuRight (NULL: monocular).
+ * CurrentFrame.mvpMapPoints must be empty on entry (TrackWithMotionModel fills it with NULL first, src/Tracking.cc:1079).
+ * out_matches [n_pairs][cap]: index of the LAST-frame feature whose map point current feature i received, -1 = none;
+ * out_nmatches [n_pairs] = the function's return value; out_rounds (optional) = resolution rounds per pair. */
+int ygz_search_by_projection_last_batch(ygz_matcher* h, ygz_orb* orb, const ygz_projection_camera* cam, int n_pairs, const int* last_frame,
+                                        const int* cur_frame, const float* world_pos, const uint8_t* valid, const float* pose,
+                                        const uint8_t* mp_desc, const float* u_right, float th, int mono, int check_level,
+                                        int check_orientation, int* out_matches, int* out_nmatches, int* out_rounds);
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>&, th, checkLevel), src/ORBmatcher.cc:43-126, for n_pairs frames:
+ * pair p searches frame frame[p] with its own list of M map points (arrays [n_pairs][M]: mTrackProjX / Y / XR, mTrackViewCos,
+ * mnTrackScaleLevel, usable = mbTrackInView && !isBad(), mp_desc [n_pairs][M][32]); occupied [n_pairs][cap] (optional) marks
+ * features that hold a map point with Observations() > 0 before the call.  out_matches [n_pairs][cap]: index into the pair's
+ * point list assigned to feature i, -1 = unchanged. */
+int ygz_search_by_projection_points_batch(ygz_matcher* h, ygz_orb* orb, const ygz_projection_camera* cam, int n_pairs, const int* frame,
+                                          int M, const float* proj_x, const float* proj_y, const float* proj_xr, const float* view_cos,
+                                          const int* level, const uint8_t* usable, const uint8_t* mp_desc, const uint8_t* occupied,
+                                          const float* u_right, float nnratio, float th, int check_level, int* out_matches,
+                                          int* out_nmatches, int* out_rounds);
+/* device-timed repeats of the last batched projection search (inputs resident) on the extractor's stream, for bench.py */
+int ygz_search_by_projection_batch_time(ygz_matcher* h, ygz_orb* orb, int iters, float* ms);
+
 /* Batched device-resident SearchByBoW over n independent (KF, F) pairs whose keypoints/descriptors are
  * extractor outputs already in HBM (stream front end, BASELINE C2): pair p matches frame kf_idx[p]
  * against frame f_idx[p] of the extractor batch; FeatureVectors are given per frame as node ids per

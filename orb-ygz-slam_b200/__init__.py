@@ -82,6 +82,10 @@ class Counters(C.Structure):
                                           "kernel_launches", "elapsed_ns")]
 
 
+class ProjectionCamera(C.Structure):      # ygz_projection_camera
+    _fields_ = [(k, C.c_float) for k in ("fx", "fy", "cx", "cy", "mb", "mbf", "min_x", "min_y", "max_x", "max_y")]
+
+
 # every symbol include/ygz_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
     "ygz_last_error", "ygz_device_count", "ygz_device_info",
@@ -98,6 +102,7 @@ ABI_SYMBOLS = [
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
     "ygz_stereo_batch", "ygz_stereo_batch_async", "ygz_stereo_frontend_time",
+    "ygz_search_by_projection_last_batch", "ygz_search_by_projection_points_batch", "ygz_search_by_projection_batch_time",
     "ygz_vocab_load", "ygz_vocab_from_memory", "ygz_vocab_destroy", "ygz_vocab_info", "ygz_vocab_transform", "ygz_vocab_transform_orb",
 ]
 
@@ -158,6 +163,11 @@ def lib():
     sigs.setdefault('ygz_search_for_initialization', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, i32p, C.c_int]
     sigs.setdefault('ygz_search_by_bow_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, u32p, i32p, i32p]
     sigs.setdefault('ygz_compute_stereo_matches', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p]
+    sigs.setdefault('ygz_search_by_projection_last_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.POINTER(ProjectionCamera), C.c_int, i32p, i32p, f32p, u8p, f32p, u8p, f32p,
+                                                                            C.c_float, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]
+    sigs.setdefault('ygz_search_by_projection_points_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.POINTER(ProjectionCamera), C.c_int, i32p, C.c_int, f32p, f32p, f32p, f32p,
+                                                                              i32p, u8p, u8p, u8p, f32p, C.c_float, C.c_float, C.c_int, i32p, i32p, i32p]
+    sigs.setdefault('ygz_search_by_projection_batch_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, f32p]
     sigs.setdefault('ygz_stereo_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p, i32p, i32p, i32p, i32p]
     sigs.setdefault('ygz_stereo_batch_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     sigs.setdefault('ygz_stereo_frontend_time', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, f32p, f32p]
@@ -608,6 +618,51 @@ class ORBmatcher:
         ms = C.c_float()
         _check(self.L.ygz_frontend_time(extractor.h, self.h, n_frames, iters, self.nnratio, int(self.checkOri),
                                         C.byref(ms)), "ygz_frontend_time")
+        return ms.value
+
+    def SearchByProjectionLastBatch(self, ex, last_frame, cur_frame, world_pos, valid, pose, K=(458.654, 457.296, 367.215, 248.375),
+                                    bounds=(0.0, 0.0, 752.0, 480.0), mb=0.0, mbf=0.0, mp_desc=None, u_right=None, th=15.0, mono=True,
+                                    check_level=True, check_ori=True):
+        """Batched device-resident SearchByProjection(Current, Last) (src/ORBmatcher.cc:1218-1350) over frame pairs of the extractor
+        batch.  world_pos [B, cap, 3], valid [B, cap], pose [B, 12].  Returns (nmatches[n], matches[n, cap], rounds[n])."""
+        lf = np.ascontiguousarray(last_frame, np.int32); cf = np.ascontiguousarray(cur_frame, np.int32)
+        n, cap = len(lf), ex.cap
+        cam = ProjectionCamera(*K, mb, mbf, *bounds)
+        wp = np.ascontiguousarray(world_pos, np.float32); va = np.ascontiguousarray(valid, np.uint8); po = np.ascontiguousarray(pose, np.float32)
+        md = None if mp_desc is None else np.ascontiguousarray(mp_desc, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        out = np.zeros((n, cap), np.int32); nm = np.zeros(n, np.int32); rd = np.zeros(n, np.int32)
+        _check(self.L.ygz_search_by_projection_last_batch(self.h, ex.h, C.byref(cam), n, _ptr(lf, i32p), _ptr(cf, i32p), _ptr(wp, f32p), _ptr(va, u8p),
+                                                          _ptr(po, f32p), _ptr(md, u8p), _ptr(ur, f32p), float(th), int(mono), int(check_level),
+                                                          int(check_ori), _ptr(out, i32p), _ptr(nm, i32p), _ptr(rd, i32p)),
+               "ygz_search_by_projection_last_batch")
+        return nm, out, rd
+
+    def SearchByProjectionPointsBatch(self, ex, frame, proj_x, proj_y, proj_xr, view_cos, level, usable, mp_desc, occupied=None, u_right=None,
+                                      K=(458.654, 457.296, 367.215, 248.375), bounds=(0.0, 0.0, 752.0, 480.0), mb=0.0, mbf=0.0, nnratio=0.8,
+                                      th=1.0, check_level=True):
+        """Batched device-resident SearchByProjection(F, vpMapPoints) (src/ORBmatcher.cc:43-126): arrays [n, M] per pair.
+        Returns (nmatches[n], matches[n, cap], rounds[n])."""
+        fr = np.ascontiguousarray(frame, np.int32)
+        n, cap = len(fr), ex.cap
+        px = np.ascontiguousarray(proj_x, np.float32); M = px.shape[1]
+        py = np.ascontiguousarray(proj_y, np.float32); pxr = np.ascontiguousarray(proj_xr, np.float32)
+        vc = np.ascontiguousarray(view_cos, np.float32); lv = np.ascontiguousarray(level, np.int32); us = np.ascontiguousarray(usable, np.uint8)
+        md = np.ascontiguousarray(mp_desc, np.uint8)
+        oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        cam = ProjectionCamera(*K, mb, mbf, *bounds)
+        out = np.zeros((n, cap), np.int32); nm = np.zeros(n, np.int32); rd = np.zeros(n, np.int32)
+        _check(self.L.ygz_search_by_projection_points_batch(self.h, ex.h, C.byref(cam), n, _ptr(fr, i32p), M, _ptr(px, f32p), _ptr(py, f32p),
+                                                            _ptr(pxr, f32p), _ptr(vc, f32p), _ptr(lv, i32p), _ptr(us, u8p), _ptr(md, u8p),
+                                                            _ptr(oc, u8p), _ptr(ur, f32p), float(nnratio), float(th), int(check_level),
+                                                            _ptr(out, i32p), _ptr(nm, i32p), _ptr(rd, i32p)),
+               "ygz_search_by_projection_points_batch")
+        return nm, out, rd
+
+    def time_projection_batch(self, ex, iters):
+        ms = C.c_float()
+        _check(self.L.ygz_search_by_projection_batch_time(self.h, ex.h, iters, C.byref(ms)), "ygz_search_by_projection_batch_time")
         return ms.value
 
     def time_bow_batch(self, extractor, n_pairs, iters):

@@ -314,6 +314,8 @@ inline float uright(const ygz_frame_view* f, int i) { return f->u_right ? f->u_r
 
 }  // namespace
 
+#include "projection_batch.cuh"
+
 struct ygz_matcher {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -331,6 +333,11 @@ struct ygz_matcher {
     int bow_pairs_cap = 0, bow_cap = 0, bow_frames = 0;
     BowBatchArgs last_args{};
     int last_pairs = 0;
+    // batched projection searches: device scratch slots (grown on demand) and the last launch (for the timing entry)
+    void* pj_buf[16] = {};
+    size_t pj_bytes[16] = {};
+    ProjArgs pj_last{};
+    int pj_last_pairs = 0, pj_last_mode = -1, pj_last_nq = 0;
 };
 
 static int matcher_free(ygz_matcher* h) {
@@ -339,6 +346,7 @@ static int matcher_free(ygz_matcher* h) {
     cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_pq); cudaFree(h->d_pt); cudaFree(h->d_dist);
     cudaFree(h->d_bi); cudaFree(h->d_bd); cudaFree(h->d_sd);
     cudaFree(h->d_kf_idx); cudaFree(h->d_f_idx); cudaFree(h->d_matches); cudaFree(h->d_nmatches); cudaFree(h->d_node);
+    for (void* b : h->pj_buf) cudaFree(b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1082,6 +1090,160 @@ int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matche
     YGZ_CUDA_TRY(cudaEventRecord(hA->ev1, sA));
     YGZ_CUDA_TRY(cudaEventSynchronize(hA->ev1));
     YGZ_CUDA_TRY(cudaEventElapsedTime(ms, hA->ev0, hA->ev1));
+    return YGZ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------- batched projection searches (host side)
+namespace {
+enum { PJ_QF, PJ_TF, PJ_WP, PJ_VALID, PJ_POSE, PJ_PX, PJ_PY, PJ_PXR, PJ_VC, PJ_LVL, PJ_USABLE, PJ_QDESC, PJ_OCC, PJ_UR, PJ_OUT, PJ_CNT };
+
+// device copy of a host array in scratch slot `slot` (NULL stays NULL)
+template <class T>
+int pj_upload(ygz_matcher* h, int slot, const T* host, size_t count, const T** dev) {
+    *dev = nullptr;
+    if (!host || count == 0) return YGZ_OK;
+    const size_t bytes = count * sizeof(T);
+    if (bytes > h->pj_bytes[slot]) {
+        cudaFree(h->pj_buf[slot]); h->pj_buf[slot] = nullptr; h->pj_bytes[slot] = 0;
+        YGZ_CUDA_TRY(cudaMalloc(&h->pj_buf[slot], bytes + bytes / 4));
+        h->pj_bytes[slot] = bytes + bytes / 4;
+    }
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->pj_buf[slot], host, bytes, cudaMemcpyHostToDevice, h->stream));
+    *dev = static_cast<const T*>(h->pj_buf[slot]);
+    return YGZ_OK;
+}
+int pj_alloc(ygz_matcher* h, int slot, size_t bytes, void** dev) {
+    if (bytes > h->pj_bytes[slot]) {
+        cudaFree(h->pj_buf[slot]); h->pj_buf[slot] = nullptr; h->pj_bytes[slot] = 0;
+        YGZ_CUDA_TRY(cudaMalloc(&h->pj_buf[slot], bytes));
+        h->pj_bytes[slot] = bytes;
+    }
+    *dev = h->pj_buf[slot];
+    return YGZ_OK;
+}
+
+int pj_common(ygz_matcher* h, ygz_orb* orb, const ygz_projection_camera* cam, int n_pairs, const int* q_frame, const int* t_frame,
+              const float* u_right, const uint8_t* occupied, ProjArgs* A) {
+    void *d_kps, *d_desc, *d_counts;
+    int cap = 0, rc;
+    if ((rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap))) return rc;
+    if (cap > PJ_MAX_CAP) { set_last_error("batched projection search supports up to 4096 key slots per frame"); return YGZ_ERR_CAPACITY; }
+    const int B = ygz_orb_max_batch(orb);
+    for (int i = 0; i < n_pairs; i++) YGZ_ARG_CHECK(q_frame[i] >= 0 && t_frame[i] >= 0 && t_frame[i] < B);
+    std::memset(A, 0, sizeof(*A));
+    A->kps = (const ygz_keypoint*)d_kps; A->desc = (const uint4*)d_desc; A->counts = (const int*)d_counts; A->cap = cap;
+    float scale[16], inv[16], s2[16], is2[16];
+    int fpl[16];
+    if ((rc = ygz_orb_tables(orb, scale, inv, s2, is2, fpl))) return rc;
+    for (int l = 0; l < 16; l++) A->scale[l] = scale[l];
+    A->fx = cam->fx; A->fy = cam->fy; A->cx = cam->cx; A->cy = cam->cy; A->mb = cam->mb; A->mbf = cam->mbf;
+    A->min_x = cam->min_x; A->min_y = cam->min_y; A->max_x = cam->max_x; A->max_y = cam->max_y;
+    YGZ_ARG_CHECK(cam->max_x > cam->min_x && cam->max_y > cam->min_y);
+    if ((rc = pj_upload(h, PJ_QF, q_frame, n_pairs, &A->q_frame)) || (rc = pj_upload(h, PJ_TF, t_frame, n_pairs, &A->t_frame))) return rc;
+    if ((rc = pj_upload(h, PJ_UR, u_right, (size_t)B * cap, &A->u_right))) return rc;
+    if ((rc = pj_upload(h, PJ_OCC, occupied, (size_t)n_pairs * cap, &A->occupied))) return rc;
+    void* out = nullptr;
+    if ((rc = pj_alloc(h, PJ_OUT, (size_t)n_pairs * cap * 4, &out))) return rc;
+    A->matches = (int*)out;
+    if ((rc = pj_alloc(h, PJ_CNT, (size_t)n_pairs * 8, &out))) return rc;
+    A->nmatches = (int*)out; A->rounds = (int*)out + n_pairs;
+    return YGZ_OK;
+}
+
+int pj_launch(ygz_matcher* h, const ProjArgs& A, int n_pairs, int mode, int nq, cudaStream_t st) {
+    const size_t smem = proj_smem_bytes(A.cap, nq);
+    if (smem > 220 * 1024) { set_last_error("batched projection search: shared-memory budget exceeded (too many key slots / query points)"); return YGZ_ERR_CAPACITY; }
+    NvtxRange nvtx_range(mode == 0 ? "ygz/SearchByProjection(Cur,Last) batch" : "ygz/SearchByProjection(F,points) batch");
+    if (mode == 0) {
+        YGZ_CUDA_TRY(cudaFuncSetAttribute(k_projection_batch<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_projection_batch<0><<<n_pairs, PJ_THREADS, smem, st>>>(A);
+    } else {
+        YGZ_CUDA_TRY(cudaFuncSetAttribute(k_projection_batch<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_projection_batch<1><<<n_pairs, PJ_THREADS, smem, st>>>(A);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    h->pj_last = A; h->pj_last_pairs = n_pairs; h->pj_last_mode = mode; h->pj_last_nq = nq;
+    return YGZ_OK;
+}
+
+int pj_finish(ygz_matcher* h, const ProjArgs& A, int n_pairs, int* out_matches, int* out_nmatches, int* out_rounds) {
+    if (out_matches) YGZ_CUDA_TRY(cudaMemcpyAsync(out_matches, A.matches, (size_t)n_pairs * A.cap * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_nmatches) YGZ_CUDA_TRY(cudaMemcpyAsync(out_nmatches, A.nmatches, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_rounds) YGZ_CUDA_TRY(cudaMemcpyAsync(out_rounds, A.rounds, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return YGZ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ygz_search_by_projection_last_batch(ygz_matcher* h, ygz_orb* orb, const ygz_projection_camera* cam, int n_pairs, const int* last_frame,
+                                        const int* cur_frame, const float* world_pos, const uint8_t* valid, const float* pose,
+                                        const uint8_t* mp_desc, const float* u_right, float th, int mono, int check_level, int check_orientation,
+                                        int* out_matches, int* out_nmatches, int* out_rounds) {
+    YGZ_ARG_CHECK(h && orb && cam && n_pairs >= 1 && last_frame && cur_frame && world_pos && valid && pose);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    ProjArgs A;
+    int rc;
+    YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));      // the extractor's stream produced the inputs
+    if ((rc = pj_common(h, orb, cam, n_pairs, last_frame, cur_frame, u_right, nullptr, &A))) return rc;
+    const int B = ygz_orb_max_batch(orb);
+    for (int i = 0; i < n_pairs; i++) YGZ_ARG_CHECK(last_frame[i] < B);
+    if ((rc = pj_upload(h, PJ_WP, world_pos, (size_t)B * A.cap * 3, &A.world_pos)) || (rc = pj_upload(h, PJ_VALID, valid, (size_t)B * A.cap, &A.valid)) ||
+        (rc = pj_upload(h, PJ_POSE, pose, (size_t)B * 12, &A.pose))) return rc;
+    const uint4* qd = nullptr;
+    if ((rc = pj_upload(h, PJ_QDESC, reinterpret_cast<const uint4*>(mp_desc), mp_desc ? (size_t)B * A.cap * 2 : 0, &qd))) return rc;
+    A.q_desc = qd;
+    A.th = th; A.mono = mono; A.check_level = check_level; A.check_ori = check_orientation;
+    if ((rc = pj_launch(h, A, n_pairs, 0, A.cap, h->stream))) return rc;
+    return pj_finish(h, A, n_pairs, out_matches, out_nmatches, out_rounds);
+}
+
+int ygz_search_by_projection_points_batch(ygz_matcher* h, ygz_orb* orb, const ygz_projection_camera* cam, int n_pairs, const int* frame,
+                                          int M, const float* proj_x, const float* proj_y, const float* proj_xr, const float* view_cos,
+                                          const int* level, const uint8_t* usable, const uint8_t* mp_desc, const uint8_t* occupied,
+                                          const float* u_right, float nnratio, float th, int check_level, int* out_matches,
+                                          int* out_nmatches, int* out_rounds) {
+    YGZ_ARG_CHECK(h && orb && cam && n_pairs >= 1 && frame && M >= 1 && proj_x && proj_y && proj_xr && view_cos && level && usable && mp_desc);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    ProjArgs A;
+    int rc;
+    YGZ_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)ygz_orb_stream(orb)));
+    if ((rc = pj_common(h, orb, cam, n_pairs, frame, frame, u_right, occupied, &A))) return rc;
+    const size_t n = (size_t)n_pairs * M;
+    for (size_t i = 0; i < n; i++) YGZ_ARG_CHECK(!usable[i] || (level[i] >= 0 && level[i] < 16));
+    A.M = M;
+    const uint4* qd = nullptr;
+    if ((rc = pj_upload(h, PJ_PX, proj_x, n, &A.proj_x)) || (rc = pj_upload(h, PJ_PY, proj_y, n, &A.proj_y)) ||
+        (rc = pj_upload(h, PJ_PXR, proj_xr, n, &A.proj_xr)) || (rc = pj_upload(h, PJ_VC, view_cos, n, &A.view_cos)) ||
+        (rc = pj_upload(h, PJ_LVL, level, n, &A.level)) || (rc = pj_upload(h, PJ_USABLE, usable, n, &A.usable)) ||
+        (rc = pj_upload(h, PJ_QDESC, reinterpret_cast<const uint4*>(mp_desc), n * 2, &qd))) return rc;
+    A.q_desc = qd;
+    A.th = th; A.nnratio = nnratio; A.check_level = check_level;
+    if ((rc = pj_launch(h, A, n_pairs, 1, M, h->stream))) return rc;
+    return pj_finish(h, A, n_pairs, out_matches, out_nmatches, out_rounds);
+}
+
+/* device-timed repeats of the last batched projection search (inputs resident) on the extractor's stream, for bench.py */
+int ygz_search_by_projection_batch_time(ygz_matcher* h, ygz_orb* orb, int iters, float* ms) {
+    YGZ_ARG_CHECK(h && orb && ms && iters >= 1 && h->pj_last_pairs >= 1);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    void *d_kps, *d_desc, *d_counts;
+    int cap = 0, rc;
+    if ((rc = ygz_orb_device_outputs(orb, &d_kps, &d_desc, &d_counts, &cap))) return rc;
+    if (cap != h->pj_last.cap) { set_last_error("the extractor's output capacity changed since the last batched projection search"); return YGZ_ERR_ARG; }
+    ProjArgs A = h->pj_last;
+    A.kps = (const ygz_keypoint*)d_kps; A.desc = (const uint4*)d_desc; A.counts = (const int*)d_counts;
+    cudaStream_t st = (cudaStream_t)ygz_orb_stream(orb);
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev0, st));
+    for (int i = 0; i < iters; i++)
+        if ((rc = pj_launch(h, A, h->pj_last_pairs, h->pj_last_mode, h->pj_last_nq, st))) return rc;
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev1, st));
+    YGZ_CUDA_TRY(cudaEventSynchronize(h->ev1));
+    YGZ_CUDA_TRY(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return YGZ_OK;
 }
 
