@@ -334,9 +334,51 @@ def aux_metrics(m, device):
         it = 20
         ms = sia.time(P, it) / it
         aux["sia_c3"] = {"problems_per_launch": P, "patches": 200, "levels": "3..1", "gn_iters_per_level": 10,
-                         "ms_per_launch": ms, "alignments_per_s": P / (ms / 1e3)}
+                         "ms_per_launch": ms, "alignments_per_s": P / (ms / 1e3),
+                         "see_also": "bench.py --workload c3 (first-class C3 line with the CPU arm and the pose gate)"}
     except Exception as e:        # aux numbers never break the headline line
         aux["sia_c3"] = {"error": str(e)[:200]}
+    try:
+        # C2+ : what Tracking::TrackWithMotionModel adds per frame — SearchByProjection(Current, Last) (src/ORBmatcher.cc:1218-1350) for every
+        # consecutive frame pair of a batch, on the extractor's resident outputs (k_projection_batch), with the oracle's time beside it
+        import time as _t
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        Bp = 256
+        exp = m.ORBextractor(width=W, height=H, max_batch=Bp, device=device, **ORB)
+        res = exp.extract_batch(make_frames(1000, Bp))
+        cap = exp.cap
+        K4 = (458.654, 457.296, 367.215, 248.375)
+        rng = np.random.default_rng(3)
+        wp = np.zeros((Bp, cap, 3), np.float32); valid = np.zeros((Bp, cap), np.uint8)
+        for f, (k, d) in enumerate(res):
+            n = len(k); z = rng.uniform(2, 10, n)
+            wp[f, :n] = np.stack([(k["x"] - K4[2]) * z / K4[0], (k["y"] - K4[3]) * z / K4[1], z], -1)
+            valid[f, :n] = 1
+        pose = np.tile(np.concatenate([np.eye(3, dtype=np.float32).reshape(-1), np.zeros(3, np.float32)]), (Bp, 1)).astype(np.float32)
+        last = np.array([(i - 1) % Bp for i in range(Bp)], np.int32); cur = np.arange(Bp, dtype=np.int32)
+        mtp = m.ORBmatcher(0.9, True, device=device)
+        nm, out, rounds = mtp.SearchByProjectionLastBatch(exp, last, cur, wp, valid, pose, K=K4, th=15.0, mono=True)
+        ms = mtp.time_projection_batch(exp, 10) / 10
+        # oracle, one thread, a few pairs (and the parity gate on them)
+        sc = (np.float32(1.2) ** 0 * np.cumprod(np.concatenate([[1.0], np.full(7, 1.2)]))).astype(np.float32)
+        t0 = _t.perf_counter(); npairs = 0; same = True
+        for p_ in range(1, 9):
+            (ka, da), (kb, db) = res[last[p_]], res[cur[p_]]
+            cv = m.make_frame_view(kb, db, K=K4, scale_factors=sc, cls=O.FrameView)
+            lv = m.make_frame_view(ka, da, map_point=np.arange(len(ka), dtype=np.int32), K=K4, scale_factors=sc, cls=O.FrameView)
+            mp = m.make_map_points(wp[last[p_]][:len(ka)], da, cls=O.MapPoints)
+            on = O.lib().orc_search_by_projection_last(1, cv.ptr(), lv.ptr(), mp.ptr(), 15.0, 1, 1)
+            same = same and on == nm[p_] and bool((cv.map_point == out[p_, :len(kb)]).all())
+            npairs += 1
+        cpu_ms = (_t.perf_counter() - t0) / npairs * 1e3
+        aux["projection_last_batch_c2plus"] = {"pairs_per_launch": Bp, "ms_per_launch": ms, "frame_pairs_per_s": Bp / (ms / 1e3),
+                                               "matches_per_pair": float(nm.mean()), "reservation_rounds_max": int(rounds.max()),
+                                               "cpu_baseline": {"ms_per_pair_1_thread": cpu_ms, "frame_pairs_per_s_1_thread": 1e3 / cpu_ms,
+                                                                "kind": "port (includes the Python marshalling of the views)"},
+                                               "parity_gate_8_pairs_identical": same}
+    except Exception as e:
+        aux["projection_last_batch_c2plus"] = {"error": str(e)[:200]}
     try:
         q, t, _ = synth.synth_descriptors(5, 2000, 2000)
         mt = m.ORBmatcher(0.7, True, device=device)
@@ -346,7 +388,15 @@ def aux_metrics(m, device):
         for _ in range(20):
             mt.bf_top2(q, t)
         dt = (_t.perf_counter() - t0) / 20
-        aux["bf_top2_c5"] = {"nq": 2000, "nt": 2000, "ms_per_call_host_buffers": dt * 1e3, "comparisons_per_s": 4e6 / dt}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O2
+        t0 = _t.perf_counter()
+        for _ in range(3):
+            O2.bf_top2(q, t)
+        cdt = (_t.perf_counter() - t0) / 3
+        aux["bf_top2_c5"] = {"nq": 2000, "nt": 2000, "ms_per_call_host_buffers": dt * 1e3, "comparisons_per_s": 4e6 / dt,
+                             "cpu_baseline": {"ms_per_call_1_thread": cdt * 1e3, "comparisons_per_s_1_thread": 4e6 / cdt, "kind": "port"},
+                             "see_also": "bench.py --workload c5 (first-class C5 line)"}
     except Exception as e:
         aux["bf_top2_c5"] = {"error": str(e)[:200]}
     try:

@@ -1,14 +1,11 @@
 // ygz::ORBextractor — header-only host mirror of the reference class (include/ORBextractor.h:45-172) over the C ABI
-// of libygz_b200.so.  Same constructor arguments, getters, public mvImagePyramid and operator() overloads; the
-// OpenCV-typed signatures Tracking.cc/Frame.cc use are provided when YGZ_WITH_OPENCV is defined.
+// of libygz_b200.so.  Same constructor arguments, getters, public mvImagePyramid and operator() overloads over flat views; the
+// OpenCV / Frame* typed signatures Tracking.cc / Frame.cc use are in ygz/adapters.h.
 #pragma once
 #include <cstdint>
 #include <cstdio>
 #include <vector>
 #include "../ygz_b200.h"
-#ifdef YGZ_WITH_OPENCV
-#include <opencv2/core/core.hpp>
-#endif
 
 // The classes live in namespace ygz (the reference's) unless ygz/adapters.h moved them to ygz::flat to free the reference's
 // class names for the literal-signature adapters.
@@ -165,20 +162,6 @@ protected:
     ygz_orb* h_ = nullptr;
     bool pyramid_stale_ = false;
 
-#ifdef YGZ_WITH_OPENCV
-public:   // literal reference signatures (include/ORBextractor.h:69-73)
-    void operator()(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints, cv::OutputArray descriptors) {
-        cv::Mat im = image.getMat();
-        std::vector<KeyPoint> k;
-        std::vector<uint8_t> d;
-        (*this)(ImageView(im.data, im.cols, im.rows, (int)im.step), ImageView(), k, d);
-        static_assert(sizeof(cv::KeyPoint) == sizeof(KeyPoint), "cv::KeyPoint layout");
-        keypoints.resize(k.size());
-        if (!k.empty()) std::memcpy((void*)keypoints.data(), k.data(), k.size() * sizeof(KeyPoint));
-        if (k.empty()) descriptors.release();
-        else { descriptors.create((int)k.size(), 32, CV_8U); std::memcpy(descriptors.getMat().data, d.data(), d.size()); }
-    }
-#endif
 };
 
 YGZ_MIRROR_END  // namespace
