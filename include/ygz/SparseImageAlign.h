@@ -40,6 +40,9 @@ public:
         if (!h_ || problem.n <= 0) return 0;                           // "no features to track" (:24-27)
         SE3fPOD out;
         int n = 0;
+        // run() upstream overwrites n_iter_ with its own per-level table {10, 10, ...} (src/SparseImageAlign.cc:40-45): the constructor's
+        // n_iter never takes effect (checked against the compiled reference, tests/test_ref_sia.py); the C ABI keeps it explicit
+        n_iter_ = 10;
         int rc = ygz_sia_run(h_, &problem, 1, max_level_, min_level_, n_iter_, eps_, out.q, out.t, H_, &n);
         if (rc != YGZ_OK) { std::fprintf(stderr, "ygz::SparseImgAlign::run: %d %s\n", rc, ygz_last_error()); return 0; }
         TCR = out;

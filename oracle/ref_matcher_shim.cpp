@@ -28,9 +28,10 @@
 #include <ygz/adapters.h>
 #define REFM(name) adp_##name
 #else
+#include <opencv2/core/core.hpp>  // (and the standard headers it pulls) before the access macros below
+#include "Common.h"
 #define protected public          // ComputeThreeMaxima, RadiusByViewingCos and CheckDistEpipolarLine are protected upstream
 #define private public
-#include <opencv2/core/core.hpp>
 #include "ORBmatcher.h"
 #undef protected
 #undef private

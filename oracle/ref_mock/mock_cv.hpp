@@ -132,6 +132,7 @@ public:
     Mat() : flags(0), dims(0), rows(0), cols(0), data(nullptr) {}
     Mat(int r, int c, int t) : Mat() { create(r, c, t); }
     Mat(Size s, int t) : Mat() { create(s.height, s.width, t); }
+    Mat(Size s, int t, const Scalar& v) : Mat() { create(s.height, s.width, t); setTo(v); }      // byte fill: only called with Scalar(0)
     Mat(int r, int c, int t, void* d, size_t st = 0) : flags(t), dims(2), rows(r), cols(c), data((uchar*)d) {
         step.buf[1] = mock_elem_size(t);
         step.buf[0] = st ? st : (size_t)c * step.buf[1];
@@ -373,5 +374,11 @@ struct FileStorage {
     FileNode operator[](const std::string&) const { return FileNode(); }
 };
 template <class T> static inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
+
+// highgui: the display branch of SparseImgAlign (display_ == false on this path)
+#define CV_WINDOW_AUTOSIZE 1
+static inline void namedWindow(const std::string&, int = 1) {}
+static inline void imshow(const std::string&, const Mat&) {}
+static inline int waitKey(int = 0) { return -1; }
 
 }  // namespace cv

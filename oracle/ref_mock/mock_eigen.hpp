@@ -8,10 +8,23 @@
 #pragma once
 #include <cmath>
 #include <cstddef>
+#include <algorithm>
 #include <initializer_list>
+#include <ostream>
 #include <vector>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+// Third-party arithmetic the aligner needs and this image does not have (Eigen's LDLT, Sophus' quaternion SE3): forwarded to the
+// oracle's restatements of the published algorithms (oracle/sparse_align.cpp), exactly as the image primitives forward to cvprims.cpp.
+extern "C" {
+void orc_ldlt_solve6(const float* A_rowmajor36, const float* b6, float* x6);
+void orc_se3_exp(const float* x6, float* q, float* t);
+void orc_se3_mul(const float* qa, const float* ta, const float* qb, const float* tb, float* q, float* t);
+void orc_se3_inv(const float* q, const float* t, float* qo, float* to);
+void orc_se3_apply(const float* q, const float* t, const float* p3, float* o3);
+void orc_quat_to_matrix(const float* q, float* R9);
+}
 
 namespace Eigen {
 
@@ -89,6 +102,20 @@ template <class T, int R, int C, int Opt = 0> struct Matrix {
             }
         return m;
     }
+    // ---- the pieces src/SparseImageAlign.cc / include/NLSSolver_impl.hpp use
+    Matrix& noalias() { return *this; }
+    struct LDLTProxy {
+        const Matrix& m;
+        Matrix<T, R, 1> solve(const Matrix<T, R, 1>& b) const {
+            static_assert(R == 6 && C == 6, "ldlt().solve: 6x6 only");
+            Matrix<T, R, 1> x;
+            orc_ldlt_solve6(m.d, b.d, x.d);                     // Eigen LDLT<Matrix6f, Lower>: pivoted, pseudo-inverse of D
+            return x;
+        }
+    };
+    LDLTProxy ldlt() const { return LDLTProxy{*this}; }
+    Matrix<T, R, 1> diagonal() const { Matrix<T, R, 1> v; for (int i = 0; i < R; i++) v.d[i] = (*this)(i, i); return v; }
+    Matrix<T, R * C, R * C> asDiagonal() const { Matrix<T, R * C, R * C> m; for (int i = 0; i < R * C; i++) m(i, i) = d[i]; return m; }
     Matrix& operator+=(const Matrix& o) { for (int i = 0; i < R * C; i++) d[i] += o.d[i]; return *this; }
     Matrix& operator-=(const Matrix& o) { for (int i = 0; i < R * C; i++) d[i] -= o.d[i]; return *this; }
     Matrix& operator*=(T s) { for (int i = 0; i < R * C; i++) d[i] *= s; return *this; }
@@ -112,6 +139,36 @@ template <class T, int R, int C, class S> Matrix<T, R, C> operator*(const Matrix
 template <class T, int R, int C, class S> Matrix<T, R, C> operator*(S s, const Matrix<T, R, C>& a) { Matrix<T, R, C> m; for (int i = 0; i < R * C; i++) m.d[i] = (T)s * a.d[i]; return m; }
 template <class T, int R, int C, class S> Matrix<T, R, C> operator/(const Matrix<T, R, C>& a, S s) { Matrix<T, R, C> m; for (int i = 0; i < R * C; i++) m.d[i] = a.d[i] / (T)s; return m; }
 
+// R x Dynamic (jacobian_cache_ of SparseImgAlign: Matrix<float, 6, Dynamic, ColMajor>)
+template <class T, int R, int Opt> struct Matrix<T, R, Dynamic, Opt> {
+    std::vector<T> d;            // column major
+    int c = 0;
+    void resize(int, int cols_) { c = cols_; d.assign((size_t)R * cols_, T(0)); }
+    void setZero() { std::fill(d.begin(), d.end(), T(0)); }
+    int rows() const { return R; }
+    int cols() const { return c; }
+    struct ColRef {
+        Matrix& m; int j;
+        ColRef& operator=(const Matrix<T, R, 1>& v) { for (int i = 0; i < R; i++) m.d[(size_t)j * R + i] = v.d[i]; return *this; }
+        ColRef& operator=(const Matrix<T, 1, R>& v) { for (int i = 0; i < R; i++) m.d[(size_t)j * R + i] = v.d[i]; return *this; }   // row assigned to a column
+        operator Matrix<T, R, 1>() const { Matrix<T, R, 1> v; for (int i = 0; i < R; i++) v.d[i] = m.d[(size_t)j * R + i]; return v; }
+    };
+    ColRef col(int j) { return ColRef{*this, j}; }
+};
+
+struct VectorXf {
+    std::vector<float> v;
+    VectorXf() {}
+    template <int N> VectorXf(const Matrix<float, N, 1>& m) : v(m.d, m.d + N) {}
+    int size() const { return (int)v.size(); }
+    float operator[](int i) const { return v[i]; }
+};
+
+template <class T, int R, int C> std::ostream& operator<<(std::ostream& os, const Matrix<T, R, C>& m) {
+    for (int i = 0; i < R; i++) { for (int j = 0; j < C; j++) os << m(i, j) << (j + 1 < C ? " " : ""); if (i + 1 < R) os << "\n"; }
+    return os;
+}
+
 typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<float, 4, 1> Vector4f;
@@ -125,6 +182,8 @@ typedef Matrix<float, 4, 4> Matrix4f;
 typedef Matrix<double, 2, 2> Matrix2d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<float, 6, 1> Vector6f;       // Thirdparty/sophus/sophus/se3.hpp:40 puts these into namespace Eigen
+typedef Matrix<double, 6, 1> Vector6d;
 
 template <class T> struct Quaternion {
     T w_, x_, y_, z_;
@@ -154,6 +213,7 @@ template <class T> struct SO3 {
     SO3 operator*(const SO3& o) const { return SO3(R * o.R); }
     Eigen::Matrix<T, 3, 1> operator*(const Eigen::Matrix<T, 3, 1>& p) const { return R * p; }
 };
+#ifndef MOCK_SE3_QUATERNION
 template <class T> struct SE3 {
     Eigen::Matrix<T, 3, 3> R;
     Eigen::Matrix<T, 3, 1> t;
@@ -169,6 +229,22 @@ template <class T> struct SE3 {
     SE3 operator*(const SE3& o) const { return SE3(R * o.R, t + R * o.t); }
     Eigen::Matrix<T, 3, 1> operator*(const Eigen::Matrix<T, 3, 1>& p) const { return R * p + t; }
 };
+#else
+// Quaternion form for the aligner (oracle/Makefile: -DMOCK_SE3_QUATERNION): unit quaternion (x, y, z, w) + translation with the
+// arithmetic of Sophus' SE3Group / SO3Group (compose + renormalise, rotate by Eigen's _transformVector, exp with the small-angle
+// branch), forwarded to the oracle's restatement of Thirdparty/sophus/sophus/{se3,so3}.hpp.
+template <class T> struct SE3 {
+    float q[4], t[3];
+    SE3() { q[0] = q[1] = q[2] = 0.f; q[3] = 1.f; t[0] = t[1] = t[2] = 0.f; }
+    static SE3 fromQT(const float* qq, const float* tt) { SE3 r; for (int i = 0; i < 4; i++) r.q[i] = qq[i]; for (int i = 0; i < 3; i++) r.t[i] = tt[i]; return r; }
+    static SE3 exp(const Eigen::Matrix<T, 6, 1>& a) { SE3 r; orc_se3_exp(a.d, r.q, r.t); return r; }
+    SE3 inverse() const { SE3 r; orc_se3_inv(q, t, r.q, r.t); return r; }
+    SE3 operator*(const SE3& o) const { SE3 r; orc_se3_mul(q, t, o.q, o.t, r.q, r.t); return r; }
+    Eigen::Matrix<T, 3, 1> operator*(const Eigen::Matrix<T, 3, 1>& p) const { Eigen::Matrix<T, 3, 1> o; orc_se3_apply(q, t, p.d, o.d); return o; }
+    Eigen::Matrix<T, 3, 3> rotationMatrix() const { Eigen::Matrix<T, 3, 3> R; orc_quat_to_matrix(q, R.d); return R; }
+    Eigen::Matrix<T, 3, 1> translation() const { return Eigen::Matrix<T, 3, 1>(t[0], t[1], t[2]); }
+};
+#endif
 typedef SO3<float> SO3f;
 typedef SE3<float> SE3f;
 typedef SO3<double> SO3d;

@@ -6,8 +6,13 @@
 // _ref/libvocab_ref.so).  Entry points mirror the oracle's orc_vocab_* (ygz_oracle.h) so tests/test_ref_vocab.py runs
 // loadFromBinaryFile (:1478-1522) and transform (:1151-1292) of both on the same files and descriptors: word ids, weights,
 // FeatureVector node ids, the normalised BowVector.
+#include <opencv2/core/core.hpp>  // (and the standard headers it pulls) before the access macro below
+#include <algorithm>
+#include <cassert>
+#include <fstream>
+#include <limits>
+#include <numeric>
 #define protected public          // transform(feature, id, weight, nid, levelsup) and m_nodes are protected upstream
-#include <opencv2/core/core.hpp>
 #include "Thirdparty/DBoW2/DBoW2/FORB.h"
 #include "Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h"
 #undef protected

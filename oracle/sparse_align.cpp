@@ -358,6 +358,15 @@ void orc_se3_inv(const float* q, const float* t, float* qo, float* to) {
     std::memcpy(qo, r.q, 16); std::memcpy(to, r.t, 12);
 }
 
+/* the third-party arithmetic, exposed for oracle/ref_mock (the reference's src/SparseImageAlign.cc compiled against the stand-in
+ * Eigen / Sophus forwards its ldlt().solve / SE3 operations here: see ref_mock/mock_eigen.hpp) */
+void orc_ldlt_solve6(const float* A, const float* b, float* x) { ldlt_solve6(A, b, x); }
+void orc_se3_apply(const float* q, const float* t, const float* p, float* o) {
+    SE3 T; std::memcpy(T.q, q, 16); std::memcpy(T.t, t, 12);
+    se3_apply(T, p, o);
+}
+void orc_quat_to_matrix(const float* q, float* R) { quat_to_matrix(q, R); }
+
 /* test switch: 1 = H / Jres / chi2 summed in double (see computeResiduals); per calling thread */
 void orc_sia_wide_sums(int on) { g_wide_sums = on != 0; }
 

@@ -199,6 +199,9 @@ long orc_frontend_batch_voc(int nfeatures, float scaleFactor, int nlevels, int i
 void orc_se3_exp(const float* x6, float* q, float* t);
 void orc_se3_mul(const float* qa, const float* ta, const float* qb, const float* tb, float* q, float* t);
 void orc_se3_inv(const float* q, const float* t, float* qo, float* to);
+void orc_se3_apply(const float* q, const float* t, const float* p3, float* o3);
+void orc_quat_to_matrix(const float* q, float* R9);
+void orc_ldlt_solve6(const float* A_rowmajor36, const float* b6, float* x6);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,7 @@ struct ygz_orb {
     int n_blur_tiles = 0;
     size_t fast_smem = 0, oct_smem = 0;
     int fast_warp_smem = 0;
-    int oct_node_smem = 0, oct_key_cache = 0;
+    int oct_node_smem = 0, oct_key_cache = 0, oct_unroll = 4;     // measured (C1, B=256): 4 keys in flight 0.275 ms, 8 keys 0.296 ms (spills), one 0.300 ms
     int launches_per_run = 0;
     ygz_counters ctr = {};
     // DSO key-point selection (ygz_orb_extract_frame_dso): occupancy map, per-cell winners, compacted list, mnGridSize
@@ -303,6 +303,7 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         (void)kc;
         h->oct_key_cache = 0;     // measured on B200 (C1, B=256): 0 keys 0.304 ms, 4608 keys 0.312 ms, 9216 keys 0.338 ms — occupancy beats the cache
         if (const char* e = getenv("YGZ_OCT_KEY_CACHE")) h->oct_key_cache = std::max(0, atoi(e));   // tuning knob
+        if (const char* e = getenv("YGZ_OCT_UNROLL")) h->oct_unroll = atoi(e) == 8 ? 8 : 4;           // tuning knob
     }
     oct_smem = (size_t)h->oct_node_smem + (size_t)h->oct_key_cache * 6 + 16;
     h->oct_smem = oct_smem;
@@ -431,7 +432,8 @@ int ygz_orb_create(const ygz_orb_config* cfg, ygz_orb** out) {
         TRY_OR_FREE(cudaMemcpy(h->d_pattern, fp.data(), fp.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     TRY_OR_FREE(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fast_smem, 1024)));
-    TRY_OR_FREE(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_octree<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
+    TRY_OR_FREE(cudaFuncSetAttribute(k_octree<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(oct_smem, 1024)));
     TRY_OR_FREE(cudaDeviceSynchronize());
 #undef TRY_OR_FREE
     *out = h;
@@ -551,8 +553,12 @@ static int launch_detect(ygz_orb* h, int n) {
 static int launch_octree(ygz_orb* h, int n) {
     NvtxRange nvtx_range("ygz/DistributeOctTree");
     dim3 grid(n, h->cfg.nlevels);
-    k_octree<<<grid, OCT_THREADS, h->oct_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->d_keys,
-                                                            h->d_keynode, h->d_nkeys, h->d_sel, h->d_nsel, h->oct_node_smem, h->oct_key_cache);
+    if (h->oct_unroll == 4)
+        k_octree<4><<<grid, OCT_THREADS, h->oct_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->d_keys,
+                                                                   h->d_keynode, h->d_nkeys, h->d_sel, h->d_nsel, h->oct_node_smem, h->oct_key_cache);
+    else
+        k_octree<8><<<grid, OCT_THREADS, h->oct_smem, h->stream>>>(h->P, h->d_cells, h->d_pool, h->d_cell_count, h->d_keys,
+                                                                   h->d_keynode, h->d_nkeys, h->d_sel, h->d_nsel, h->oct_node_smem, h->oct_key_cache);
     YGZ_CUDA_TRY(cudaGetLastError());
     return YGZ_OK;
 }

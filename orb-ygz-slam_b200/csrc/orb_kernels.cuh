@@ -434,7 +434,8 @@ __device__ __forceinline__ int quadrant_of(int x, int y, int x0, int x1, int y0,
     return (x < hx ? 0 : 1) + (y < hy ? 0 : 2);    // n1 UL, n2 UR, n3 BL, n4 BR (:511-519)
 }
 
-__global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellDesc* __restrict__ cells,
+template <int OCT_U>       // keys per thread in flight in the vote / relabel loops
+__global__ void __launch_bounds__(OCT_THREADS, 4) k_octree(OrbParams P, const CellDesc* __restrict__ cells,
                                                         const uint32_t* __restrict__ pool,
                                                         const uint16_t* __restrict__ cell_count,
                                                         uint32_t* __restrict__ keys_all, uint16_t* __restrict__ keynode_all,
@@ -561,13 +562,22 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
         for (int i = tid; i < Lsz; i += OCT_THREADS) S.processed[i] = 0;
         __syncthreads();
         // P2: keys of expandable nodes vote for their quadrant
-#pragma unroll 4
-        for (int k = tid; k < n; k += OCT_THREADS) {
-            const int nid = keynode[k];
-            if (CNT[nid] > 1) {
-                const uint32_t c = keys[k];
-                const int q = quadrant_of(cand_x(c), cand_y(c), X0[nid], X1[nid], Y0[nid], Y1[nid]);
-                atomicAdd(&S.qcnt[nid * 4 + q], 1);
+        // (node label and packed key are fetched together, OCT_U keys per thread in flight: the loop is bound by the latency of these
+        //  two global loads, and fetching the key only after the label's node test doubled the dependent chain)
+        for (int k0 = tid; k0 < n; k0 += OCT_THREADS * OCT_U) {
+            int nid[OCT_U]; uint32_t c[OCT_U];
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * OCT_THREADS;
+                if (k < n) { nid[u] = keynode[k]; c[u] = keys[k]; }
+            }
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * OCT_THREADS;
+                if (k < n && CNT[nid[u]] > 1) {
+                    const int q = quadrant_of(cand_x(c[u]), cand_y(c[u]), X0[nid[u]], X1[nid[u]], Y0[nid[u]], Y1[nid[u]]);
+                    atomicAdd(&S.qcnt[nid[u] * 4 + q], 1);
+                }
             }
         }
         __syncthreads();
@@ -663,15 +673,24 @@ __global__ void __launch_bounds__(OCT_THREADS) k_octree(OrbParams P, const CellD
         }
         __syncthreads();
         // P6: relabel keys
-#pragma unroll 4
-        for (int k = tid; k < n; k += OCT_THREADS) {
-            const int nid = keynode[k];
-            if (S.processed[nid]) {
-                const uint32_t c = keys[k];
-                const int q = quadrant_of(cand_x(c), cand_y(c), X0[nid], X1[nid], Y0[nid], Y1[nid]);
-                keynode[k] = (uint16_t)S.childpos[nid * 4 + q];
-            } else {
-                keynode[k] = (uint16_t)S.newpos[nid];
+        for (int k0 = tid; k0 < n; k0 += OCT_THREADS * OCT_U) {
+            int nid[OCT_U]; uint32_t c[OCT_U];
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * OCT_THREADS;
+                if (k < n) { nid[u] = keynode[k]; c[u] = keys[k]; }
+            }
+#pragma unroll
+            for (int u = 0; u < OCT_U; u++) {
+                const int k = k0 + u * OCT_THREADS;
+                if (k < n) {
+                    if (S.processed[nid[u]]) {
+                        const int q = quadrant_of(cand_x(c[u]), cand_y(c[u]), X0[nid[u]], X1[nid[u]], Y0[nid[u]], Y1[nid[u]]);
+                        keynode[k] = (uint16_t)S.childpos[nid[u] * 4 + q];
+                    } else {
+                        keynode[k] = (uint16_t)S.newpos[nid[u]];
+                    }
+                }
             }
         }
         const int nToExpand = s_misc[2];

@@ -232,3 +232,17 @@ def adapters_lib():
                                     C.c_void_p, u8p, C.c_int, C.c_int, u8p]
     L.adp_sia_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p]
     return L
+
+
+def sia_run(problem, max_level, min_level, n_iter=10):
+    """The reference's ygz::SparseImgAlign::run (oracle/_ref/libsia_ref.so: src/SparseImageAlign.cc + NLSSolver_impl.hpp compiled
+    unmodified; oracle/ref_sia_shim.cpp).  problem: _Keep(SiaProblem) built with cls=oracle_lib.SiaProblem.
+    Returns (n_tracked, q, t, H[6, 6], chi2) or None when the library is not built."""
+    L = _load("libsia_ref.so")
+    if L is None:
+        return None
+    L.refs_sia_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.POINTER(C.c_float)]
+    q = np.zeros(4, np.float32); t = np.zeros(3, np.float32); H = np.zeros(36, np.float32)
+    chi2 = C.c_float()
+    n = L.refs_sia_run(C.cast(problem.ptr(), C.c_void_p), max_level, min_level, n_iter, _ptr(q, f32p), _ptr(t, f32p), _ptr(H, f32p), C.byref(chi2))
+    return n, q, t, H.reshape(6, 6), chi2.value
