@@ -18,6 +18,7 @@ namespace ygz {
 
     class MapPoint;
     class KeyFrame;
+    class ORBextractor;
 
     class Frame {
     public:
@@ -79,12 +80,20 @@ namespace ygz {
             return vIndices;
         }
 
+        // src/Frame.cc:509-682.  Not restated: oracle/Makefile (_ref/libstereo_ref.so) compiles the reference's own text of this function
+        // (cut out of src/Frame.cc at build time into a deleted-after-use intermediate, never into the repo) as this member.
+        void ComputeStereoMatches();
+
         static float fx, fy, cx, cy;                 // include/Frame.h:231-234
         float mbf = 0;                               // :243
         float mb = 0;                                // :246
         int N = 0;                                   // :253 (uninitialised upstream)
         std::vector<cv::KeyPoint> mvKeys;            // :259
+        std::vector<cv::KeyPoint> mvKeysRight;       // :260
         std::vector<float> mvuRight;                 // :263
+        std::vector<float> mvDepth;                  // :264
+        cv::Mat mDescriptorsRight;                   // :271
+        ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;   // :225
         DBoW2::FeatureVector mFeatVec;               // :268
         cv::Mat mDescriptors;                        // :271
         std::vector<MapPoint *> mvpMapPoints;        // :274

@@ -164,6 +164,21 @@ public:
     void release() { holder.reset(); data = nullptr; rows = cols = 0; dims = 0; }
 
     static MatZeros zeros(int r, int c, int t) { return MatZeros{r, c, t}; }
+    // Mat::ones / convertTo(CV_32F): the 11x11 float patches of Frame::ComputeStereoMatches (src/Frame.cc:604-627)
+    static Mat ones(int r, int c, int t) {
+        Mat m(r, c, t);
+        for (int y = 0; y < r; y++) for (int x = 0; x < c; x++) { if ((t & 7) == CV_32F) m.at<float>(y, x) = 1.f; else m.data[(size_t)y * m.step.buf[0] + x] = 1; }
+        return m;
+    }
+    void convertTo(Mat& dst, int rtype) const {             // 8U -> 32F (or a copy); dst may alias *this (a ROI header)
+        Mat out(rows, cols, rtype);
+        for (int y = 0; y < rows; y++)
+            for (int x = 0; x < cols; x++) {
+                const double v = depth() == CV_32F ? (double)at<float>(y, x) : (double)data[(size_t)y * step.buf[0] + x];
+                if ((rtype & 7) == CV_32F) out.at<float>(y, x) = (float)v; else out.data[(size_t)y * out.step.buf[0] + x] = (uchar)v;
+            }
+        dst = out;
+    }
     static MatZeros zeros(Size s, int t) { return MatZeros{s.height, s.width, t}; }
 
     Mat clone() const {
@@ -247,6 +262,13 @@ static inline Mat operator*(const Mat& a, double s) { return mock_scale(a, s); }
 static inline Mat operator*(double s, const Mat& a) { return mock_scale(a, s); }
 static inline Mat operator/(const Mat& a, double s) { return mock_scale(a, 1.0 / s); }
 static inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
+static inline double norm(const Mat& a, const Mat& b, int type) {      // CV_32F, NORM_L1: sum |a - b| accumulated in double (OpenCV's normDiffL1_32f)
+    assert(type == NORM_L1);
+    double s = 0;
+    for (int y = 0; y < a.rows; y++) for (int x = 0; x < a.cols; x++) s += std::fabs((double)(a.at<float>(y, x) - b.at<float>(y, x)));
+    return s;
+}
 
 template <class T> class Mat_ : public Mat {
 public:

@@ -246,3 +246,21 @@ def sia_run(problem, max_level, min_level, n_iter=10):
     chi2 = C.c_float()
     n = L.refs_sia_run(C.cast(problem.ptr(), C.c_void_p), max_level, min_level, n_iter, _ptr(q, f32p), _ptr(t, f32p), _ptr(H, f32p), C.byref(chi2))
     return n, q, t, H.reshape(6, 6), chi2.value
+
+
+def compute_stereo_matches(pyrL, pyrR, keysL, descL, keysR, descR, scale, inv_scale, mb, mbf):
+    """The reference's own Frame::ComputeStereoMatches (oracle/_ref/libstereo_ref.so, oracle/ref_stereo_shim.cpp); arguments and
+    returns as oracle_lib.compute_stereo_matches.  None when the library is not built."""
+    L = _load("libstereo_ref.so")
+    if L is None:
+        return None
+    L.refst_compute_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                               f32p, f32p, C.c_float, C.c_float, f32p, f32p]
+    keysL = np.ascontiguousarray(keysL, KP_DTYPE); keysR = np.ascontiguousarray(keysR, KP_DTYPE)
+    descL = np.ascontiguousarray(descL, np.uint8); descR = np.ascontiguousarray(descR, np.uint8)
+    scale = np.ascontiguousarray(scale, np.float32); inv_scale = np.ascontiguousarray(inv_scale, np.float32)
+    u = np.zeros(len(keysL), np.float32); z = np.zeros(len(keysL), np.float32)
+    n = L.refst_compute_stereo_matches(C.cast(C.pointer(pyrL.struct), C.c_void_p), C.cast(C.pointer(pyrR.struct), C.c_void_p), len(scale),
+                                       keysL.ctypes.data, descL.ctypes.data, len(keysL), keysR.ctypes.data, descR.ctypes.data, len(keysR),
+                                       _ptr(scale, f32p), _ptr(inv_scale, f32p), float(mb), float(mbf), _ptr(u, f32p), _ptr(z, f32p))
+    return u, z, n
