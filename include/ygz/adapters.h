@@ -23,12 +23,11 @@
 // _ref/libadapters_e2e.so: the SAME caller code, oracle/ref_matcher_shim.cpp, is compiled once against the reference's
 // ORBmatcher.cc and once against this header; tests/test_adapters_gpu.py compares the two on a B200).
 //
-// Usage in the reference tree: include this header AFTER Common.h / Frame.h / KeyFrame.h / MapPoint.h (it needs cv::Mat,
-// cv::KeyPoint and the Eigen typedefs they bring) and
-//     namespace ygz { typedef b200::ORBmatcherT<Frame, KeyFrame, MapPoint> ORBmatcher;
-//                     typedef b200::ORBextractorT<Frame> ORBextractor;
-//                     typedef b200::SparseImgAlignT<Frame> SparseImgAlign; }
-// (or define YGZ_B200_REFERENCE_NAMES before including it).  INTEGRATION.md §2-§4.
+// Usage in the reference tree: let include/ORBextractor.h, ORBmatcher.h and SparseImageAlign.h each be
+//     #define YGZ_B200_REFERENCE_NAMES
+//     #include <ygz/adapters.h>
+// which declares ygz::ORBmatcher / ORBextractor / SparseImgAlign as the specialisations for ygz::Frame / KeyFrame / MapPoint (those
+// may still be incomplete at that point; they must be complete where a method is called).  INTEGRATION.md §2.
 #pragma once
 #include <cmath>
 #include <cstring>
@@ -51,6 +50,22 @@
 #include "SparseImageAlign.h"
 
 namespace ygz {
+namespace b200 {
+template <class Frame, class KeyFrame, class MapPoint> class ORBmatcherT;
+template <class Frame> class ORBextractorT;
+template <class Frame> class SparseImgAlignT;
+}  // namespace b200
+#ifdef YGZ_B200_REFERENCE_NAMES
+// The reference's own class names, for an unchanged Tracking.cc / Frame.cc.  Naming a specialisation does not instantiate it, so
+// this works with Frame / KeyFrame / MapPoint still incomplete: the header can take the place of include/ORBextractor.h,
+// ORBmatcher.h and SparseImageAlign.h, which Frame.h itself includes (Frame holds ORBextractor* members, include/Frame.h:225).
+class Frame;
+class KeyFrame;
+class MapPoint;
+typedef b200::ORBmatcherT<Frame, KeyFrame, MapPoint> ORBmatcher;
+typedef b200::ORBextractorT<Frame> ORBextractor;
+typedef b200::SparseImgAlignT<Frame> SparseImgAlign;
+#endif
 namespace b200 {
 using flat::ExtractorFrame;
 using flat::ImageView;
@@ -468,11 +483,5 @@ public:
 
 }  // namespace b200
 
-#ifdef YGZ_B200_REFERENCE_NAMES
-// the reference's own class names, for an unchanged Tracking.cc (Frame / KeyFrame / MapPoint must be complete here)
-typedef b200::ORBmatcherT<Frame, KeyFrame, MapPoint> ORBmatcher;
-typedef b200::ORBextractorT<Frame> ORBextractor;
-typedef b200::SparseImgAlignT<Frame> SparseImgAlign;
-#endif
 
 }  // namespace ygz

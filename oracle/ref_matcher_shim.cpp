@@ -21,11 +21,11 @@
 #ifdef SHIM_USE_ADAPTERS
 #include <opencv2/core/core.hpp>
 #include "Common.h"
+#define YGZ_B200_REFERENCE_NAMES   // adapters first, as the replaced include/ORBextractor.h would be (Frame.h includes it upstream)
+#include <ygz/adapters.h>
 #include "MapPoint.h"
 #include "KeyFrame.h"
 #include "Frame.h"
-#define YGZ_B200_REFERENCE_NAMES
-#include <ygz/adapters.h>
 #define REFM(name) adp_##name
 #else
 #include <opencv2/core/core.hpp>  // (and the standard headers it pulls) before the access macros below

@@ -18,7 +18,9 @@ namespace ygz {
 
     class MapPoint;
     class KeyFrame;
+#ifndef YGZ_B200_REFERENCE_NAMES     // (ygz/adapters.h declares the name as a typedef when it provides the reference's class names)
     class ORBextractor;
+#endif
 
     class Frame {
     public:
