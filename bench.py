@@ -614,6 +614,13 @@ def main():
     barrier()
     ms_dev = mt.time_frontend2(ex, mt2, ex2, B, args.steps)
     barrier()
+    ms_dev_n = {}
+    if os.environ.get("YGZ_BENCH_SWEEP_INFLIGHT"):          # tuning knob: device-resident throughput vs batches in flight
+        for k in range(1, len(pairs) + 1):
+            m.ORBmatcher.time_frontend_n([(p[0], p[1]) for p in pairs[:k]], B, max(k, 2), NNRATIO, CHECK_ORI)
+            ms_dev_n[k] = m.ORBmatcher.time_frontend_n([(p[0], p[1]) for p in pairs[:k]], B, args.steps, NNRATIO, CHECK_ORI)
+        print("in-flight sweep (frames/s):", {k: round(B * args.steps / (v / 1e3)) for k, v in ms_dev_n.items()}, file=sys.stderr)
+    barrier()
     # ---- end-to-end timing through the public C-ABI calls with host buffers (copies inside)
     barrier()
     e2e_pipelined(2)                     # warm the second handle pair

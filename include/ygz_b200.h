@@ -276,6 +276,11 @@ int ygz_frontend_time(ygz_orb* orb, ygz_matcher* h, int n_frames, int iters, flo
 int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matcher* hB, int n_frames, int iters,
                        float nnratio, int check_orientation, float* ms);
 
+/* The same with k (1..8) handle pairs in flight on k streams: step i runs on pair i % k; timed from the start on the first stream until
+ * every stream has drained. */
+int ygz_frontend_time_n(ygz_orb* const* orbs, ygz_matcher* const* matchers, int k, int n_frames, int iters, float nnratio,
+                        int check_orientation, float* ms);
+
 /* ------------------------------------------------------------------ SparseImgAlign
  * replaces ygz::SparseImgAlign (include/SparseImageAlign.h:14-113, src/SparseImageAlign.cc) and its
  * Gauss-Newton driver (include/NLSSolver_impl.hpp:17-91). */

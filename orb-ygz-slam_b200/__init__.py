@@ -97,7 +97,7 @@ ABI_SYMBOLS = [
     "ygz_descriptor_distance", "ygz_matcher_create", "ygz_matcher_destroy", "ygz_hamming_bf_top2",
     "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_bow_kf", "ygz_search_for_triangulation", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
-    "ygz_matcher_set_vocabulary", "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2",
+    "ygz_matcher_set_vocabulary", "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2", "ygz_frontend_time_n",
     "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
@@ -612,6 +612,17 @@ class ORBmatcher:
         ms = C.c_float()
         _check(self.L.ygz_frontend_time2(extractor.h, self.h, other_extractor.h, other_matcher.h, n_frames, iters,
                                          self.nnratio, int(self.checkOri), C.byref(ms)), "ygz_frontend_time2")
+        return ms.value
+
+    @staticmethod
+    def time_frontend_n(pairs, n_frames, iters, nnratio, check_ori):
+        """pairs: [(ORBextractor, ORBmatcher), ...] — k handle pairs in flight on k streams; returns total ms over iters steps."""
+        k = len(pairs)
+        orbs = (C.c_void_p * k)(*[p[0].h for p in pairs]); hs = (C.c_void_p * k)(*[p[1].h for p in pairs])
+        ms = C.c_float()
+        L = lib()
+        L.ygz_frontend_time_n.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
+        _check(L.ygz_frontend_time_n(orbs, hs, k, n_frames, iters, float(nnratio), int(check_ori), C.byref(ms)), "ygz_frontend_time_n")
         return ms.value
 
     def time_frontend(self, extractor, n_frames, iters):

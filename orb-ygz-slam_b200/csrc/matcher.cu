@@ -1095,6 +1095,42 @@ int ygz_frontend_time2(ygz_orb* orbA, ygz_matcher* hA, ygz_orb* orbB, ygz_matche
 
 }  // extern "C"
 
+// The same with k handle pairs in flight (k streams): step i runs on pair i % k.  k = 2 is ygz_frontend_time2.
+extern "C" int ygz_frontend_time_n(ygz_orb* const* orbs, ygz_matcher* const* hs, int k, int n_frames, int iters, float nnratio, int check_ori,
+                                   float* ms) {
+    YGZ_ARG_CHECK(orbs && hs && k >= 1 && k <= 8 && ms && iters >= 1);
+    for (int i = 0; i < k; i++) YGZ_ARG_CHECK(orbs[i] && hs[i] && hs[i]->last_pairs >= 1);
+    YGZ_CUDA_TRY(cudaSetDevice(hs[0]->device));
+    BowBatchArgs A[8];
+    cudaStream_t st[8];
+    int rc;
+    for (int i = 0; i < k; i++) {
+        if ((rc = refreshed_args(hs[i], orbs[i], nnratio, check_ori, &A[i]))) return rc;
+        st[i] = (cudaStream_t)ygz_orb_stream(orbs[i]);
+        YGZ_CUDA_TRY(cudaStreamSynchronize(hs[i]->stream));
+        YGZ_CUDA_TRY(cudaStreamSynchronize(st[i]));
+    }
+    YGZ_CUDA_TRY(cudaEventRecord(hs[0]->ev0, st[0]));
+    for (int i = 1; i < k; i++) YGZ_CUDA_TRY(cudaStreamWaitEvent(st[i], hs[0]->ev0, 0));
+    for (int it = 0; it < iters; it++) {
+        const int i = it % k;
+        if ((rc = ygz_orb_run(orbs[i], n_frames))) return rc;
+        if (hs[i]->vocab && (rc = launch_node_ids(hs[i], orbs[i], hs[i]->bow_frames, A[i].cap, st[i]))) return rc;
+        { NvtxRange nvtx_range("ygz/SearchByBoW batch");
+        k_bow_match_batch<<<hs[i]->last_pairs, BOW_THREADS, bow_smem_bytes(A[i].cap), st[i]>>>(A[i]);
+        }
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    for (int i = 1; i < k; i++) {
+        YGZ_CUDA_TRY(cudaEventRecord(hs[i]->ev1, st[i]));
+        YGZ_CUDA_TRY(cudaStreamWaitEvent(st[0], hs[i]->ev1, 0));
+    }
+    YGZ_CUDA_TRY(cudaEventRecord(hs[0]->ev1, st[0]));
+    YGZ_CUDA_TRY(cudaEventSynchronize(hs[0]->ev1));
+    YGZ_CUDA_TRY(cudaEventElapsedTime(ms, hs[0]->ev0, hs[0]->ev1));
+    return YGZ_OK;
+}
+
 // ---------------------------------------------------------------------------------- batched projection searches (host side)
 namespace {
 enum { PJ_QF, PJ_TF, PJ_WP, PJ_VALID, PJ_POSE, PJ_PX, PJ_PY, PJ_PXR, PJ_VC, PJ_LVL, PJ_USABLE, PJ_QDESC, PJ_OCC, PJ_UR, PJ_OUT, PJ_CNT };
