@@ -26,43 +26,63 @@ struct VocabDev {
     int L;
 };
 
-constexpr int VOC_GROUP = 16;   // lanes per descriptor: two descents per warp, up to 16 children per step (k = 10 for ORBvoc)
+// Lanes per descriptor (GROUP): 10 for trees with k <= 10 (ORBvoc.bin: k = 10) — three descents per warp, every lane of a group busy at
+// every level — and 16 for wider trees (two descents per warp).  Measured on the ORBvoc-shaped tree, 256 frames: 16 lanes 0.146 ms.
+template <int GROUP> struct VocGroup { static constexpr int per_warp = 32 / GROUP; };
 
 // mask_stopped: node id 0xFFFFFFFF for words of weight 0 — TemplatedVocabulary::transform adds a feature to the FeatureVector
 // only `if (w > 0)` (TemplatedVocabulary.h:1186-1190), so SearchByBoW never sees the features of stopped words.
+template <int GROUP>
 __global__ void __launch_bounds__(256) k_vocab_transform(VocabDev V, const uint4* __restrict__ desc, size_t desc_stride_u4,
                                                          const int* __restrict__ counts, int cap, int n_total, int levelsup,
                                                          int mask_stopped, int* __restrict__ word_id, float* __restrict__ weight,
                                                          int* __restrict__ node_id) {
+    constexpr int PER_WARP = 32 / GROUP;
     // feature f = (frame, slot): frame = f / cap, slot = f % cap (cap = n_total and counts = NULL for a flat list)
-    const int f = (blockIdx.x * blockDim.x + threadIdx.x) / VOC_GROUP;
-    const int gl = threadIdx.x & (VOC_GROUP - 1);
-    bool live = f < n_total;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane / GROUP;                       // group inside the warp; lanes past PER_WARP * GROUP idle
+    const int gl = lane - grp * GROUP;
+    const int f = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * PER_WARP + grp;
+    bool live = grp < PER_WARP && f < n_total;
     if (live && counts) {
         const int frame = f / cap, slot = f - frame * cap;
         live = slot < __ldg(counts + frame);
     }
-    const unsigned gmask = __ballot_sync(0xffffffffu, live) & (0xFFFFu << ((threadIdx.x & 16)));     // this group's lanes, if live
+    const unsigned glanes = (GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u)) << (grp * GROUP);
+    const unsigned gmask = __ballot_sync(0xffffffffu, live) & glanes;     // this group's lanes, if live (a group is live or dead as a whole)
     if (!live) return;
     const uint4* d = desc + (size_t)f * desc_stride_u4;
     const uint4 a0 = __ldg(d), a1 = __ldg(d + 1);
     const int nid_level = V.L - levelsup;
     int cur = 0, level = 0, nid_node = 0;
     int4 m = __ldg(V.meta);
+    const int base = grp * GROUP;
     while (m.y > 0) {
         ++level;
         int best = INT_MAX, bestc = INT_MAX;
-        for (int c = gl; c < m.y; c += VOC_GROUP) {
+        for (int c = gl; c < m.y; c += GROUP) {
             const uint4* b = V.desc + 2 * (size_t)(m.x + c);
             const uint4 b0 = __ldg(b), b1 = __ldg(b + 1);
             const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
             if (dist < best) { best = dist; bestc = c; }       // first minimum in child order (the reference's strict <)
         }
+        // minimum over the group's lanes, result on every lane: a butterfly for power-of-two groups, otherwise a fold onto lane 0 of
+        // the group (offsets 8, 4, 2, 1; partners past the group are ignored) and a broadcast
+        if ((GROUP & (GROUP - 1)) == 0) {
 #pragma unroll
-        for (int o = VOC_GROUP / 2; o; o >>= 1) {
-            const int ob = __shfl_xor_sync(gmask, best, o), oc = __shfl_xor_sync(gmask, bestc, o);
-            if (ob < best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
+            for (int o = GROUP / 2; o; o >>= 1) {
+                const int ob = __shfl_xor_sync(gmask, best, o), oc = __shfl_xor_sync(gmask, bestc, o);
+                if (ob < best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
+            }
+        } else {
+#pragma unroll
+            for (int o = 8; o; o >>= 1) {
+                const int src = min(lane + o, base + GROUP - 1);
+                const int ob = __shfl_sync(gmask, best, src), oc = __shfl_sync(gmask, bestc, src);
+                if (gl + o < GROUP && (ob < best || (ob == best && oc < bestc))) { best = ob; bestc = oc; }
+            }
+            bestc = __shfl_sync(gmask, bestc, base);
         }
         cur = m.x + bestc;
         m = __ldg(V.meta + cur);
@@ -75,6 +95,19 @@ __global__ void __launch_bounds__(256) k_vocab_transform(VocabDev V, const uint4
         if (weight) weight[f] = w;
         node_id[f] = (mask_stopped && !(w > 0.f)) ? -1 : nid_node;
     }
+}
+
+// one launch over n descriptors with the group width that fits the tree
+static cudaError_t launch_vocab_transform(int k, cudaStream_t st, VocabDev V, const uint4* desc, size_t stride_u4, const int* counts, int cap, int n,
+                                          int levelsup, int mask_stopped, int* word_id, float* weight, int* node_id) {
+    if (k <= 10) {
+        const int per_cta = (256 / 32) * (32 / 10);
+        k_vocab_transform<10><<<ceil_div(n, per_cta), 256, 0, st>>>(V, desc, stride_u4, counts, cap, n, levelsup, mask_stopped, word_id, weight, node_id);
+    } else {
+        const int per_cta = (256 / 32) * (32 / 16);
+        k_vocab_transform<16><<<ceil_div(n, per_cta), 256, 0, st>>>(V, desc, stride_u4, counts, cap, n, levelsup, mask_stopped, word_id, weight, node_id);
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -123,10 +156,10 @@ int vocab_node_ids_async(ygz_vocab* v, const void* d_desc, const int* d_counts, 
                          uint32_t* d_node_out, cudaStream_t st) {
     const int n = n_frames * cap;
     { NvtxRange nvtx_range("ygz/ComputeBoW");
-    k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, st>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, d_counts, cap, n,
-                                                                   levelsup, 1, nullptr, nullptr, reinterpret_cast<int*>(d_node_out));
+    if (launch_vocab_transform(v->k, st, v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, d_counts, cap, n, levelsup, 1, nullptr, nullptr,
+                               reinterpret_cast<int*>(d_node_out)) != cudaSuccess) return YGZ_ERR_CUDA;
     }
-    return cudaGetLastError() == cudaSuccess ? YGZ_OK : YGZ_ERR_CUDA;
+    return YGZ_OK;
 }
 int vocab_device(const ygz_vocab* v) { return v->device; }
 }  // namespace ygz_b200
@@ -234,10 +267,9 @@ int ygz_vocab_transform(ygz_vocab* v, const uint8_t* desc, int n, int levelsup, 
     if (rc) return rc;
     YGZ_CUDA_TRY(cudaMemcpyAsync(v->d_in, desc, (size_t)n * 32, cudaMemcpyHostToDevice, v->stream));
     { NvtxRange nvtx_range("ygz/ComputeBoW");
-    k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n,
-                                                                          levelsup, 0, v->d_wid, v->d_w, v->d_nid);
+    YGZ_CUDA_TRY(launch_vocab_transform(v->k, v->stream, v->dev(), reinterpret_cast<const uint4*>(v->d_in), 2, nullptr, n, n, levelsup, 0, v->d_wid,
+                                        v->d_w, v->d_nid));
     }
-    YGZ_CUDA_TRY(cudaGetLastError());
     YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(weight, v->d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     YGZ_CUDA_TRY(cudaMemcpyAsync(node_id, v->d_nid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
@@ -270,11 +302,9 @@ int ygz_vocab_transform_orb(ygz_vocab* v, ygz_orb* orb, int n_frames, int levels
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ms) { YGZ_CUDA_TRY(cudaEventCreate(&e0)); YGZ_CUDA_TRY(cudaEventCreate(&e1)); YGZ_CUDA_TRY(cudaEventRecord(e0, v->stream)); }
     { NvtxRange nvtx_range("ygz/ComputeBoW");
-    k_vocab_transform<<<ceil_div(n, 256 / VOC_GROUP), 256, 0, v->stream>>>(v->dev(), reinterpret_cast<const uint4*>(d_desc), 2,
-                                                                          reinterpret_cast<const int*>(d_counts), cap, n, levelsup, 0,
-                                                                          v->d_wid, v->d_w, v->d_nid);
+    YGZ_CUDA_TRY(launch_vocab_transform(v->k, v->stream, v->dev(), reinterpret_cast<const uint4*>(d_desc), 2, reinterpret_cast<const int*>(d_counts), cap,
+                                        n, levelsup, 0, v->d_wid, v->d_w, v->d_nid));
     }
-    YGZ_CUDA_TRY(cudaGetLastError());
     if (ms) { YGZ_CUDA_TRY(cudaEventRecord(e1, v->stream)); }
     if (word_id) YGZ_CUDA_TRY(cudaMemcpyAsync(word_id, v->d_wid, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));
     if (weight) YGZ_CUDA_TRY(cudaMemcpyAsync(weight, v->d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, v->stream));

@@ -1,0 +1,111 @@
+"""Writes profiles/README.md (round 2) from the committed artefacts: r2_launches_ncu_B256.csv, kernel_metrics.json, r2_bench_*.json.
+usage: python profiles/scripts/make_readme.py"""
+import csv
+import json
+import os
+
+P = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load(name):
+    try:
+        return json.load(open(os.path.join(P, name)))
+    except Exception:
+        return None
+
+
+def launches():
+    rows = list(csv.reader(open(os.path.join(P, "r2_launches_ncu_B256.csv"))))
+    h = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    kn, mv, gs, bs = (rows[h].index(k) for k in ("Kernel Name", "Metric Value", "Grid Size", "Block Size"))
+    out = []
+    for r in rows[h + 1:]:
+        if len(r) > mv:
+            out.append((r[kn].split("(")[0].split("::")[-1], r[gs], r[bs], float(r[mv].replace(",", "")) / 1e3))
+    return out
+
+
+def main():
+    b = load("r2_bench_N1.json")
+    ref = load("r2_bench_reference_arm.json")
+    km = load("kernel_metrics.json") or {}
+    L = launches()
+    tot = sum(x[3] for x in L)
+    st = b["stages_ms_per_step"]
+    out = []
+    w = out.append
+    w("# profiles/ — round 2 (B200, sm_100a, CUDA 12.9)\n")
+    w("Produced by `profiles/scripts/prof_r2_checkpoint.sh` / `prof_r2_ncu.sh` (one `gpurun` call each, fresh B200 box, SM clock %s MHz = max, throttle reasons %s)."
+      % (b["clocks"]["sm_mhz"], b["clocks"]["reasons"] or "none"))
+    w("Numbers printed under ncu are never used as bench values; `r2_bench_N1.json` is the un-profiled `python bench.py --steps 20 --warmup 3` line of the same build")
+    w("(`kernel_metrics.json` carries the sha1 of `orb-ygz-slam_b200/csrc/` it was captured from: `%s`; `bench.py` refuses to quote it for another build).\n" % km.get("csrc_sha", "?")[:12])
+    w("| file | what |\n|---|---|")
+    w("| `r2_launches_ncu_B256.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off` over exactly ONE bench-shaped step (`scripts/prof1.py` brackets it with `cudaProfilerStart/Stop`): every kernel launch with its device time |")
+    w("| `r2_full_B256_raw.csv`, `r2_full_pyramid_B256_raw.csv` | `ncu --set full --clock-control none --import-source on`, raw pages of every kernel of the step (B = 256) |")
+    w("| `kernel_metrics.json` | per-kernel summary of those captures (`scripts/ncu_summary.py`): DRAM bytes, issue / pipe utilisation, warp instructions — what `bench.py` quotes in `roofline.traffic` / `limiter` |")
+    w("| `r2_bench_N1.json`, `r2_bench_reference_arm.json` | C2 headline line and `--impl reference` (oracle port, all host threads, B = 256 frames/step) on the same box |")
+    w("| `r2_bench_c5_N1.json`, `r2_bench_c5_N8.json`, `r2_bench_c5_reference_arm.json` | `bench.py --workload c5` (stereo 1242x375 x2, 2000 features, extractor x2 + ComputeStereoMatches + brute force) at 1 and 8 GPUs, CPU arm |")
+    w("| `r2_bench_c3_N1.json`, `r2_bench_c3_N8.json`, `r2_bench_c3_reference_arm.json` | `bench.py --workload c3` (SparseImgAlign, 592 problems/step) at 1 and 8 GPUs, CPU arm |")
+    w("| `r2_sanitizer_memcheck_smoke.log`, `r2_sanitizer_racecheck_smoke.log` | `compute-sanitizer --tool memcheck / racecheck python __graft_entry__.py smoke` |")
+    w("| `r1_*` | round-1 artefacts, kept for comparison |\n")
+    w("## Launch list of one C2 step (ncu, cold cache, serialised) vs the bench's own stage timing\n")
+    w("| # | kernel | grid | block | device time (us) | share of step |\n|---|---|---|---|---:|---:|")
+    for i, (k, g, bl, us) in enumerate(L):
+        w("| %d | %s | %s | %s | %.1f | %.1f%% |" % (i, k, g, bl.split(",")[0].strip("( "), us, 100 * us / tot))
+    w("| | **sum** | | | **%.1f** | |\n" % tot)
+    ssum = sum(st.values())
+    w("| stage (bench.py, CUDA events, warm, back to back) | ms / step | share |\n|---|---:|---:|")
+    for k, v in st.items():
+        w("| %s | %.3f | %.1f%% |" % (k, v, 100 * v / ssum))
+    w("| sum of stages | %.3f | |" % ssum)
+    w("| whole step on one stream (`value_single_stream`) | %.3f | |" % (1e3 * b["config"]["frames_per_step"] / b["value_single_stream"]))
+    w("| whole step, two batches in flight on two streams (`value`) | %.3f | |" % b["ms_per_step"])
+    w("| end to end, host buffers, three batches in flight (`e2e`) | %.3f | |\n" % b["e2e"]["ms_per_step"])
+    name = {"k_fast_cells_v2": "fast_cells", "k_octree": "octree", "k_blur_levels": "blur_levels", "k_orient_describe": "orient_describe",
+            "k_vocab_transform": "vocab_transform", "k_bow_match_batch": "bow_match"}
+    agg = {}
+    for k, g, bl, us in L:
+        key = "pyramid(7 launches)" if k.startswith("k_pyr") else name.get(k)
+        if key:
+            agg[key] = agg.get(key, 0) + us
+    w("Kernel shares, profiler pass vs live CUDA-event timing: " + ", ".join(
+        "%s %.1f %% vs %.1f %%" % (k, 100 * agg[k] / tot, 100 * st[k] / ssum) for k in st if k in agg) + ".\n")
+    w("## Headline numbers of the build\n")
+    w("* C2 (752x480, 1000 features, 8 levels; extractor + Frame::ComputeBoW + SearchByBoW, B = 256): **%.0f frames/s** device-resident, **%.0f frames/s** end to end "
+      "(H2D %.0f MB + D2H %.0f MB per step inside the timed region); CPU arm (oracle port, %s threads) %.0f frames/s; OpenCV-primitive CPU arm %s frames/s."
+      % (b["value"], b["e2e"]["value"], b["e2e"]["h2d_bytes_per_step"] / 1e6, b["e2e"]["d2h_bytes_per_step"] / 1e6,
+         (b.get("cpu_baseline") or {}).get("cores", "?"), (b.get("cpu_baseline") or {}).get("value", float("nan")),
+         "%.0f" % b["cpu_baseline_opencv"]["value"] if b.get("cpu_baseline_opencv", {}).get("value") else "n/a"))
+    r = b["roofline"]
+    w("* roofline, dominant kernel `%s`: %.0f MB algorithmic per launch / %.3f ms = **%.0f GB/s = %.3f of the measured %.0f GB/s**; DRAM traffic %s; %s."
+      % (r["kernel"], r["algorithmic_bytes_per_launch"] / 1e6, r["kernel_ms_per_launch"], r["achieved"], r["frac"], r["peak"],
+         ("%.0f MB" % (r["traffic"] / 1e6)) if r.get("traffic") else "n/a", r["limiter"]))
+    pf = r["pyramid_plus_fast"]
+    w("* pyramid + FAST, strict accounting (every level read once): %.0f MB / %.3f ms = %.0f GB/s = **%.3f** of peak.\n" % (pf["strict_bytes_per_step"] / 1e6, pf["ms_per_step"], pf["achieved"], pf["frac"]))
+    for wl, unit in (("c5", "stereo pairs/s"), ("c3", "alignments/s")):
+        j1, j8 = load("r2_bench_%s_N1.json" % wl), load("r2_bench_%s_N8.json" % wl)
+        if j1:
+            cb = j1.get("cpu_baseline") or {}
+            w("* %s: **%.0f %s** device-resident, %.0f end to end at 1 GPU%s; CPU arm %s (%s threads)%s."
+              % (wl.upper(), j1["value"], unit, j1["e2e"]["value"],
+                 ("; **%.0f** / %.0f at 8 GPUs" % (j8["value"], j8["e2e"]["value"])) if j8 else "",
+                 "%.0f" % cb["value"] if cb.get("value") else "n/a", cb.get("cores", "?"),
+                 "; in-bench parity gate: %s" % (cb.get("parity_gate_pair0_bit_exact", cb.get("parity_gate_max_pose_diff")),) if cb else ""))
+    w("")
+    w("## Per-kernel summary (ncu --set full, B = 256)\n")
+    w("| stage | kernel | ms (ncu) | issue active | ALU / FMA / LSU pipe | warps active | DRAM read + write | warp instructions | regs |\n|---|---|---:|---:|---|---:|---|---:|---:|")
+    for k, v in (km.get("kernels") or {}).items():
+        w("| %s | `%s` | %.3f | %.1f %% | %.0f / %.0f / %.0f %% | %.0f %% | %.1f + %.1f MB | %.0f M | %d |"
+          % (k, v["kernel"], v.get("duration_ns", 0) / 1e6, v.get("issue_active_pct", 0), v.get("alu_pct", 0), v.get("fma_pct", 0), v.get("lsu_pct", 0),
+             v.get("warps_active_pct", 0), v.get("dram_bytes_read", 0) / 1e6, v.get("dram_bytes_write", 0) / 1e6, v.get("warp_instructions", 0) / 1e6,
+             int(v.get("registers", 0))))
+    w("")
+    w("Every kernel of the step is issue-bound (59-87 % of the issue slots, ALU pipe 45-69 %) except the two latency-bound ones (`k_octree`, `k_bow_match_batch`);")
+    w("the step as a whole saturates at two batches in flight (`ygz_frontend_time_n`: 126 / 133 / 133 / 133 k frames/s at 1 / 2 / 3 / 4 in flight), i.e. it is bound by")
+    w("the aggregate instruction count (1.58 G warp instructions per 256 frames), not by bytes: DRAM traffic per step is within 1.1 x of the algorithmic bytes.")
+    open(os.path.join(P, "README.md"), "w").write("\n".join(out) + "\n")
+    print("written")
+
+
+if __name__ == "__main__":
+    main()
