@@ -27,7 +27,9 @@ struct VocabDev {
 };
 
 // Lanes per descriptor (GROUP): 10 for trees with k <= 10 (ORBvoc.bin: k = 10) — three descents per warp, every lane of a group busy at
-// every level — and 16 for wider trees (two descents per warp).  Measured on the ORBvoc-shaped tree, 256 frames: 16 lanes 0.146 ms.
+// every level — and 16 for wider trees (two descents per warp).  Measured on the ORBvoc-shaped tree, 256 frames: 16 lanes 0.146 ms,
+// 10 lanes 0.135 ms; persistent CTAs with the top three levels of the tree (1 111 nodes, 53 KB) in shared memory: 0.150 ms (the top of
+// the tree already hits L1; the shared-memory copy only costs occupancy) — not kept.
 template <int GROUP> struct VocGroup { static constexpr int per_warp = 32 / GROUP; };
 
 // mask_stopped: node id 0xFFFFFFFF for words of weight 0 — TemplatedVocabulary::transform adds a feature to the FeatureVector
