@@ -80,6 +80,31 @@ public:
         vnMatches12.resize(F1.n > 0 ? F1.n : 0);
         return n;
     }
+    // The Sim3 family of the back end (loop closing); the map-point table must carry `normal`.
+    // SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th)  :265-373   (Scw 4x4 row-major)
+    int SearchByProjection(const ygz_frame_view& KF, const float Scw[16], const ygz_map_points& mps, const std::vector<int>& vpPoints,
+                           std::vector<int>& vpMatched, int th) {
+        vpMatched.resize(KF.n > 0 ? KF.n : 1, -1);
+        const int n = ok(ygz_search_by_projection_sim3(h_, &KF, Scw, &mps, vpPoints.data(), (int)vpPoints.size(), vpMatched.data(), th));
+        vpMatched.resize(KF.n > 0 ? KF.n : 0);
+        return n;
+    }
+    // Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint)  :888-1004   (KF.map_point is the key frame's slot table, updated)
+    int Fuse(ygz_frame_view& KF, const float Scw[16], const ygz_map_points& mps, const std::vector<int>& vpPoints, float th,
+             std::vector<int>& vpReplacePoint) {
+        vpReplacePoint.resize(vpPoints.size() ? vpPoints.size() : 1, -1);
+        const int n = ok(ygz_fuse_sim3(h_, &KF, Scw, &mps, vpPoints.data(), (int)vpPoints.size(), th, vpReplacePoint.data()));
+        vpReplacePoint.resize(vpPoints.size());
+        return n;
+    }
+    // SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  :1006-1216
+    int SearchBySim3(const ygz_frame_view& KF1, const ygz_frame_view& KF2, const ygz_map_points& mps, std::vector<int>& vpMatches12,
+                     const std::vector<int>& idxInKF2, float s12, const float R12[9], const float t12[3], float th) {
+        vpMatches12.resize(KF1.n > 0 ? KF1.n : 1, -1);
+        const int n = ok(ygz_search_by_sim3(h_, &KF1, &KF2, &mps, vpMatches12.data(), idxInKF2.data(), s12, R12, t12, th));
+        vpMatches12.resize(KF1.n > 0 ? KF1.n : 0);
+        return n;
+    }
     ygz_matcher* handle() { return h_; }
 
     // ---- direct (patch) projection search, SURVEY.md §8(f) rank 1 -------------------------------------------------

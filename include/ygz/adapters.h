@@ -146,7 +146,7 @@ struct DescRows {
 template <class MapPoint> struct PointTable {
     std::vector<MapPoint*> pts;
     std::unordered_map<MapPoint*, int> index;
-    std::vector<float> wp, mind, maxd, px, py, pxr, vcos;
+    std::vector<float> wp, mind, maxd, px, py, pxr, vcos, nrm;
     std::vector<uint8_t> desc, bad, inview;
     std::vector<int> obs, lvl;
 
@@ -159,6 +159,8 @@ template <class MapPoint> struct PointTable {
         pts.push_back(p);
         const auto w = p->GetWorldPos();
         wp.push_back(w(0)); wp.push_back(w(1)); wp.push_back(w(2));
+        const auto nv = p->GetNormal();
+        nrm.push_back(nv(0)); nrm.push_back(nv(1)); nrm.push_back(nv(2));
         const auto d = p->GetDescriptor();
         desc.resize(desc.size() + 32, 0);
         if (d.data) std::memcpy(&desc[(size_t)i * 32], d.data, 32);
@@ -178,7 +180,7 @@ template <class MapPoint> struct PointTable {
         v.world_pos = wp.data(); v.desc = desc.data(); v.bad = bad.data(); v.observations = obs.data();
         v.min_dist = mind.data(); v.max_dist = maxd.data(); v.track_in_view = inview.data();
         v.track_proj_x = px.data(); v.track_proj_y = py.data(); v.track_proj_xr = pxr.data();
-        v.track_scale_level = lvl.data(); v.track_view_cos = vcos.data();
+        v.track_scale_level = lvl.data(); v.track_view_cos = vcos.data(); v.normal = nrm.data();
         return v;
     }
 };

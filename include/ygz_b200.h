@@ -178,6 +178,7 @@ typedef struct {
     const float* track_proj_xr;
     const int* track_scale_level;
     const float* track_view_cos;
+    const float* normal;            /* m x 3, MapPoint::GetNormal (used by the Sim3 searches only; may be NULL elsewhere) */
 } ygz_map_points;
 
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:155-263.
@@ -208,6 +209,21 @@ int ygz_search_by_projection_kf(ygz_matcher* h, int check_orientation, ygz_frame
 /* ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:375-478 */
 int ygz_search_for_initialization(ygz_matcher* h, float nnratio, int check_orientation, const ygz_frame_view* f1,
                                   const ygz_frame_view* f2, float* prev_matched_xy, int* matches12, int window);
+
+/* The Sim3 family of the back end (loop closing; the map-point table must carry `normal`).  Scw: 4x4 row-major similarity.
+ * SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:265-373: point_ids index the table;
+ * matched[kf->n] = map-point index per key-frame feature, in / out (-1 = NULL). */
+int ygz_search_by_projection_sim3(ygz_matcher* h, const ygz_frame_view* kf, const float* Scw, const ygz_map_points* mps,
+                                  const int* point_ids, int n_points, int* matched, int th);
+/* Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint), :888-1004: kf->map_point is the key frame's slot table, in / out (a free
+ * slot receives the point: AddObservation + AddMapPoint); replace_point[n_points] in / out (upstream initialises it with NULL = -1):
+ * the map point already sitting in the chosen slot.  Returns nFused. */
+int ygz_fuse_sim3(ygz_matcher* h, ygz_frame_view* kf, const float* Scw, const ygz_map_points* mps, const int* point_ids, int n_points,
+                  float th, int* replace_point);
+/* SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th), :1006-1216: matches12[kf1->n] in / out (map-point index of KF2's point, -1 =
+ * none); idx_in_kf2[mps->m] = pMP->GetIndexInKeyFrame(pKF2) (-1 = not observed there); R12 row-major 3x3, t12 3. */
+int ygz_search_by_sim3(ygz_matcher* h, const ygz_frame_view* kf1, const ygz_frame_view* kf2, const ygz_map_points* mps, int* matches12,
+                       const int* idx_in_kf2, float s12, const float* R12, const float* t12, float th);
 
 /* Batched, device-resident projection searches over the extractor's resident outputs (one CTA per pair; the sequential occupancy
  * semantics of the reference loops are resolved exactly by ordered reservation rounds, csrc/projection_batch.cuh).  Assumption: every

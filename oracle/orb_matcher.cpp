@@ -528,3 +528,217 @@ int orc_search_for_initialization(float nnratio, int check_ori, const orc_frame_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// The Sim3 family of the back end (loop closing): SearchByProjection(KF, Scw, ...) :265-373, Fuse(KF, Scw, ...) :888-1004,
+// SearchBySim3 :1006-1216.  They do their geometry in CV_32F cv::Mat algebra; the restatement follows the arithmetic OpenCV's small
+// float matrices get in oracle/ref_mock/mock_cv.hpp (against which the reference's own code is compiled for the pin): a matrix
+// product accumulates in double and rounds once, scaling multiplies by a double factor and rounds, elementwise ops are float.
+namespace {
+inline void mat33_vec(const float* R, const float* p, float* o) {
+    for (int i = 0; i < 3; i++) {
+        double s = 0;
+        for (int k = 0; k < 3; k++) s += (double)R[3 * i + k] * p[k];
+        o[i] = (float)s;
+    }
+}
+inline float norm3(const float* p) { double s = 0; for (int k = 0; k < 3; k++) s += (double)p[k] * p[k]; return (float)std::sqrt(s); }
+inline double dot3(const float* a, const float* b) { double s = 0; for (int k = 0; k < 3; k++) s += (double)a[k] * b[k]; return s; }
+
+struct SimCam { float R[9], t[3], Ow[3]; };
+// Decompose Scw (:274-278 / :897-901)
+void decompose_scw(const float* S, SimCam& C) {
+    double d = 0;
+    for (int k = 0; k < 3; k++) d += (double)S[k] * S[k];                         // sRcw.row(0).dot(sRcw.row(0))
+    const float scw = (float)std::sqrt(d);
+    const double inv = 1.0 / scw;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.R[3 * i + j] = (float)(S[4 * i + j] * inv);       // sRcw / scw
+    for (int i = 0; i < 3; i++) C.t[i] = (float)(S[4 * i + 3] * inv);                                           // Scw.col(3) / scw
+    float nRt[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) nRt[3 * i + j] = (float)(C.R[3 * j + i] * -1.0);   // -Rcw.t()
+    mat33_vec(nRt, C.t, C.Ow);
+}
+inline int predict_scale(float max_dist_raw, float dist, const orc_frame_view* kf) {        // MapPoint::PredictScale(dist, pKF)
+    const float ratio = max_dist_raw / dist;
+    int nScale = (int)std::ceil(std::log(ratio) / kf->log_scale_factor);
+    if (nScale < 0) nScale = 0; else if (nScale >= kf->n_levels) nScale = kf->n_levels - 1;
+    return nScale;
+}
+inline bool kf_is_in_image(const orc_frame_view* kf, float x, float y) {                   // KeyFrame::IsInImage, integer bounds
+    return x >= (int)kf->min_x && x < (int)kf->max_x && y >= (int)kf->min_y && y < (int)kf->max_y;
+}
+}  // namespace
+
+extern "C" {
+
+// SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th) :265-373.
+// point_ids index mps; matched[kf->n]: map-point index per KF feature (in / out, -1 = NULL).
+int orc_search_by_projection_sim3(const orc_frame_view* kf, const float* Scw, const orc_map_points* mps, const int* point_ids, int n_points,
+                                  int* matched, int th) {
+    SimCam C;
+    decompose_scw(Scw, C);
+    std::vector<char> already(mps->m, 0);                        // spAlreadyFound(vpMatched) minus NULL
+    for (int i = 0; i < kf->n; i++) if (matched[i] >= 0) already[matched[i]] = 1;
+    Grid g(kf);
+    int nmatches = 0;
+    for (int iMP = 0; iMP < n_points; iMP++) {
+        const int pMP = point_ids[iMP];
+        if (mp_bad(mps, pMP) || already[pMP]) continue;
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        float pc[3];
+        mat33_vec(C.R, Pw, pc);
+        for (int k = 0; k < 3; k++) pc[k] = pc[k] + C.t[k];
+        if (pc[2] < 0.0) continue;
+        const float invz = 1 / pc[2];
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float u = kf->fx * x + kf->cx, v = kf->fy * y + kf->cy;
+        if (!kf_is_in_image(kf, u, v)) continue;
+        const float maxDistance = 1.2f * mps->max_dist[pMP], minDistance = 0.8f * mps->min_dist[pMP];
+        float PO[3];
+        for (int k = 0; k < 3; k++) PO[k] = Pw[k] - C.Ow[k];
+        const float dist = norm3(PO);
+        if (dist < minDistance || dist > maxDistance) continue;
+        const float* Pn = mps->normal + 3 * (size_t)pMP;
+        if (dot3(PO, Pn) < 0.5 * dist) continue;
+        const int lvl = predict_scale(mps->max_dist[pMP], dist, kf);
+        const float radius = th * kf->scale_factors[lvl];
+        const std::vector<int> cand = features_in_area(kf, g, u, v, radius);
+        if (cand.empty()) continue;
+        const uint8_t* dMP = mps->desc + 32 * (size_t)pMP;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            if (matched[idx] >= 0) continue;
+            const int kpLevel = kf->keys[idx].octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            const int d = descriptor_distance(dMP, kf->desc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) { matched[bestIdx] = pMP; nmatches++; }
+    }
+    return nmatches;
+}
+
+// Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint) :888-1004.
+// kf->map_point is pKF's slot table (in / out: AddMapPoint fills free slots); replace_point[n_points] (in / out, the caller
+// initialises it, upstream with NULL = -1).
+int orc_fuse_sim3(orc_frame_view* kf, const float* Scw, const orc_map_points* mps, const int* point_ids, int n_points, float th,
+                  int* replace_point) {
+    SimCam C;
+    decompose_scw(Scw, C);
+    std::vector<char> already(mps->m, 0);                        // spAlreadyFound = pKF->GetMapPoints(): non-null and not bad, at entry
+    for (int i = 0; i < kf->n; i++) if (kf->map_point[i] >= 0 && !mp_bad(mps, kf->map_point[i])) already[kf->map_point[i]] = 1;
+    Grid g(kf);
+    int nFused = 0;
+    for (int iMP = 0; iMP < n_points; iMP++) {
+        const int pMP = point_ids[iMP];
+        if (mp_bad(mps, pMP) || already[pMP]) continue;
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        float pc[3];
+        mat33_vec(C.R, Pw, pc);
+        for (int k = 0; k < 3; k++) pc[k] = pc[k] + C.t[k];
+        if (pc[2] < 0.0f) continue;
+        const float invz = (float)(1.0 / pc[2]);
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float u = kf->fx * x + kf->cx, v = kf->fy * y + kf->cy;
+        if (!kf_is_in_image(kf, u, v)) continue;
+        const float maxDistance = 1.2f * mps->max_dist[pMP], minDistance = 0.8f * mps->min_dist[pMP];
+        float PO[3];
+        for (int k = 0; k < 3; k++) PO[k] = Pw[k] - C.Ow[k];
+        const float dist3D = norm3(PO);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = mps->normal + 3 * (size_t)pMP;
+        if (dot3(PO, Pn) < 0.5 * dist3D) continue;
+        const int lvl = predict_scale(mps->max_dist[pMP], dist3D, kf);
+        const float radius = th * kf->scale_factors[lvl];
+        const std::vector<int> cand = features_in_area(kf, g, u, v, radius);
+        if (cand.empty()) continue;
+        const uint8_t* dMP = mps->desc + 32 * (size_t)pMP;
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int idx : cand) {
+            const int kpLevel = kf->keys[idx].octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            const int d = descriptor_distance(dMP, kf->desc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        if (bestDist <= TH_LOW) {
+            const int pMPinKF = kf->map_point[bestIdx];
+            if (pMPinKF >= 0) {
+                if (!mp_bad(mps, pMPinKF)) replace_point[iMP] = pMPinKF;
+            } else {
+                kf->map_point[bestIdx] = pMP;                  // pMP->AddObservation(pKF, bestIdx); pKF->AddMapPoint(pMP, bestIdx)
+            }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
+// SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) :1006-1216.  matches12[kf1->n] in / out (map-point index of KF2 or -1);
+// idx_in_kf2[mps->m] = pMP->GetIndexInKeyFrame(pKF2) (-1 = not observed there).
+int orc_search_by_sim3(const orc_frame_view* kf1, const orc_frame_view* kf2, const orc_map_points* mps, int* matches12,
+                       const int* idx_in_kf2, float s12, const float* R12, const float* t12, float th) {
+    const float fx = kf1->fx, fy = kf1->fy, cx = kf1->cx, cy = kf1->cy;            // pKF1's intrinsics in BOTH directions, as upstream
+    float sR12[9], sR21[9], t21[3], nsR21[9];
+    const double inv_s = 1.0 / s12;
+    for (int i = 0; i < 9; i++) sR12[i] = (float)(R12[i] * (double)s12);           // s12 * R12
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) sR21[3 * i + j] = (float)(R12[3 * j + i] * inv_s);   // (1.0 / s12) * R12.t()
+    for (int i = 0; i < 9; i++) nsR21[i] = (float)(sR21[i] * -1.0);
+    mat33_vec(nsR21, t12, t21);                                                    // -sR21 * t12
+    const int N1 = kf1->n, N2 = kf2->n;
+    std::vector<char> am1(N1, 0), am2(N2, 0);
+    for (int i = 0; i < N1; i++) {
+        const int pMP = matches12[i];
+        if (pMP >= 0) {
+            am1[i] = 1;
+            const int idx2 = idx_in_kf2[pMP];
+            if (idx2 >= 0 && idx2 < N2) am2[idx2] = 1;
+        }
+    }
+    std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1);
+    Grid g1(kf1), g2(kf2);
+    auto one_way = [&](const orc_frame_view* from, const orc_frame_view* to, const Grid& gto, const std::vector<char>& am, const float* sR,
+                       const float* tt, std::vector<int>& out) {
+        for (int i = 0; i < from->n; i++) {
+            const int pMP = from->map_point[i];
+            if (pMP < 0 || am[i]) continue;
+            if (mp_bad(mps, pMP)) continue;
+            const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+            float pa[3], pb[3];
+            mat33_vec(from->Rcw, Pw, pa);
+            for (int k = 0; k < 3; k++) pa[k] = pa[k] + from->tcw[k];
+            mat33_vec(sR, pa, pb);
+            for (int k = 0; k < 3; k++) pb[k] = pb[k] + tt[k];
+            if (pb[2] < 0.0) continue;
+            const float invz = (float)(1.0 / pb[2]);
+            const float x = pb[0] * invz, y = pb[1] * invz;
+            const float u = fx * x + cx, v = fy * y + cy;
+            if (!kf_is_in_image(to, u, v)) continue;
+            const float maxDistance = 1.2f * mps->max_dist[pMP], minDistance = 0.8f * mps->min_dist[pMP];
+            const float dist3D = norm3(pb);
+            if (dist3D < minDistance || dist3D > maxDistance) continue;
+            const int lvl = predict_scale(mps->max_dist[pMP], dist3D, to);
+            const float radius = th * to->scale_factors[lvl];
+            const std::vector<int> cand = features_in_area(to, gto, u, v, radius);
+            if (cand.empty()) continue;
+            const uint8_t* dMP = mps->desc + 32 * (size_t)pMP;
+            int bestDist = INT_MAX, bestIdx = -1;
+            for (int idx : cand) {
+                const int o = to->keys[idx].octave;
+                if (o < lvl - 1 || o > lvl) continue;
+                const int d = descriptor_distance(dMP, to->desc + 32 * (size_t)idx);
+                if (d < bestDist) { bestDist = d; bestIdx = idx; }
+            }
+            if (bestDist <= TH_HIGH) out[i] = bestIdx;
+        }
+    };
+    one_way(kf1, kf2, g2, am1, sR21, t21, vnMatch1);
+    one_way(kf2, kf1, g1, am2, sR12, t12, vnMatch2);
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = vnMatch1[i1];
+        if (idx2 >= 0 && vnMatch2[idx2] == i1) { matches12[i1] = kf2->map_point[idx2]; nFound++; }
+    }
+    return nFound;
+}
+
+}  // extern "C"

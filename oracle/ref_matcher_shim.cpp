@@ -97,6 +97,7 @@ struct Points {
         for (size_t i = 0; i < mp.size(); i++) {
             MapPoint &m = mp[i];
             if (p->world_pos) m.mWorldPos = Vector3f(p->world_pos[3 * i], p->world_pos[3 * i + 1], p->world_pos[3 * i + 2]);
+            if (p->normal) m.mNormalVector = Vector3f(p->normal[3 * i], p->normal[3 * i + 1], p->normal[3 * i + 2]);
             m.mDescriptor = cv::Mat(1, 32, CV_8U);
             if (p->desc) std::memcpy(m.mDescriptor.data, p->desc + 32 * i, 32);
             m.mbBad = p->bad ? p->bad[i] != 0 : false;
@@ -452,6 +453,64 @@ int adp_sia_run(const orc_sia_problem *p, int max_level, int min_level, int n_it
     const size_t n = align.run(&R, &Cf, TCR);
     ygz::b200::pose_to_qt(TCR, out_q, out_t);
     return (int) n;
+}
+
+}  // extern "C"
+#endif
+
+#ifndef SHIM_USE_ADAPTERS
+// ---- the Sim3 family of the back end (cv::Mat geometry): SearchByProjection(KF, Scw, ...) :265, Fuse(KF, Scw, ...) :888, SearchBySim3 :1006
+namespace {
+cv::Mat mat_from(const float *v, int r, int c) {
+    cv::Mat m(r, c, CV_32F);
+    for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) m.at<float>(i, j) = v[i * c + j];
+    return m;
+}
+}  // namespace
+
+extern "C" {
+
+int refm_search_by_projection_sim3(const orc_frame_view *kf, const float *Scw, const orc_map_points *mps, const int *point_ids, int n_points,
+                                   int *matched, int th) {
+    Points P(mps);
+    KeyFrame *K = make_keyframe(kf, P);
+    std::vector<MapPoint *> pts(n_points), vpMatched(kf->n, nullptr);
+    for (int i = 0; i < n_points; i++) pts[i] = P.at(point_ids[i]);
+    for (int i = 0; i < kf->n; i++) vpMatched[i] = P.at(matched[i]);
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchByProjection(K, mat_from(Scw, 4, 4), pts, vpMatched, th);
+    store_map_points(vpMatched, P, matched);
+    delete K;
+    return n;
+}
+
+int refm_fuse_sim3(orc_frame_view *kf, const float *Scw, const orc_map_points *mps, const int *point_ids, int n_points, float th,
+                   int *replace_point) {
+    Points P(mps);
+    KeyFrame *K = make_keyframe(kf, P);
+    std::vector<MapPoint *> pts(n_points), rep(n_points, nullptr);
+    for (int i = 0; i < n_points; i++) { pts[i] = P.at(point_ids[i]); rep[i] = P.at(replace_point[i]); }
+    ORBmatcher m(0.8f);
+    const int n = m.Fuse(K, mat_from(Scw, 4, 4), pts, th, rep);
+    store_map_points(rep, P, replace_point);
+    store_map_points(K->mvpMapPoints, P, kf->map_point);
+    delete K;
+    return n;
+}
+
+int refm_search_by_sim3(const orc_frame_view *kf1, const orc_frame_view *kf2, const orc_map_points *mps, int *matches12, const int *idx_in_kf2,
+                        float s12, const float *R12, const float *t12, float th) {
+    Points P(mps);
+    KeyFrame *K1 = make_keyframe(kf1, P), *K2 = make_keyframe(kf2, P);
+    for (size_t i = 0; i < P.mp.size(); i++)
+        if (idx_in_kf2[i] >= 0) P.mp[i].mObservations[K2] = (size_t) idx_in_kf2[i];
+    std::vector<MapPoint *> vp(kf1->n, nullptr);
+    for (int i = 0; i < kf1->n; i++) vp[i] = P.at(matches12[i]);
+    ORBmatcher m(0.75f, true);
+    const int n = m.SearchBySim3(K1, K2, vp, s12, mat_from(R12, 3, 3), mat_from(t12, 3, 1), th);
+    store_map_points(vp, P, matches12);
+    delete K1; delete K2;
+    return n;
 }
 
 }  // extern "C"

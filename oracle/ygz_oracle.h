@@ -89,6 +89,7 @@ typedef struct {
     const float* track_proj_xr;
     const int* track_scale_level;
     const float* track_view_cos;
+    const float* normal;            /* m x 3, GetNormal (the Sim3 searches; NULL elsewhere) */
 } orc_map_points;
 
 /* ---- ORBmatcher (src/ORBmatcher.cc).  All return nmatches like the reference. */
@@ -114,6 +115,16 @@ int orc_search_by_bow_kf(float nnratio, int check_ori, const orc_frame_view* kf1
  * (:603-609); level_sigma2 = pKF2->mvLevelSigma2; pairs = (idx1, idx2) in ascending idx1 (capacity kf1->n). */
 int orc_search_for_triangulation(int check_ori, const orc_frame_view* kf1, const orc_frame_view* kf2, const float* F12,
                                  float ex, float ey, const float* level_sigma2, int only_stereo, int* pairs);
+/* The Sim3 family of the back end (cv::Mat geometry; point_ids index the map-point table, which must carry `normal`):
+ * SearchByProjection(KF, Scw, vpPoints, vpMatched, th) :265-373 — Scw 4x4 row-major, matched[kf->n] in / out */
+int orc_search_by_projection_sim3(const orc_frame_view* kf, const float* Scw, const orc_map_points* mps, const int* point_ids, int n_points,
+                                  int* matched, int th);
+/* Fuse(KF, Scw, vpPoints, th, vpReplacePoint) :888-1004 — kf->map_point in / out (AddMapPoint), replace_point[n_points] in / out */
+int orc_fuse_sim3(orc_frame_view* kf, const float* Scw, const orc_map_points* mps, const int* point_ids, int n_points, float th,
+                  int* replace_point);
+/* SearchBySim3(KF1, KF2, vpMatches12, s12, R12, t12, th) :1006-1216 — idx_in_kf2[m] = GetIndexInKeyFrame(pKF2) */
+int orc_search_by_sim3(const orc_frame_view* kf1, const orc_frame_view* kf2, const orc_map_points* mps, int* matches12,
+                       const int* idx_in_kf2, float s12, const float* R12, const float* t12, float th);
 /* ComputeThreeMaxima :1471-1502 */
 void orc_three_maxima(const int* hist_sizes, int L, int* ind1, int* ind2, int* ind3);
 /* Frame::GetFeaturesInArea src/Frame.cc:424-481 (grid built as AssignFeaturesToGrid :314-330) */

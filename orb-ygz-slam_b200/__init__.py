@@ -49,7 +49,7 @@ class MapPoints(C.Structure):
     _fields_ = [("m", C.c_int), ("world_pos", f32p), ("desc", u8p), ("bad", u8p), ("observations", i32p),
                 ("min_dist", f32p), ("max_dist", f32p), ("track_in_view", u8p), ("track_proj_x", f32p),
                 ("track_proj_y", f32p), ("track_proj_xr", f32p), ("track_scale_level", i32p),
-                ("track_view_cos", f32p)]
+                ("track_view_cos", f32p), ("normal", f32p)]
 
 
 class SiaProblem(C.Structure):
@@ -102,6 +102,7 @@ ABI_SYMBOLS = [
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
     "ygz_stereo_batch", "ygz_stereo_batch_async", "ygz_stereo_frontend_time",
+    "ygz_search_by_projection_sim3", "ygz_fuse_sim3", "ygz_search_by_sim3",
     "ygz_search_by_projection_last_batch", "ygz_search_by_projection_points_batch", "ygz_search_by_projection_batch_time",
     "ygz_vocab_load", "ygz_vocab_from_memory", "ygz_vocab_destroy", "ygz_vocab_info", "ygz_vocab_transform", "ygz_vocab_transform_orb",
 ]
@@ -163,6 +164,9 @@ def lib():
     sigs.setdefault('ygz_search_for_initialization', {})['argtypes'] = [C.c_void_p, C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView), f32p, i32p, C.c_int]
     sigs.setdefault('ygz_search_by_bow_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, i32p, i32p, C.c_int, u32p, i32p, i32p]
     sigs.setdefault('ygz_compute_stereo_matches', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p]
+    sigs.setdefault('ygz_search_by_projection_sim3', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), f32p, C.POINTER(MapPoints), i32p, C.c_int, i32p, C.c_int]
+    sigs.setdefault('ygz_fuse_sim3', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), f32p, C.POINTER(MapPoints), i32p, C.c_int, C.c_float, i32p]
+    sigs.setdefault('ygz_search_by_sim3', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), i32p, i32p, C.c_float, f32p, f32p, C.c_float]
     sigs.setdefault('ygz_search_by_projection_last_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.POINTER(ProjectionCamera), C.c_int, i32p, i32p, f32p, u8p, f32p, u8p, f32p,
                                                                             C.c_float, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]
     sigs.setdefault('ygz_search_by_projection_points_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.POINTER(ProjectionCamera), C.c_int, i32p, C.c_int, f32p, f32p, f32p, f32p,
@@ -463,7 +467,7 @@ def make_frame_view(keys, desc, map_point=None, u_right=None, outlier=None, K=(4
     return k
 
 
-def make_map_points(world_pos, desc, bad=None, observations=None, min_dist=None, max_dist=None, track=None, cls=None):
+def make_map_points(world_pos, desc, bad=None, observations=None, min_dist=None, max_dist=None, track=None, cls=None, normal=None):
     cls = cls or MapPoints
     m = len(world_pos)
     v = cls()
@@ -490,6 +494,7 @@ def make_map_points(world_pos, desc, bad=None, observations=None, min_dist=None,
     opt("track_proj_xr", track.get("xr", np.zeros(m)), np.float32, f32p)
     opt("track_scale_level", track.get("level", np.zeros(m)), np.int32, i32p)
     opt("track_view_cos", track.get("view_cos", np.ones(m)), np.float32, f32p)
+    opt("normal", normal, np.float32, f32p)
     return _Keep(v, refs)
 
 

@@ -1284,3 +1284,224 @@ int ygz_search_by_projection_batch_time(ygz_matcher* h, ygz_orb* orb, int iters,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// The Sim3 family of the back end (loop closing), src/ORBmatcher.cc:265-373 (SearchByProjection(KF, Scw, ...)), :888-1004
+// (Fuse(KF, Scw, ...)), :1006-1216 (SearchBySim3).  Same pattern as the front-end searches: the host projects the points (CV_32F
+// cv::Mat algebra upstream: a product accumulates in double and rounds once) and enumerates the window candidates, ONE launch of
+// k_hamming_pairs computes every candidate distance, the order-dependent decisions follow on the host in the reference's order.
+namespace {
+struct SimCamH { float R[9], t[3], Ow[3]; };
+inline void mat33_vec_h(const float* R, const float* p, float* o) {
+    for (int i = 0; i < 3; i++) { double a = 0; for (int k = 0; k < 3; k++) a += (double)R[3 * i + k] * p[k]; o[i] = (float)a; }
+}
+inline float norm3_h(const float* p) { double a = 0; for (int k = 0; k < 3; k++) a += (double)p[k] * p[k]; return (float)std::sqrt(a); }
+inline double dot3_h(const float* a, const float* b) { double r = 0; for (int k = 0; k < 3; k++) r += (double)a[k] * b[k]; return r; }
+void decompose_scw_h(const float* S, SimCamH& C) {          // :274-278
+    double d = 0;
+    for (int k = 0; k < 3; k++) d += (double)S[k] * S[k];
+    const float scw = (float)std::sqrt(d);
+    const double inv = 1.0 / scw;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.R[3 * i + j] = (float)(S[4 * i + j] * inv);
+    for (int i = 0; i < 3; i++) C.t[i] = (float)(S[4 * i + 3] * inv);
+    float nRt[9];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) nRt[3 * i + j] = (float)(C.R[3 * j + i] * -1.0);
+    mat33_vec_h(nRt, C.t, C.Ow);
+}
+inline int predict_scale_h(float max_dist_raw, float dist, const ygz_frame_view* kf) {     // MapPoint::PredictScale, src/MapPoint.cc:343-357
+    const float ratio = max_dist_raw / dist;
+    int l = (int)std::ceil(std::log(ratio) / kf->log_scale_factor);
+    if (l < 0) l = 0; else if (l >= kf->n_levels) l = kf->n_levels - 1;
+    return l;
+}
+inline bool in_image_h(const ygz_frame_view* kf, float x, float y) {                        // KeyFrame::IsInImage (integer bounds)
+    return x >= (int)kf->min_x && x < (int)kf->max_x && y >= (int)kf->min_y && y < (int)kf->max_y;
+}
+struct SimJob { int q, pMP, level, first, count; };
+// project map point pMP through (R, t) [+ the depth / angle gates when Ow is given], predict its level, list the window candidates
+// of `kf` (level band [l-1, l]) into (pq, pt).  invz_double: `1.0 / z` (Fuse, SearchBySim3) vs `1 / z` (SearchByProjection).
+bool sim_candidates(const ygz_frame_view* kf, const Grid& g, const ygz_map_points* mps, int pMP, const float* pc, float fx, float fy,
+                    float cx, float cy, const float* Ow, bool invz_double, float th, std::vector<int>& cand, int* level_out) {
+    const float invz = invz_double ? (float)(1.0 / pc[2]) : 1 / pc[2];
+    const float x = pc[0] * invz, y = pc[1] * invz;
+    const float u = fx * x + cx, v = fy * y + cy;
+    if (!in_image_h(kf, u, v)) return false;
+    const float maxDistance = 1.2f * mps->max_dist[pMP], minDistance = 0.8f * mps->min_dist[pMP];
+    float dist;
+    if (Ow) {
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        float PO[3];
+        for (int k = 0; k < 3; k++) PO[k] = Pw[k] - Ow[k];
+        dist = norm3_h(PO);
+        if (dist < minDistance || dist > maxDistance) return false;
+        if (dot3_h(PO, mps->normal + 3 * (size_t)pMP) < 0.5 * dist) return false;       // viewing angle below 60 degrees
+    } else {
+        dist = norm3_h(pc);
+        if (dist < minDistance || dist > maxDistance) return false;
+    }
+    const int lvl = predict_scale_h(mps->max_dist[pMP], dist, kf);
+    const float radius = th * kf->scale_factors[lvl];
+    std::vector<int> all;
+    features_in_area(kf, g, u, v, radius, -1, -1, all);
+    cand.clear();
+    for (int idx : all) {
+        const int o = kf->keys[idx].octave;
+        if (o < lvl - 1 || o > lvl) continue;
+        cand.push_back(idx);
+    }
+    *level_out = lvl;
+    return !cand.empty();
+}
+}  // namespace
+
+extern "C" {
+
+int ygz_search_by_projection_sim3(ygz_matcher* h, const ygz_frame_view* kf, const float* Scw, const ygz_map_points* mps, const int* point_ids,
+                                  int n_points, int* matched, int th) {
+    YGZ_ARG_CHECK(h && kf && Scw && mps && mps->normal && matched && (n_points == 0 || point_ids));
+    SimCamH C;
+    decompose_scw_h(Scw, C);
+    std::vector<char> already(mps->m, 0);
+    for (int i = 0; i < kf->n; i++) if (matched[i] >= 0) { YGZ_ARG_CHECK(matched[i] < mps->m); already[matched[i]] = 1; }
+    Grid g(kf);
+    std::vector<SimJob> jobs;
+    std::vector<int> pq, pt, cand;
+    for (int i = 0; i < n_points; i++) {
+        const int pMP = point_ids[i];
+        YGZ_ARG_CHECK(pMP >= 0 && pMP < mps->m);
+        if (mp_bad(mps, pMP) || already[pMP]) continue;
+        float pc[3];
+        mat33_vec_h(C.R, mps->world_pos + 3 * (size_t)pMP, pc);
+        for (int k = 0; k < 3; k++) pc[k] = pc[k] + C.t[k];
+        if (pc[2] < 0.0) continue;
+        int lvl;
+        if (!sim_candidates(kf, g, mps, pMP, pc, kf->fx, kf->fy, kf->cx, kf->cy, C.Ow, false, (float)th, cand, &lvl)) continue;
+        jobs.push_back(SimJob{i, pMP, lvl, (int)pq.size(), (int)cand.size()});
+        for (int idx : cand) { pq.push_back(pMP); pt.push_back(idx); }
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, mps->desc, mps->m, kf->desc, kf->n, pq, pt, dist);
+    if (rc) return rc;
+    int nmatches = 0;
+    for (const SimJob& j : jobs) {
+        int bestDist = 256, bestIdx = -1;
+        for (int p = j.first; p < j.first + j.count; p++) {
+            if (matched[pt[p]] >= 0) continue;                  // vpMatched[idx] set by an earlier point of this very loop, too
+            if (dist[p] < bestDist) { bestDist = dist[p]; bestIdx = pt[p]; }
+        }
+        if (bestDist <= TH_LOW) { matched[bestIdx] = j.pMP; nmatches++; }
+    }
+    return nmatches;
+}
+
+int ygz_fuse_sim3(ygz_matcher* h, ygz_frame_view* kf, const float* Scw, const ygz_map_points* mps, const int* point_ids, int n_points,
+                  float th, int* replace_point) {
+    YGZ_ARG_CHECK(h && kf && Scw && mps && mps->normal && kf->map_point && replace_point && (n_points == 0 || point_ids));
+    SimCamH C;
+    decompose_scw_h(Scw, C);
+    std::vector<char> already(mps->m, 0);                       // pKF->GetMapPoints() at entry
+    for (int i = 0; i < kf->n; i++) if (kf->map_point[i] >= 0 && !mp_bad(mps, kf->map_point[i])) already[kf->map_point[i]] = 1;
+    Grid g(kf);
+    std::vector<SimJob> jobs;
+    std::vector<int> pq, pt, cand;
+    for (int i = 0; i < n_points; i++) {
+        const int pMP = point_ids[i];
+        YGZ_ARG_CHECK(pMP >= 0 && pMP < mps->m);
+        if (mp_bad(mps, pMP) || already[pMP]) continue;
+        float pc[3];
+        mat33_vec_h(C.R, mps->world_pos + 3 * (size_t)pMP, pc);
+        for (int k = 0; k < 3; k++) pc[k] = pc[k] + C.t[k];
+        if (pc[2] < 0.0f) continue;
+        int lvl;
+        if (!sim_candidates(kf, g, mps, pMP, pc, kf->fx, kf->fy, kf->cx, kf->cy, C.Ow, true, th, cand, &lvl)) continue;
+        jobs.push_back(SimJob{i, pMP, lvl, (int)pq.size(), (int)cand.size()});
+        for (int idx : cand) { pq.push_back(pMP); pt.push_back(idx); }
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, mps->desc, mps->m, kf->desc, kf->n, pq, pt, dist);
+    if (rc) return rc;
+    int nFused = 0;
+    for (const SimJob& j : jobs) {
+        int bestDist = INT_MAX, bestIdx = -1;
+        for (int p = j.first; p < j.first + j.count; p++)
+            if (dist[p] < bestDist) { bestDist = dist[p]; bestIdx = pt[p]; }
+        if (bestDist <= TH_LOW) {
+            const int pMPinKF = kf->map_point[bestIdx];
+            if (pMPinKF >= 0) {
+                if (!mp_bad(mps, pMPinKF)) replace_point[j.q] = pMPinKF;
+            } else {
+                kf->map_point[bestIdx] = j.pMP;                 // AddObservation + AddMapPoint: the slot is taken for the points that follow
+            }
+            nFused++;
+        }
+    }
+    return nFused;
+}
+
+int ygz_search_by_sim3(ygz_matcher* h, const ygz_frame_view* kf1, const ygz_frame_view* kf2, const ygz_map_points* mps, int* matches12,
+                       const int* idx_in_kf2, float s12, const float* R12, const float* t12, float th) {
+    YGZ_ARG_CHECK(h && kf1 && kf2 && mps && matches12 && idx_in_kf2 && R12 && t12 && kf1->map_point && kf2->map_point && s12 > 0.f);
+    const float fx = kf1->fx, fy = kf1->fy, cx = kf1->cx, cy = kf1->cy;          // pKF1's intrinsics in both directions, as upstream
+    float sR12[9], sR21[9], nsR21[9], t21[3];
+    const double inv_s = 1.0 / s12;
+    for (int i = 0; i < 9; i++) sR12[i] = (float)(R12[i] * (double)s12);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) sR21[3 * i + j] = (float)(R12[3 * j + i] * inv_s);
+    for (int i = 0; i < 9; i++) nsR21[i] = (float)(sR21[i] * -1.0);
+    mat33_vec_h(nsR21, t12, t21);
+    const int N1 = kf1->n, N2 = kf2->n;
+    std::vector<char> am1(N1, 0), am2(N2, 0);
+    for (int i = 0; i < N1; i++) {
+        const int pMP = matches12[i];
+        if (pMP >= 0) {
+            YGZ_ARG_CHECK(pMP < mps->m);
+            am1[i] = 1;
+            const int i2 = idx_in_kf2[pMP];
+            if (i2 >= 0 && i2 < N2) am2[i2] = 1;
+        }
+    }
+    Grid g1(kf1), g2(kf2);
+    // both directions are independent per point: enumerate all candidates, one distance launch per direction
+    auto one_way = [&](const ygz_frame_view* from, const ygz_frame_view* to, const Grid& gto, const std::vector<char>& am, const float* sR,
+                       const float* tt, std::vector<int>& out) -> int {
+        std::vector<SimJob> jobs;
+        std::vector<int> pq, pt, cand;
+        for (int i = 0; i < from->n; i++) {
+            const int pMP = from->map_point[i];
+            if (pMP < 0 || am[i]) continue;
+            if (pMP >= mps->m) { set_last_error("map point index out of range"); return YGZ_ERR_ARG; }
+            if (mp_bad(mps, pMP)) continue;
+            float pa[3], pb[3];
+            mat33_vec_h(from->Rcw, mps->world_pos + 3 * (size_t)pMP, pa);
+            for (int k = 0; k < 3; k++) pa[k] = pa[k] + from->tcw[k];
+            mat33_vec_h(sR, pa, pb);
+            for (int k = 0; k < 3; k++) pb[k] = pb[k] + tt[k];
+            if (pb[2] < 0.0) continue;
+            int lvl;
+            if (!sim_candidates(to, gto, mps, pMP, pb, fx, fy, cx, cy, nullptr, true, th, cand, &lvl)) continue;
+            jobs.push_back(SimJob{i, pMP, lvl, (int)pq.size(), (int)cand.size()});
+            for (int idx : cand) { pq.push_back(pMP); pt.push_back(idx); }
+        }
+        std::vector<int> dist;
+        int rc = pair_distances(h, mps->desc, mps->m, to->desc, to->n, pq, pt, dist);
+        if (rc) return rc;
+        for (const SimJob& j : jobs) {
+            int bestDist = INT_MAX, bestIdx = -1;
+            for (int p = j.first; p < j.first + j.count; p++)
+                if (dist[p] < bestDist) { bestDist = dist[p]; bestIdx = pt[p]; }
+            if (bestDist <= TH_HIGH) out[j.q] = bestIdx;
+        }
+        return YGZ_OK;
+    };
+    std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1);
+    int rc;
+    if ((rc = one_way(kf1, kf2, g2, am1, sR21, t21, vnMatch1))) return rc;
+    if ((rc = one_way(kf2, kf1, g1, am2, sR12, t12, vnMatch2))) return rc;
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int i2 = vnMatch1[i1];
+        if (i2 >= 0 && vnMatch2[i2] == i1) { matches12[i1] = kf2->map_point[i2]; nFound++; }
+    }
+    return nFound;
+}
+
+}  // extern "C"

@@ -39,7 +39,7 @@ class MapPoints(C.Structure):
     _fields_ = [("m", C.c_int), ("world_pos", f32p), ("desc", u8p), ("bad", u8p), ("observations", i32p),
                 ("min_dist", f32p), ("max_dist", f32p), ("track_in_view", u8p), ("track_proj_x", f32p),
                 ("track_proj_y", f32p), ("track_proj_xr", f32p), ("track_scale_level", i32p),
-                ("track_view_cos", f32p)]
+                ("track_view_cos", f32p), ("normal", f32p)]
 
 
 class SiaProblem(C.Structure):
@@ -103,6 +103,9 @@ def lib(native=False):
     L.orc_search_for_initialization.argtypes = [C.c_float, C.c_int, C.POINTER(FrameView), C.POINTER(FrameView),
                                                 f32p, i32p, C.c_int]
     L.orc_three_maxima.argtypes = [i32p, C.c_int, i32p, i32p, i32p]
+    L.orc_search_by_projection_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int]
+    L.orc_fuse_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
+    L.orc_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, i32p, C.c_float, f32p, f32p, C.c_float]
     L.orc_features_in_area.argtypes = [C.POINTER(FrameView), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                        i32p, C.c_int]
     L.orc_bf_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p]

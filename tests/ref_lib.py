@@ -264,3 +264,15 @@ def compute_stereo_matches(pyrL, pyrR, keysL, descL, keysR, descR, scale, inv_sc
                                        keysL.ctypes.data, descL.ctypes.data, len(keysL), keysR.ctypes.data, descR.ctypes.data, len(keysR),
                                        _ptr(scale, f32p), _ptr(inv_scale, f32p), float(mb), float(mbf), _ptr(u, f32p), _ptr(z, f32p))
     return u, z, n
+
+
+def matcher_sim3_lib():
+    """The Sim3-family entry points of oracle/_ref/libmatcher_ref.so (SearchByProjection(KF, Scw), Fuse(KF, Scw), SearchBySim3)."""
+    L = matcher_lib()
+    if L is None:
+        return None
+    i32p = C.POINTER(C.c_int)
+    L.refm_search_by_projection_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int]
+    L.refm_fuse_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
+    L.refm_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, i32p, C.c_float, f32p, f32p, C.c_float]
+    return L
