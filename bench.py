@@ -369,7 +369,7 @@ def aux_metrics(m, device):
             lv = m.make_frame_view(ka, da, map_point=np.arange(len(ka), dtype=np.int32), K=K4, scale_factors=sc, cls=O.FrameView)
             mp = m.make_map_points(wp[last[p_]][:len(ka)], da, cls=O.MapPoints)
             on = O.lib().orc_search_by_projection_last(1, cv.ptr(), lv.ptr(), mp.ptr(), 15.0, 1, 1)
-            same = same and on == nm[p_] and bool((cv.map_point == out[p_, :len(kb)]).all())
+            same = bool(same and int(on) == int(nm[p_]) and bool((cv.map_point == out[p_, :len(kb)]).all()))
             npairs += 1
         cpu_ms = (_t.perf_counter() - t0) / npairs * 1e3
         aux["projection_last_batch_c2plus"] = {"pairs_per_launch": Bp, "ms_per_launch": ms, "frame_pairs_per_s": Bp / (ms / 1e3),
@@ -454,8 +454,17 @@ def workload_config(batch):
 _JSON_FD = None
 
 
+def _json_default(o):
+    """numpy scalars / arrays that slip into the line (a numpy.bool_ once broke the whole bench line)"""
+    if isinstance(o, np.generic):
+        return o.item()
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    return str(o)
+
+
 def emit_json(obj):
-    line = (json.dumps(obj) + "\n").encode()
+    line = (json.dumps(obj, default=_json_default) + "\n").encode()
     sys.stdout.flush()
     if _JSON_FD is None:
         os.write(1, line)
