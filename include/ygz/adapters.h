@@ -15,6 +15,7 @@
 //   ORBmatcher::SearchForInitialization(Frame&, Frame&, std::vector<cv::Point2f>&, std::vector<int>&, int)  :103
 //   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, Matrix3f&, vector<pair<size_t,size_t>>&, bool) :108
 //   ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&)                                          :47
+//   ORBmatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, ...) / Fuse(KeyFrame*, cv::Mat Scw, ...) / SearchBySim3     :66, :123, :113
 //   SparseImgAlign::run(Frame*, Frame*, SE3f&)                                                              include/SparseImageAlign.h:33
 //
 // The classes are templates over the SLAM types (duck-typed: only the members the reference methods themselves touch are
@@ -354,6 +355,64 @@ public:
         vMatchedPairs.clear();
         vMatchedPairs.reserve(n);
         for (int i = 0; i < n; i++) vMatchedPairs.push_back(std::make_pair((size_t)pairs[2 * i], (size_t)pairs[2 * i + 1]));
+        return n;
+    }
+
+    // ---- the Sim3 family of the back end (LoopClosing.cc).  Scw / R12 / t12 are CV_32F cv::Mat upstream: any type with rows, cols and at<float>().
+    template <class Mat> static void mat_to_floats(const Mat& m, int r, int c, float* out) {
+        for (int i = 0; i < r; i++) for (int j = 0; j < c; j++) out[i * c + j] = m.template at<float>(i, j);
+    }
+    // SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, vector<MapPoint*>& vpMatched, int th)  :265-373
+    template <class Mat>
+    int SearchByProjection(KeyFrame* pKF, Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th) {
+        Table T; Gather gk;
+        gk.keyframe(pKF, T);
+        std::vector<int> ids, matched(pKF->N > 0 ? pKF->N : 1, -1);
+        ids.reserve(vpPoints.size());
+        for (MapPoint* p : vpPoints) ids.push_back(T.add(p));
+        for (int i = 0; i < pKF->N && i < (int)vpMatched.size(); i++) matched[i] = T.add(vpMatched[i]);
+        float S[16];
+        mat_to_floats(Scw, 4, 4, S);
+        const ygz_map_points mps = T.view();
+        const int n = ok(ygz_search_by_projection_sim3(h_, &gk.v, S, &mps, ids.data(), (int)ids.size(), matched.data(), th));
+        for (int i = 0; i < pKF->N && i < (int)vpMatched.size(); i++) vpMatched[i] = T.at(matched[i]);
+        return n;
+    }
+    // Fuse(KeyFrame* pKF, cv::Mat Scw, const vector<MapPoint*>& vpPoints, float th, vector<MapPoint*>& vpReplacePoint)  :888-1004
+    template <class Mat>
+    int Fuse(KeyFrame* pKF, Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {
+        Table T; Gather gk;
+        gk.keyframe(pKF, T);
+        std::vector<int> ids, rep(vpPoints.size() ? vpPoints.size() : 1, -1);
+        ids.reserve(vpPoints.size());
+        for (MapPoint* p : vpPoints) ids.push_back(T.add(p));
+        for (size_t i = 0; i < vpPoints.size() && i < vpReplacePoint.size(); i++) rep[i] = T.add(vpReplacePoint[i]);
+        const std::vector<int> before = gk.mp;
+        float S[16];
+        mat_to_floats(Scw, 4, 4, S);
+        const ygz_map_points mps = T.view();
+        const int n = ok(ygz_fuse_sim3(h_, &gk.v, S, &mps, ids.data(), (int)ids.size(), th, rep.data()));
+        for (size_t i = 0; i < vpPoints.size() && i < vpReplacePoint.size(); i++) vpReplacePoint[i] = T.at(rep[i]);
+        for (int i = 0; i < pKF->N; i++)                       // slots the search filled: the two calls of :996-997, in slot order
+            if (gk.mp[i] != before[i] && gk.mp[i] >= 0) { T.at(gk.mp[i])->AddObservation(pKF, (size_t)i); pKF->AddMapPoint(T.at(gk.mp[i]), (size_t)i); }
+        return n;
+    }
+    // SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, float th)  :1006-1216
+    template <class Mat>
+    int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const Mat& R12, const Mat& t12, const float th) {
+        Table T; Gather g1, g2;
+        g1.keyframe(pKF1, T);
+        g2.keyframe(pKF2, T);
+        std::vector<int> m12(pKF1->N > 0 ? pKF1->N : 1, -1);
+        for (int i = 0; i < pKF1->N && i < (int)vpMatches12.size(); i++) m12[i] = T.add(vpMatches12[i]);
+        std::vector<int> idx2(T.pts.size() ? T.pts.size() : 1, -1);
+        for (size_t i = 0; i < T.pts.size(); i++) idx2[i] = T.pts[i]->GetIndexInKeyFrame(pKF2);
+        float R[9], t[3];
+        mat_to_floats(R12, 3, 3, R);
+        mat_to_floats(t12, 3, 1, t);
+        const ygz_map_points mps = T.view();
+        const int n = ok(ygz_search_by_sim3(h_, &g1.v, &g2.v, &mps, m12.data(), idx2.data(), s12, R, t, th));
+        for (int i = 0; i < pKF1->N && i < (int)vpMatches12.size(); i++) vpMatches12[i] = T.at(m12[i]);
         return n;
     }
 

@@ -458,7 +458,6 @@ int adp_sia_run(const orc_sia_problem *p, int max_level, int min_level, int n_it
 }  // extern "C"
 #endif
 
-#ifndef SHIM_USE_ADAPTERS
 // ---- the Sim3 family of the back end (cv::Mat geometry): SearchByProjection(KF, Scw, ...) :265, Fuse(KF, Scw, ...) :888, SearchBySim3 :1006
 namespace {
 cv::Mat mat_from(const float *v, int r, int c) {
@@ -470,7 +469,7 @@ cv::Mat mat_from(const float *v, int r, int c) {
 
 extern "C" {
 
-int refm_search_by_projection_sim3(const orc_frame_view *kf, const float *Scw, const orc_map_points *mps, const int *point_ids, int n_points,
+int REFM(search_by_projection_sim3)(const orc_frame_view *kf, const float *Scw, const orc_map_points *mps, const int *point_ids, int n_points,
                                    int *matched, int th) {
     Points P(mps);
     KeyFrame *K = make_keyframe(kf, P);
@@ -484,7 +483,7 @@ int refm_search_by_projection_sim3(const orc_frame_view *kf, const float *Scw, c
     return n;
 }
 
-int refm_fuse_sim3(orc_frame_view *kf, const float *Scw, const orc_map_points *mps, const int *point_ids, int n_points, float th,
+int REFM(fuse_sim3)(orc_frame_view *kf, const float *Scw, const orc_map_points *mps, const int *point_ids, int n_points, float th,
                    int *replace_point) {
     Points P(mps);
     KeyFrame *K = make_keyframe(kf, P);
@@ -498,7 +497,7 @@ int refm_fuse_sim3(orc_frame_view *kf, const float *Scw, const orc_map_points *m
     return n;
 }
 
-int refm_search_by_sim3(const orc_frame_view *kf1, const orc_frame_view *kf2, const orc_map_points *mps, int *matches12, const int *idx_in_kf2,
+int REFM(search_by_sim3)(const orc_frame_view *kf1, const orc_frame_view *kf2, const orc_map_points *mps, int *matches12, const int *idx_in_kf2,
                         float s12, const float *R12, const float *t12, float th) {
     Points P(mps);
     KeyFrame *K1 = make_keyframe(kf1, P), *K2 = make_keyframe(kf2, P);
@@ -514,4 +513,3 @@ int refm_search_by_sim3(const orc_frame_view *kf1, const orc_frame_view *kf2, co
 }
 
 }  // extern "C"
-#endif

@@ -231,6 +231,9 @@ def adapters_lib():
     L.adp_extract_frame.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p, u8p, C.c_int, C.c_int, u8p]
     L.adp_sia_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p]
+    L.adp_search_by_projection_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int]
+    L.adp_fuse_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
+    L.adp_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, i32p, C.c_float, f32p, f32p, C.c_float]
     return L
 
 

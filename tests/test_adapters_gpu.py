@@ -182,3 +182,59 @@ def test_sia_adapter(adp, gpu, oracle, synth):
     assert an == n and n > 150
     assert S.pose_diff(q, t, aq, at) < 1e-4
     assert S.pose_diff(aq, at, s["q_true"], s["t_true"]) < 5e-3
+
+
+def test_sim3_family_adapters(adp, pkg, oracle, frames):
+    """SearchByProjection(KeyFrame*, cv::Mat Scw, ...), Fuse(KeyFrame*, cv::Mat Scw, ...), SearchBySim3 with the reference's signatures
+    (KeyFrame* / MapPoint* / cv::Mat in, AddObservation + AddMapPoint performed on the objects) vs the oracle."""
+    import test_ref_sim3 as S
+    (_, ka, da), (_, kb, db) = frames
+    rng = np.random.default_rng(11)
+    Rm = S.rot((0.2, 1.0, 0.1), 0.03); t = np.array([0.05, -0.02, 0.1])
+    Xw, nrm, mind, maxd = S.world_points(ka, Rm, t, rng, shift=(-9.0, -5.0))
+    m, extra, s, th = len(ka), 40, 1.3, 10
+    Xw2 = np.concatenate([Xw, np.zeros((extra, 3), np.float32)]); nrm2 = np.concatenate([nrm, np.zeros((extra, 3), np.float32)])
+    desc = np.concatenate([da, rng.integers(0, 256, (extra, 32), dtype=np.uint8)])
+    mps = pkg.make_map_points(Xw2, desc, bad=(rng.random(m + extra) < 0.05).astype(np.uint8), min_dist=np.r_[mind, np.ones(extra)],
+                              max_dist=np.r_[maxd, np.ones(extra)], normal=nrm2, cls=oracle.MapPoints)
+    Scw = np.eye(4, dtype=np.float32); Scw[:3, :3] = (s * Rm).astype(np.float32); Scw[:3, 3] = (s * t).astype(np.float32)
+    ids = rng.permutation(m).astype(np.int32)
+    slots = np.full(len(kb), -1, np.int32)
+    slots[::7] = m + rng.integers(0, extra, len(slots[::7]))
+    out = []
+    for L, pre in ((oracle.lib(), "orc_"), (adp, "adp_")):
+        kf = pkg.make_frame_view(kb, db, K=S.K, bounds=S.BOUNDS, scale_factors=H.SCALE8, cls=oracle.FrameView)
+        matched = slots.copy()
+        n1 = getattr(L, pre + "search_by_projection_sim3")(vp(kf), Scw.ctypes.data_as(oracle.f32p), vp(mps), ids.ctypes.data_as(oracle.i32p), m,
+                                                            matched.ctypes.data_as(oracle.i32p), th)
+        kf2 = pkg.make_frame_view(kb, db, map_point=slots.copy(), K=S.K, bounds=S.BOUNDS, scale_factors=H.SCALE8, cls=oracle.FrameView)
+        rep = np.full(m, -1, np.int32)
+        n2 = getattr(L, pre + "fuse_sim3")(vp(kf2), Scw.ctypes.data_as(oracle.f32p), vp(mps), ids.ctypes.data_as(oracle.i32p), m, C.c_float(5.0),
+                                           rep.ctypes.data_as(oracle.i32p))
+        out.append((n1, matched, n2, rep, kf2.map_point.copy()))
+    o, a = out
+    assert o[0] == a[0] and (o[1] == a[1]).all() and o[2] == a[2] and (o[3] == a[3]).all() and (o[4] == a[4]).all() and o[0] > 50 and o[2] > 50
+    # SearchBySim3
+    rng = np.random.default_rng(12)
+    R2 = S.rot((0.1, 1.0, 0.0), 0.01); t2 = np.array([-0.1, -0.05, 0.02])
+    n1, n2 = len(ka), len(kb)
+    X1, nr1, mi1, ma1 = S.world_points(ka, np.eye(3), np.zeros(3), rng)
+    X2, nr2, mi2, ma2 = S.world_points(kb, R2, t2, rng)
+    mps = pkg.make_map_points(np.concatenate([X1, X2]), np.concatenate([da, db]), bad=(rng.random(n1 + n2) < 0.04).astype(np.uint8),
+                              min_dist=np.r_[mi1, mi2] * 0.5, max_dist=np.r_[ma1, ma2] * 1.5, normal=np.concatenate([nr1, nr2]), cls=oracle.MapPoints)
+    mp1 = np.where(rng.random(n1) < 0.85, np.arange(n1), -1).astype(np.int32)
+    mp2 = np.where(rng.random(n2) < 0.85, n1 + np.arange(n2), -1).astype(np.int32)
+    R12 = R2.T.astype(np.float32); t12 = (-(R2.T @ t2)).astype(np.float32)
+    pre12 = np.full(n1, -1, np.int32)
+    pre12[::13] = n1 + rng.integers(0, n2, len(pre12[::13]))
+    idx2 = np.full(n1 + n2, -1, np.int32); idx2[n1:] = np.arange(n2)
+    out = []
+    for L, pre in ((oracle.lib(), "orc_"), (adp, "adp_")):
+        k1 = pkg.make_frame_view(ka, da, map_point=mp1, K=S.K, bounds=S.BOUNDS, scale_factors=H.SCALE8, cls=oracle.FrameView)
+        k2 = pkg.make_frame_view(kb, db, map_point=mp2, K=S.K, bounds=S.BOUNDS, scale_factors=H.SCALE8, Rcw=R2.astype(np.float32), tcw=t2.astype(np.float32),
+                                 cls=oracle.FrameView)
+        m12 = pre12.copy()
+        n = getattr(L, pre + "search_by_sim3")(vp(k1), vp(k2), vp(mps), m12.ctypes.data_as(oracle.i32p), idx2.ctypes.data_as(oracle.i32p), C.c_float(1.0),
+                                               R12.reshape(9).ctypes.data_as(oracle.f32p), t12.ctypes.data_as(oracle.f32p), C.c_float(7.5))
+        out.append((n, m12))
+    assert out[0][0] == out[1][0] and (out[0][1] == out[1][1]).all() and out[0][0] > 30
