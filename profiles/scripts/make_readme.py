@@ -21,7 +21,7 @@ def launches():
     out = []
     for r in rows[h + 1:]:
         if len(r) > mv:
-            out.append((r[kn].split("(")[0].split("::")[-1], r[gs], r[bs], float(r[mv].replace(",", "")) / 1e3))
+            out.append((r[kn].split("(")[0].split("::")[-1].split("<")[0], r[gs], r[bs], float(r[mv].replace(",", "")) / 1e3))
     return out
 
 
@@ -79,7 +79,11 @@ def main():
     r = b["roofline"]
     w("* roofline, dominant kernel `%s`: %.0f MB algorithmic per launch / %.3f ms = **%.0f GB/s = %.3f of the measured %.0f GB/s**; DRAM traffic %s; %s."
       % (r["kernel"], r["algorithmic_bytes_per_launch"] / 1e6, r["kernel_ms_per_launch"], r["achieved"], r["frac"], r["peak"],
-         ("%.0f MB" % (r["traffic"] / 1e6)) if r.get("traffic") else "n/a", r["limiter"]))
+         ("%.0f MB" % (r["traffic"] / 1e6)) if r.get("traffic") else
+         ("%.0f MB (profiles/kernel_metrics.json, captured in the same call after the bench line)" %
+          ((km["kernels"]["fast_cells"]["dram_bytes_read"] + km["kernels"]["fast_cells"]["dram_bytes_write"]) / 1e6)) if "fast_cells" in (km.get("kernels") or {}) else "n/a",
+         r["limiter"] if not r["limiter"].startswith("not profiled") else
+         "ncu: issue slots active %.0f %%, ALU pipe %.0f %%, LSU pipe %.0f %%" % tuple(km["kernels"]["fast_cells"][k] for k in ("issue_active_pct", "alu_pct", "lsu_pct"))))
     pf = r["pyramid_plus_fast"]
     w("* pyramid + FAST, strict accounting (every level read once): %.0f MB / %.3f ms = %.0f GB/s = **%.3f** of peak.\n" % (pf["strict_bytes_per_step"] / 1e6, pf["ms_per_step"], pf["achieved"], pf["frac"]))
     for wl, unit in (("c5", "stereo pairs/s"), ("c3", "alignments/s")):

@@ -19,12 +19,13 @@ UNIT = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1, "usecond": 1e3, "ms
 batch, out = int(sys.argv[1]), sys.argv[2]
 kernels = {}
 for rep in sys.argv[3:]:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep is read through ncu; a .csv is the raw page already exported (ncu -i rep --page raw --csv)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     kn = hdr.index("Kernel Name")
     for r in rows[2:]:
-        name = r[kn].split("(")[0].split("::")[-1]
+        name = r[kn].split("(")[0].split("::")[-1].split("<")[0]          # k_octree<4>, k_vocab_transform<10> -> base name
         st = STAGE.get(name)
         if not st:
             continue

@@ -7,4 +7,4 @@ ncu -i gpurun_out/${TAG}_full.ncu-rep --page source --csv -k regex:k_fast_cells_
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/${TAG}_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -2 gpurun_out/${TAG}_sanitizer_racecheck.log
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/${TAG}_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -1 gpurun_out/${TAG}_sanitizer_memcheck.log
 [ -n "$SKIP_C3C5" ] || bash profiles/scripts/run_c3c5.sh $TAG
-rm -f gpurun_out/${TAG}_full.ncu-rep gpurun_out/${TAG}_full_pyr.ncu-rep.bak
+
