@@ -181,8 +181,8 @@ def run_c5(args, B, ctx):
     ctr = exL.counters()
     ctr["matches"] = n_match
     ctr["elapsed_ns"] = int(ms_dev * 1e6)
-    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e])
-    t_dev, t_e = shard.timings_max(gathered, 2)
+    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e, t_orb])
+    t_dev, t_e, t_o = shard.timings_max(gathered, 3)
     if rank != 0:
         return
     total = world * B * args.steps
@@ -322,6 +322,22 @@ def run_c3(args, P, ctx):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    # tracker form: both frames were just extracted on this device, the aligner reads their pyramids in place (ygz_sia_run_orb)
+    ex = m.ORBextractor(100, 2.0, C3_LEVELS, 20, 7, width=C3_W, height=C3_H, max_batch=2 * nd, device=local)
+    ex.extract_batch([scenes[i // 2][3]["ref" if i % 2 == 0 else "cur"] for i in range(2 * nd)])
+    feats = [m.make_sia_features(scenes[i][3]["K"], scenes[i][3]["px"], scenes[i][3]["xyz"]) for i in range(nd)]
+    fbatch = [feats[i % nd] for i in range(P)]
+    rf = np.array([2 * (i % nd) for i in range(P)], np.int32)
+    cf = rf + 1
+    qo, to, _, nto = sia.run_batch_orb(ex, ex, fbatch, rf, cf)
+    orb_same = bool(np.array_equal(qo, q) and np.array_equal(to, t) and np.array_equal(nto, nt))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sia.run_batch_orb(ex, ex, fbatch, rf, cf)
+    torch.cuda.synchronize()
+    t_orb = time.perf_counter() - t0
+    barrier()
     clocks = sampler.finish()
     one = m.SparseImgAlign(C3_MAX, C3_MIN, C3_ITERS, device=local, max_problems=1, max_features=256, max_level_pixels=2 * C3_W * C3_H)
     one.run(probs[0])
@@ -329,8 +345,8 @@ def run_c3(args, P, ctx):
     shard = ctx["shard"]
     ctr = dict(frames=P * args.steps, keypoints=0, matches=0, sia_iters=gn_iters * args.steps, bytes_in=0, bytes_out=0,
                kernel_launches=args.steps, elapsed_ns=int(ms_dev * 1e6))
-    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e])
-    t_dev, t_e = shard.timings_max(gathered, 2)
+    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e, t_orb])
+    t_dev, t_e, t_o = shard.timings_max(gathered, 3)
     if rank != 0:
         return
     total = world * P * args.steps
@@ -348,6 +364,12 @@ def run_c3(args, P, ctx):
         "e2e": {"value": total / t_e, "unit": "alignments/s", "h2d_bytes_per_step": int(P * img_bytes + P * C3_PATCHES * 21),
                 "d2h_bytes_per_step": int(P * (7 + 36 + 1) * 4), "ms_per_step": t_e / args.steps * 1e3,
                 "pipeline": "ygz_sia_run with host ygz_sia_problem structs (level images uploaded every call)"},
+        "e2e_device_pyramids": {"value": total / t_o, "unit": "alignments/s", "h2d_bytes_per_step": int(P * C3_PATCHES * 21 + P * 264),
+                                "d2h_bytes_per_step": int(P * (7 + 36 + 1) * 4), "ms_per_step": t_o / args.steps * 1e3,
+                                "same_result_as_host_images": orb_same,
+                                "pipeline": "ygz_sia_run_orb: level images read in place from the ORBextractor handle that extracted the two frames "
+                                            "(their upload is the extractor's, measured in the C2 / C5 e2e); per step: features + poses H2D, "
+                                            "one kernel, poses + H D2H"},
         "gpu_launches": int(args.steps), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_sia_align", "achieved": alg / (t_dev / args.steps) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (t_dev / args.steps) / 1e9 / peak, "traffic": None, "peak_source": peak_src,

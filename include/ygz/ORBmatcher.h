@@ -97,6 +97,18 @@ public:
         vpReplacePoint.resize(vpPoints.size());
         return n;
     }
+    // The search of Fuse(KeyFrame*, const vector<MapPoint*>&, th)  :748-886: best key point / distance per candidate map point (-1 / 256
+    // = none); the caller replays the observation-graph mutation (ygz::b200::ORBmatcherT::Fuse does).  false: the call failed.
+    bool FuseCandidates(const ygz_frame_view& KF, const float Ow[3], const float* invLevelSigma2, const ygz_map_points& mps,
+                        const std::vector<int>& vpMapPoints, float th, std::vector<int>& bestIdx, std::vector<int>& bestDist) {
+        const size_t n = vpMapPoints.size();
+        bestIdx.assign(n ? n : 1, -1);
+        bestDist.assign(n ? n : 1, 256);
+        const int rc = ygz_fuse_candidates(h_, &KF, Ow, invLevelSigma2, &mps, vpMapPoints.data(), (int)n, th, bestIdx.data(), bestDist.data());
+        if (rc < 0) { ok(rc); bestIdx.assign(n, -1); bestDist.assign(n, 256); return false; }    // "nothing to fuse" + a log line
+        bestIdx.resize(n); bestDist.resize(n);
+        return true;
+    }
     // SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  :1006-1216
     int SearchBySim3(const ygz_frame_view& KF1, const ygz_frame_view& KF2, const ygz_map_points& mps, std::vector<int>& vpMatches12,
                      const std::vector<int>& idxInKF2, float s12, const float R12[9], const float t12[3], float th) {

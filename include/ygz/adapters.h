@@ -397,6 +397,46 @@ public:
             if (gk.mp[i] != before[i] && gk.mp[i] >= 0) { T.at(gk.mp[i])->AddObservation(pKF, (size_t)i); pKF->AddMapPoint(T.at(gk.mp[i]), (size_t)i); }
         return n;
     }
+    // Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th = 3.0)  :748-886 (LocalMapping::SearchInNeighbors).
+    // The per-point search runs once on the device (ygz_fuse_candidates); the loop below is upstream's, with the search replaced by its
+    // result: the skip tests are evaluated when the point's turn comes and the graph calls (Replace / AddObservation / AddMapPoint, :866-880)
+    // are made on the caller's objects in upstream's order.  A point that was bad or already in pKF at entry stays so, hence it is not searched.
+    int Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th = 3.0) {
+        Table T; Gather gk;
+        gk.common(*pKF, pKF->N);
+        const auto R = pKF->GetRotation();
+        const auto t = pKF->GetTranslation();
+        const auto ow = pKF->GetCameraCenter();
+        for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) gk.v.Rcw[3 * i + j] = R(i, j); gk.v.tcw[i] = t(i); }
+        const float Ow[3] = {ow(0), ow(1), ow(2)};
+        std::vector<int> ids;
+        ids.reserve(vpMapPoints.size());
+        for (MapPoint* p : vpMapPoints) ids.push_back(p && !p->isBad() && !p->IsInKeyFrame(pKF) ? T.add(p) : -1);
+        const ygz_map_points mps = T.view();
+        std::vector<int> bestIdx, bestDist;
+        if (!Base::FuseCandidates(gk.v, Ow, pKF->mvInvLevelSigma2.data(), mps, ids, th, bestIdx, bestDist)) return 0;
+        int nFused = 0;
+        for (size_t i = 0; i < vpMapPoints.size(); i++) {
+            MapPoint* pMP = vpMapPoints[i];
+            if (!pMP) continue;
+            if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+            if (bestDist[i] <= Base::TH_LOW) {
+                const size_t idx = (size_t)bestIdx[i];
+                MapPoint* pMPinKF = pKF->GetMapPoint(idx);
+                if (pMPinKF) {
+                    if (!pMPinKF->isBad()) {
+                        if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                        else pMPinKF->Replace(pMP);
+                    }
+                } else {
+                    pMP->AddObservation(pKF, idx);
+                    pKF->AddMapPoint(pMP, idx);
+                }
+                nFused++;
+            }
+        }
+        return nFused;
+    }
     // SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12, const cv::Mat& t12, float th)  :1006-1216
     template <class Mat>
     int SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const Mat& R12, const Mat& t12, const float th) {

@@ -220,6 +220,17 @@ int ygz_search_by_projection_sim3(ygz_matcher* h, const ygz_frame_view* kf, cons
  * the map point already sitting in the chosen slot.  Returns nFused. */
 int ygz_fuse_sim3(ygz_matcher* h, ygz_frame_view* kf, const float* Scw, const ygz_map_points* mps, const int* point_ids, int n_points,
                   float th, int* replace_point);
+/* The search of ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, th), src/ORBmatcher.cc:748-886 (local mapping:
+ * SearchInNeighbors): for every entry of point_ids (index into mps, -1 = NULL) the key point of pKF the loop body picks - projection with
+ * pKF's pose (kf->Rcw / tcw, Eigen float), positive depth, image bounds, distance invariance, viewing angle (needs mps->normal), predicted
+ * level, window th * mvScaleFactors[level], level band, stereo-aware chi2 gate (kf->u_right, kf->mbf, inv_level_sigma2 = mvInvLevelSigma2),
+ * smallest descriptor distance (first minimum in GetFeaturesInArea order).  best_idx[i] = -1 / best_dist[i] = 256 when nothing survives.
+ * Ow = pKF->GetCameraCenter().  The isBad / IsInKeyFrame skip and the map mutation that ends the loop body (Replace / AddObservation /
+ * AddMapPoint, `bestDist <= TH_LOW`) need the observation graph: ygz::b200::ORBmatcherT::Fuse (include/ygz/adapters.h) replays them on
+ * the caller's objects in upstream's order.  None of the inputs read here is changed by those mutations for a point that is still
+ * eligible when its turn comes, so the one-shot search equals the interleaved one. */
+int ygz_fuse_candidates(ygz_matcher* h, const ygz_frame_view* kf, const float* Ow, const float* inv_level_sigma2,
+                        const ygz_map_points* mps, const int* point_ids, int n_points, float th, int* best_idx, int* best_dist);
 /* SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th), :1006-1216: matches12[kf1->n] in / out (map-point index of KF2's point, -1 =
  * none); idx_in_kf2[mps->m] = pMP->GetIndexInKeyFrame(pKF2) (-1 = not observed there); R12 row-major 3x3, t12 3. */
 int ygz_search_by_sim3(ygz_matcher* h, const ygz_frame_view* kf1, const ygz_frame_view* kf2, const ygz_map_points* mps, int* matches12,
@@ -326,6 +337,15 @@ int ygz_sia_destroy(ygz_sia* h);
  * getFisherInformation's H_), n_tracked = n_meas_/patch_area_ (the return value of run). */
 int ygz_sia_run(ygz_sia* h, const ygz_sia_problem* problems, int n_problems, int max_level, int min_level,
                 int n_iter, float eps, float* out_q, float* out_t, float* out_H, int* out_n_tracked);
+/* The same alignments with the level images read IN PLACE from extractor handles (the tracker's case: Frame::mvImagePyramid is the
+ * extractor's pyramid, src/Frame.cc ComputeImagePyramid -> ORBextractor::ComputePyramid, and both frames were just extracted on this
+ * device).  Problem p aligns frame ref_frame[p] of orb_ref with frame cur_frame[p] of orb_cur (the same handle may be passed twice, e.g.
+ * consecutive frames of one batch).  Of ygz_sia_problem only fx..cy, n, ref_px, world_xyz, valid and the poses are read; the level
+ * fields (n_levels, *_levels, level_w/h, inv_scale_factors) are ignored - sizes and mvInvScaleFactors come from the handles.  No image
+ * bytes cross PCIe; the call waits for the extractors' streams on the device, not on the host. */
+int ygz_sia_run_orb(ygz_sia* h, ygz_orb* orb_ref, ygz_orb* orb_cur, const ygz_sia_problem* problems, const int* ref_frame,
+                    const int* cur_frame, int n_problems, int max_level, int min_level, int n_iter, float eps, float* out_q,
+                    float* out_t, float* out_H, int* out_n_tracked);
 /* per-iteration record of the last ygz_sia_run for problem `problem`: 8 floats per evaluated iteration
  * {level, iter, chi2, n_meas, max|x|, accepted, 0, 0} (the verbose_ printout of NLSSolver_impl.hpp:76-83) */
 int ygz_sia_last_trace(ygz_sia* h, int problem, float* out, int cap, int* n);

@@ -673,6 +673,70 @@ int orc_fuse_sim3(orc_frame_view* kf, const float* Scw, const orc_map_points* mp
     return nFused;
 }
 
+// The per-point search of Fuse(pKF, vpMapPoints, th) :748-886 (local mapping; Eigen float geometry, stereo-aware chi2 gate): for
+// every entry of point_ids (-1 = NULL) the key point of `kf` the loop body would pick — best_idx[i] / best_dist[i] (-1 / 256 when a
+// gate fails or no candidate survives), WITHOUT the isBad / IsInKeyFrame skip and without the map mutation at the end of the body
+// (those need the observation graph and are replayed by the caller in upstream's order; none of the quantities read here is changed
+// by them for a point that is still eligible).  Ow = pKF->GetCameraCenter(), inv_level_sigma2 = pKF->mvInvLevelSigma2.
+void orc_fuse_candidates(const orc_frame_view* kf, const float* Ow, const float* inv_level_sigma2, const orc_map_points* mps,
+                         const int* point_ids, int n_points, float th, int* best_idx, int* best_dist) {
+    Grid g(kf);
+    const float* R = kf->Rcw;
+    const float* t = kf->tcw;
+    for (int i = 0; i < n_points; i++) {
+        best_idx[i] = -1;
+        best_dist[i] = 256;
+        const int pMP = point_ids[i];
+        if (pMP < 0) continue;
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        float pc[3];
+        for (int r = 0; r < 3; r++) {                                       // Rcw * p3Dw + tcw, float, left to right
+            float a = R[3 * r] * Pw[0];
+            a += R[3 * r + 1] * Pw[1];
+            a += R[3 * r + 2] * Pw[2];
+            pc[r] = a + t[r];
+        }
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float u = kf->fx * x + kf->cx, v = kf->fy * y + kf->cy;
+        if (!kf_is_in_image(kf, u, v)) continue;
+        const float ur = u - kf->mbf * invz;
+        const float maxDistance = 1.2f * mps->max_dist[pMP], minDistance = 0.8f * mps->min_dist[pMP];
+        float PO[3];
+        for (int k = 0; k < 3; k++) PO[k] = Pw[k] - Ow[k];
+        float sq = PO[0] * PO[0]; sq += PO[1] * PO[1]; sq += PO[2] * PO[2];
+        const float dist3D = std::sqrt(sq);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const float* Pn = mps->normal + 3 * (size_t)pMP;
+        float dt = PO[0] * Pn[0]; dt += PO[1] * Pn[1]; dt += PO[2] * Pn[2];
+        if (dt < 0.5 * dist3D) continue;                                    // viewing angle below 60 degrees
+        const int lvl = predict_scale(mps->max_dist[pMP], dist3D, kf);
+        const float radius = th * kf->scale_factors[lvl];
+        const std::vector<int> cand = features_in_area(kf, g, u, v, radius);
+        const uint8_t* dMP = mps->desc + 32 * (size_t)pMP;
+        int bestDist = 256, bestIdx = -1;
+        for (int idx : cand) {
+            const orc_keypoint& kp = kf->keys[idx];
+            const int kpLevel = kp.octave;
+            if (kpLevel < lvl - 1 || kpLevel > lvl) continue;
+            const float ex = u - kp.x, ey = v - kp.y;
+            if (uright(kf, idx) >= 0) {
+                const float er = ur - uright(kf, idx);
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+            } else {
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+            }
+            const int d = descriptor_distance(dMP, kf->desc + 32 * (size_t)idx);
+            if (d < bestDist) { bestDist = d; bestIdx = idx; }
+        }
+        best_idx[i] = bestIdx;
+        best_dist[i] = bestDist;
+    }
+}
+
 // SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) :1006-1216.  matches12[kf1->n] in / out (map-point index of KF2 or -1);
 // idx_in_kf2[mps->m] = pMP->GetIndexInKeyFrame(pKF2) (-1 = not observed there).
 int orc_search_by_sim3(const orc_frame_view* kf1, const orc_frame_view* kf2, const orc_map_points* mps, int* matches12,

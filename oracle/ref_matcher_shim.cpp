@@ -512,4 +512,65 @@ int REFM(search_by_sim3)(const orc_frame_view *kf1, const orc_frame_view *kf2, c
     return n;
 }
 
+/* ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) :748-886 on a two-key-frame map: `kf` (the target) and a second, mono key frame
+ * of n2 slots that only holds extra observations (obs2_idx[j] = slot of point j there, -1 = none), so that Observations() differs
+ * between points and MapPoint::Replace has something to move.  Observations are registered with AddObservation (stereo keys of kf
+ * count twice, src/MapPoint.cc:78-91).  point_ids[i] = -1 is a NULL entry of vpMapPoints.
+ * out: kf->map_point (slots after the call), bad[m], n_obs[m], replaced_by[m] (mpReplaced, -1 = none), kf2_slots[n2]. */
+int REFM(fuse_kf)(orc_frame_view *kf, const float *inv_level_sigma2, const orc_map_points *mps, const int *obs2_idx, int n2,
+                 const int *point_ids, int n_points, float th, uint8_t *bad_out, int *nobs_out, int *replaced_out, int *kf2_slots_out) {
+    Points P(mps);
+    KeyFrame *K = make_keyframe(kf, P);
+    K->mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + kf->n_levels);
+    KeyFrame *K2 = new KeyFrame(n2, kf->fx, kf->fy, kf->cx, kf->cy, kf->mbf, kf->mb, (int) kf->min_x, (int) kf->min_y, (int) kf->max_x,
+                                (int) kf->max_y, kf->n_levels, kf->log_scale_factor);
+    K2->mvuRight.assign(n2, -1.f);
+    K2->mvpMapPoints.assign(n2, nullptr);
+    for (size_t j = 0; j < P.mp.size(); j++) P.mp[j].nObs = 0;
+    for (int i = 0; i < kf->n; i++) if (K->mvpMapPoints[i]) K->mvpMapPoints[i]->AddObservation(K, i);
+    for (size_t j = 0; j < P.mp.size(); j++)
+        if (obs2_idx[j] >= 0) { K2->mvpMapPoints[obs2_idx[j]] = &P.mp[j]; P.mp[j].AddObservation(K2, obs2_idx[j]); }
+    MapPoint::mLog.clear();
+    std::vector<MapPoint *> pts(n_points);
+    for (int i = 0; i < n_points; i++) pts[i] = P.at(point_ids[i]);
+    ORBmatcher m(0.6f);
+    const int n = m.Fuse(K, pts, th);
+    store_map_points(K->mvpMapPoints, P, kf->map_point);
+    store_map_points(K2->mvpMapPoints, P, kf2_slots_out);
+    for (size_t j = 0; j < P.mp.size(); j++) {
+        bad_out[j] = P.mp[j].mbBad;
+        nobs_out[j] = P.mp[j].nObs;
+        replaced_out[j] = P.index(P.mp[j].mpReplaced);
+    }
+    delete K; delete K2;
+    return n;
+}
+
+#ifndef SHIM_USE_ADAPTERS
+/* The index Fuse picks for ONE point at a time against a key frame with no map points: best_idx[i] = bestIdx if bestDist <= TH_LOW else -1
+ * (read back from the observation Fuse adds).  Pins the per-point search of the restatement (orc_fuse_candidates). */
+void REFM(fuse_kf_each)(const orc_frame_view *kf, const float *inv_level_sigma2, const orc_map_points *mps, const int *point_ids, int n_points,
+                       float th, int *best_idx) {
+    Points P(mps);
+    KeyFrame *K = make_keyframe(kf, P);
+    K->mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + kf->n_levels);
+    K->mvpMapPoints.assign(kf->n, nullptr);
+    ORBmatcher m(0.6f);
+    for (int i = 0; i < n_points; i++) {
+        best_idx[i] = -1;
+        MapPoint *p = P.at(point_ids[i]);
+        if (!p) continue;
+        p->mbBad = false;
+        p->mObservations.clear();
+        std::vector<MapPoint *> one(1, p);
+        if (m.Fuse(K, one, th) == 1) {
+            best_idx[i] = (int) p->mObservations[K];
+            K->mvpMapPoints[best_idx[i]] = nullptr;
+            p->mObservations.clear();
+        }
+    }
+    delete K;
+}
+#endif
+
 }  // extern "C"

@@ -37,6 +37,8 @@ namespace ygz {
             mvpMapPoints[idx] = pMP;
             MapPoint::mLog.push_back(MapPoint::LogEntry{3, pMP, nullptr, this, (int) idx});
         }
+        void ReplaceMapPointMatch(const size_t &idx, MapPoint *pMP) { mvpMapPoints[idx] = pMP; }              // :307-309
+        void EraseMapPointMatch(const size_t &idx) { mvpMapPoints[idx] = static_cast<MapPoint *>(NULL); }     // :299-302
         // src/KeyFrame.cc:774-809
         std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r) const {
             vector<size_t> vIndices;
@@ -91,6 +93,35 @@ namespace ygz {
         std::vector<MapPoint *> mvpMapPoints;
         std::vector<std::vector<std::vector<size_t> > > mGrid;
     };
+
+    // src/MapPoint.cc:78-91
+    inline void MapPoint::AddObservation(KeyFrame *pKF, size_t idx) {
+        if (mObservations.count(pKF)) return;
+        mObservations[pKF] = idx;
+        if (pKF->mvuRight[idx] >= 0) nObs += 2;
+        else nObs++;
+        mLog.push_back(LogEntry{1, this, nullptr, pKF, (int) idx});
+    }
+
+    // src/MapPoint.cc:155-188.  Not modelled: IncreaseFound / IncreaseVisible, ComputeDistinctiveDescriptors (the survivor ends up observed
+    // by every key frame of the replaced point, so Fuse never reads its descriptor again) and Map::EraseMapPoint.
+    inline void MapPoint::Replace(MapPoint *pMP) {
+        if (pMP == this) return;                                             // upstream compares mnId
+        std::map<KeyFrame *, size_t> obs = mObservations;
+        mObservations.clear();
+        mbBad = true;
+        mpReplaced = pMP;
+        mLog.push_back(LogEntry{2, this, pMP, nullptr, -1});
+        for (std::map<KeyFrame *, size_t>::iterator mit = obs.begin(), mend = obs.end(); mit != mend; mit++) {
+            KeyFrame *pKF = mit->first;
+            if (!pMP->IsInKeyFrame(pKF)) {
+                pKF->ReplaceMapPointMatch(mit->second, pMP);
+                pMP->AddObservation(pKF, mit->second);
+            } else {
+                pKF->EraseMapPointMatch(mit->second);
+            }
+        }
+    }
 
     // src/MapPoint.cc:343-373
     inline int MapPoint::PredictScale(const float &currentDist, KeyFrame *pKF) {

@@ -26,18 +26,8 @@ namespace ygz {
         float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }    // :338-341
         int PredictScale(const float &currentDist, KeyFrame *pKF);           // :343-357 (defined after KeyFrame)
         int PredictScale(const float &currentDist, Frame *pF);               // :359-373
-        void AddObservation(KeyFrame *pKF, size_t idx) {                     // :78-91
-            if (mObservations.count(pKF)) return;
-            mObservations[pKF] = idx;
-            nObs++;
-            mLog.push_back(LogEntry{1, this, nullptr, pKF, (int) idx});
-        }
-        void Replace(MapPoint *pMP) {                                        // :192-226 (bookkeeping recorded, not replayed)
-            if (pMP == this) return;
-            mbBad = true;
-            mpReplaced = pMP;
-            mLog.push_back(LogEntry{2, this, pMP, nullptr, -1});
-        }
+        void AddObservation(KeyFrame *pKF, size_t idx);                       // :78-91  (defined after KeyFrame: stereo keys count twice)
+        void Replace(MapPoint *pMP);                                         // :155-188 (defined after KeyFrame)
 
         Vector3f mWorldPos, mNormalVector;
         cv::Mat mDescriptor;

@@ -119,6 +119,9 @@ int orc_search_for_triangulation(int check_ori, const orc_frame_view* kf1, const
  * SearchByProjection(KF, Scw, vpPoints, vpMatched, th) :265-373 — Scw 4x4 row-major, matched[kf->n] in / out */
 int orc_search_by_projection_sim3(const orc_frame_view* kf, const float* Scw, const orc_map_points* mps, const int* point_ids, int n_points,
                                   int* matched, int th);
+/* per-point search of Fuse(pKF, vpMapPoints, th) :748-886 (see orb_matcher.cpp); point_ids[i] = -1 is a NULL entry */
+void orc_fuse_candidates(const orc_frame_view* kf, const float* Ow, const float* inv_level_sigma2, const orc_map_points* mps,
+                         const int* point_ids, int n_points, float th, int* best_idx, int* best_dist);
 /* Fuse(KF, Scw, vpPoints, th, vpReplacePoint) :888-1004 — kf->map_point in / out (AddMapPoint), replace_point[n_points] in / out */
 int orc_fuse_sim3(orc_frame_view* kf, const float* Scw, const orc_map_points* mps, const int* point_ids, int n_points, float th,
                   int* replace_point);

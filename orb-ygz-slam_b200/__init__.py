@@ -98,11 +98,11 @@ ABI_SYMBOLS = [
     "ygz_hamming_pairs", "ygz_search_by_bow", "ygz_search_by_bow_kf", "ygz_search_for_triangulation", "ygz_search_by_projection_points",
     "ygz_search_by_projection_last", "ygz_search_by_projection_kf", "ygz_search_for_initialization",
     "ygz_matcher_set_vocabulary", "ygz_search_by_bow_batch", "ygz_search_by_bow_batch_async", "ygz_search_by_bow_batch_time", "ygz_frontend_time", "ygz_frontend_time2", "ygz_frontend_time_n",
-    "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_time", "ygz_sia_last_trace",
+    "ygz_sia_create", "ygz_sia_destroy", "ygz_sia_run", "ygz_sia_run_orb", "ygz_sia_time", "ygz_sia_last_trace",
     "ygz_direct_create", "ygz_direct_destroy", "ygz_direct_upload_frame", "ygz_direct_set_pose",
     "ygz_find_direct_projection", "ygz_direct_time", "ygz_compute_stereo_matches",
     "ygz_stereo_batch", "ygz_stereo_batch_async", "ygz_stereo_frontend_time",
-    "ygz_search_by_projection_sim3", "ygz_fuse_sim3", "ygz_search_by_sim3",
+    "ygz_search_by_projection_sim3", "ygz_fuse_sim3", "ygz_search_by_sim3", "ygz_fuse_candidates",
     "ygz_search_by_projection_last_batch", "ygz_search_by_projection_points_batch", "ygz_search_by_projection_batch_time",
     "ygz_vocab_load", "ygz_vocab_from_memory", "ygz_vocab_destroy", "ygz_vocab_info", "ygz_vocab_transform", "ygz_vocab_transform_orb",
 ]
@@ -166,6 +166,7 @@ def lib():
     sigs.setdefault('ygz_compute_stereo_matches', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, f32p, f32p]
     sigs.setdefault('ygz_search_by_projection_sim3', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), f32p, C.POINTER(MapPoints), i32p, C.c_int, i32p, C.c_int]
     sigs.setdefault('ygz_fuse_sim3', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), f32p, C.POINTER(MapPoints), i32p, C.c_int, C.c_float, i32p]
+    sigs.setdefault('ygz_fuse_candidates', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), f32p, f32p, C.POINTER(MapPoints), i32p, C.c_int, C.c_float, i32p, i32p]
     sigs.setdefault('ygz_search_by_sim3', {})['argtypes'] = [C.c_void_p, C.POINTER(FrameView), C.POINTER(FrameView), C.POINTER(MapPoints), i32p, i32p, C.c_float, f32p, f32p, C.c_float]
     sigs.setdefault('ygz_search_by_projection_last_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.POINTER(ProjectionCamera), C.c_int, i32p, i32p, f32p, u8p, f32p, u8p, f32p,
                                                                             C.c_float, C.c_int, C.c_int, C.c_int, i32p, i32p, i32p]
@@ -191,6 +192,7 @@ def lib():
     sigs.setdefault('ygz_sia_create', {})['argtypes'] = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     sigs.setdefault('ygz_sia_destroy', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_sia_run', {})['argtypes'] = [C.c_void_p, C.POINTER(SiaProblem), C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, i32p]
+    sigs.setdefault('ygz_sia_run_orb', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SiaProblem), i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, f32p, f32p, f32p, i32p]
     sigs.setdefault('ygz_sia_time', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, f32p]
     sigs.setdefault('ygz_orb_extract_async', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     sigs.setdefault('ygz_orb_wait', {})['argtypes'] = [C.c_void_p]
@@ -725,6 +727,28 @@ def make_sia_problem(ref_levels, cur_levels, inv_scale, K, ref_px, world_xyz, va
     return _Keep(v, [ref_levels, cur_levels, lw, lh, isf, px, xyz, val, refp, curp])
 
 
+def make_sia_features(K, ref_px, world_xyz, valid=None, ref_pose=None, cur_pose=None):
+    """ygz_sia_problem carrying only what ygz_sia_run_orb reads: camera, features, poses (the images stay in the extractor handles)."""
+    px = np.ascontiguousarray(ref_px, np.float32).reshape(-1, 2)
+    xyz = np.ascontiguousarray(world_xyz, np.float32).reshape(-1, 3)
+    n = len(px)
+    val = np.ones(n, np.uint8) if valid is None else np.ascontiguousarray(valid, np.uint8)
+    v = SiaProblem()
+    v.n_levels = 0
+    v.fx, v.fy, v.cx, v.cy = K
+    v.n = n
+    v.ref_px = _ptr(px, f32p)
+    v.world_xyz = _ptr(xyz, f32p)
+    v.valid = _ptr(val, u8p)
+    rq, rt = ref_pose if ref_pose is not None else ((0, 0, 0, 1), (0, 0, 0))
+    cq, ct = cur_pose if cur_pose is not None else ((0, 0, 0, 1), (0, 0, 0))
+    v.ref_q = (C.c_float * 4)(*rq)
+    v.ref_t = (C.c_float * 3)(*rt)
+    v.cur_q = (C.c_float * 4)(*cq)
+    v.cur_t = (C.c_float * 3)(*ct)
+    return _Keep(v, [px, xyz, val])
+
+
 class ORBVocabulary:
     """Mirror of ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (include/ORBVocabulary.h) for the calls
     the front end makes: loadFromBinaryFile and transform(features, BowVector, FeatureVector, levelsup)."""
@@ -918,6 +942,22 @@ class SparseImgAlign:
         nt = np.zeros(n, np.int32)
         _check(self.L.ygz_sia_run(self.h, arr, n, self.max_level, self.min_level, self.n_iter, self.eps, _ptr(q, f32p),
                                   _ptr(t, f32p), _ptr(H, f32p), _ptr(nt, i32p)), "ygz_sia_run")
+        return q, t, H, nt
+
+    def run_batch_orb(self, orb_ref, orb_cur, problems, ref_frame, cur_frame):
+        """ygz_sia_run_orb: level images read in place from two ORBextractor handles (frames ref_frame[p] / cur_frame[p]); the
+        problems come from make_sia_features (or make_sia_problem - their level fields are ignored)."""
+        n = len(problems)
+        arr = (SiaProblem * n)(*[p.struct for p in problems])
+        rf = np.ascontiguousarray(ref_frame, np.int32)
+        cf = np.ascontiguousarray(cur_frame, np.int32)
+        assert len(rf) == n and len(cf) == n
+        q = np.zeros((n, 4), np.float32)
+        t = np.zeros((n, 3), np.float32)
+        H = np.zeros((n, 36), np.float32)
+        nt = np.zeros(n, np.int32)
+        _check(self.L.ygz_sia_run_orb(self.h, orb_ref.h, orb_cur.h, arr, _ptr(rf, i32p), _ptr(cf, i32p), n, self.max_level, self.min_level,
+                                      self.n_iter, self.eps, _ptr(q, f32p), _ptr(t, f32p), _ptr(H, f32p), _ptr(nt, i32p)), "ygz_sia_run_orb")
         return q, t, H, nt
 
     def run(self, problem):

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
     uint16_t* const items = reinterpret_cast<uint16_t*>(sc + F2_SC_BYTES);
     unsigned long long* const bar = reinterpret_cast<unsigned long long*>(sc + F2_SC_BYTES + F2_ITEMS_BYTES);
     constexpr int TP = F2_PITCH;
+    const unsigned sc_s = smem_u32(sc), items_s = smem_u32(items);
 
     // Work items (frame, cell), frame-major.  The first n_static items are dealt to the warps round-robin; the rest are
     // drawn from a global counter (one atomic per item) so that no warp is left with a long tail: cells differ in cost
@@ -179,9 +180,11 @@ __global__ void __launch_bounds__(F2_THREADS, 4) k_fast_cells_v2(const __grid_co
                                    q[o8], q[o9], q[o10], q[o11], q[o12], q[o13], q[o14], q[o15]};
                 const int best = fast9_best_packed(q[0], r);
                 const bool corner = valid && best > tmin;       // response = best - 1
-                if (corner) sc[(y + 1) * F2_SCP + x + 1] = (uint8_t)(best - 1);
+                // predicated stores on 32-bit shared addresses (the generic-pointer form cost 12 instructions + a branch per group)
                 const unsigned bal = __ballot_sync(0xffffffffu, corner);
-                if (corner) items[ncorn + __popc(bal & lanemask_lt())] = (uint16_t)it;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t@p st.shared.u8 [%1], %2;\n\t@p st.shared.u16 [%3], %4;\n\t}"
+                             :: "r"((int)corner), "r"(sc_s + (unsigned)(y * F2_SCP + x + F2_SCP + 1)), "r"(best - 1),
+                                "r"(items_s + 2u * (unsigned)(ncorn + __popc(bal & lanemask_lt()))), "r"(it) : "memory");
                 ncorn += __popc(bal);
             }
             __syncwarp();

@@ -1438,6 +1438,75 @@ int ygz_fuse_sim3(ygz_matcher* h, ygz_frame_view* kf, const float* Scw, const yg
     return nFused;
 }
 
+int ygz_fuse_candidates(ygz_matcher* h, const ygz_frame_view* kf, const float* Ow, const float* inv_level_sigma2, const ygz_map_points* mps,
+                        const int* point_ids, int n_points, float th, int* best_idx, int* best_dist) {
+    YGZ_ARG_CHECK(h && kf && Ow && inv_level_sigma2 && mps && mps->normal && mps->min_dist && mps->max_dist && best_idx && best_dist &&
+                  (n_points == 0 || point_ids));
+    Grid g(kf);
+    std::vector<SimJob> jobs;
+    std::vector<int> pq, pt, all;
+    const float* R = kf->Rcw;
+    const float* t = kf->tcw;
+    for (int i = 0; i < n_points; i++) {
+        best_idx[i] = -1;
+        best_dist[i] = 256;
+        const int pMP = point_ids[i];
+        if (pMP < 0) continue;                                              // NULL entry of vpMapPoints
+        YGZ_ARG_CHECK(pMP < mps->m);
+        const float* Pw = mps->world_pos + 3 * (size_t)pMP;
+        float pc[3];
+        for (int r = 0; r < 3; r++) {                                       // Eigen Matrix3f * Vector3f + Vector3f: float, left to right
+            float a = R[3 * r] * Pw[0];
+            a += R[3 * r + 1] * Pw[1];
+            a += R[3 * r + 2] * Pw[2];
+            pc[r] = a + t[r];
+        }
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float u = kf->fx * (pc[0] * invz) + kf->cx, v = kf->fy * (pc[1] * invz) + kf->cy;
+        if (!in_image_h(kf, u, v)) continue;
+        const float ur = u - kf->mbf * invz;
+        float PO[3];
+        for (int k = 0; k < 3; k++) PO[k] = Pw[k] - Ow[k];
+        float sq = PO[0] * PO[0]; sq += PO[1] * PO[1]; sq += PO[2] * PO[2];
+        const float dist3D = std::sqrt(sq);
+        if (dist3D < 0.8f * mps->min_dist[pMP] || dist3D > 1.2f * mps->max_dist[pMP]) continue;
+        const float* Pn = mps->normal + 3 * (size_t)pMP;
+        float dt = PO[0] * Pn[0]; dt += PO[1] * Pn[1]; dt += PO[2] * Pn[2];
+        if (dt < 0.5 * dist3D) continue;
+        const int lvl = predict_scale_h(mps->max_dist[pMP], dist3D, kf);
+        features_in_area(kf, g, u, v, th * kf->scale_factors[lvl], -1, -1, all);
+        const int first = (int)pq.size();
+        for (int idx : all) {
+            const ygz_keypoint& kp = kf->keys[idx];
+            if (kp.octave < lvl - 1 || kp.octave > lvl) continue;
+            const float ex = u - kp.x, ey = v - kp.y;
+            const float kr = uright(kf, idx);
+            if (kr >= 0) {                                                  // stereo key: three-dimensional reprojection error
+                const float er = ur - kr;
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv_level_sigma2[kp.octave] > 7.8) continue;
+            } else {
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv_level_sigma2[kp.octave] > 5.99) continue;
+            }
+            pq.push_back(pMP); pt.push_back(idx);
+        }
+        if ((int)pq.size() > first) jobs.push_back(SimJob{i, pMP, lvl, first, (int)pq.size() - first});
+    }
+    std::vector<int> dist;
+    int rc = pair_distances(h, mps->desc, mps->m, kf->desc, kf->n, pq, pt, dist);
+    if (rc) return rc;
+    for (const SimJob& j : jobs) {
+        int bestDist = 256, bestIdx = -1;
+        for (int p = j.first; p < j.first + j.count; p++)
+            if (dist[p] < bestDist) { bestDist = dist[p]; bestIdx = pt[p]; }
+        best_idx[j.q] = bestIdx;
+        best_dist[j.q] = bestDist;
+    }
+    return YGZ_OK;
+}
+
 int ygz_search_by_sim3(ygz_matcher* h, const ygz_frame_view* kf1, const ygz_frame_view* kf2, const ygz_map_points* mps, int* matches12,
                        const int* idx_in_kf2, float s12, const float* R12, const float* t12, float th) {
     YGZ_ARG_CHECK(h && kf1 && kf2 && mps && matches12 && idx_in_kf2 && R12 && t12 && kf1->map_point && kf2->map_point && s12 > 0.f);

@@ -183,7 +183,8 @@ constexpr int FAST_THREADS = FAST_WARPS * 32;
 // min over 9 contiguous = min3 of three min3 (32 instructions for all 16 arcs), then a max3 tree.
 // No negated operand feeds a min/max (ptxas 12.9 drops the negation when fusing into VIMNMX3).
 __device__ __forceinline__ int fast9_best_packed(int c, const int* r) {
-    const unsigned K2 = 0x01FF0000u - (unsigned)(c + 256) * 0xFFFFu;
+    unsigned K2 = 0x01FF0000u - (unsigned)(c + 256) * 0xFFFFu;
+    asm volatile("" : "+r"(K2));        // opaque: otherwise ptxas re-associates to (r_k - c) * 0xFFFF + const, TWO IMADs per ring pixel (r2 profile)
     unsigned E[16], e3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) E[k] = (unsigned)r[k] * 0xFFFFu + K2;
@@ -1011,6 +1012,9 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
                 m01 += v * I;
             }
             m10 = u * colsum;
+            // (measured, C1 B=256: lane = patch ROW with the row read as three LDS.128, funnel shifts and IDP.4A against per-|v| weight rows
+            //  is ~230 instructions shorter per key point but SLOWER, 0.265 ms against 0.227: rows are 16 words apart, so every 128-bit
+            //  access is a 4-way bank conflict and the weight rows cost four more L1 requests per lane; nine LDS.32 per lane: 0.347 ms.)
         } else if (lane < 31) {                                   // small level, or a pre-existing key near the border (REFLECT_101)
             const int au = abs(u);
             const bool in15 = cx >= HALF_PATCH && cy >= HALF_PATCH && cx + HALF_PATCH < L.w && cy + HALF_PATCH < L.h;

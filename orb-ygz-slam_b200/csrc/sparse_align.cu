@@ -28,7 +28,9 @@ struct SiaProblemDev {
     int n_levels;
     int n;
     int level_w[SIA_MAX_LEVELS], level_h[SIA_MAX_LEVELS];
-    size_t off_ref[SIA_MAX_LEVELS], off_cur[SIA_MAX_LEVELS];     // byte offsets into the image arena
+    const uint8_t* img_ref[SIA_MAX_LEVELS];                      // level images on the device: the handle's own arena (ygz_sia_run) or, zero
+    const uint8_t* img_cur[SIA_MAX_LEVELS];                      // copy, the pyramids two extractor handles hold (ygz_sia_run_orb)
+    int stride_ref[SIA_MAX_LEVELS], stride_cur[SIA_MAX_LEVELS];  // bytes per image row (== level_w in the arena)
     float inv_scale[SIA_MAX_LEVELS];
     float fx, fy, cx, cy;
     float ref_q[4], ref_t[3], cur_q[4], cur_t[3];
@@ -170,7 +172,6 @@ __device__ void ldlt_solve6(const float* Ain, const float* b, float* x) {
 
 struct SiaArgs {
     const SiaProblemDev* prob;      // [P]
-    const uint8_t* arena;           // level images of all problems
     const float* ref_px;            // [P][maxN][2]
     const float* xyz;               // [P][maxN][3]
     const uint8_t* valid;           // [P][maxN]
@@ -224,10 +225,10 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
 
     for (int level = A.max_level; level >= A.min_level; level--) {
         const int cols = P.level_w[level], rows = P.level_h[level];
-        const uint8_t* ref_img = A.arena + P.off_ref[level];
-        const uint8_t* cur_img = A.arena + P.off_cur[level];
+        const uint8_t* ref_img = P.img_ref[level];
+        const uint8_t* cur_img = P.img_cur[level];
         const float scale = P.inv_scale[level];
-        const int stride = cols;
+        const int stride = P.stride_ref[level], cstride = P.stride_cur[level];
         // ---- jacobian_cache_.setZero() (:41) + precomputeReferencePatches (:57-128)
         for (int i = tid; i < N * 96; i += SIA_THREADS) jac[i] = 0.f;
         __syncthreads();
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
                 const float su = u_cur - u_cur_i, sv = v_cur - v_cur_i;
                 const float w_tl = (1.0f - su) * (1.0f - sv), w_tr = su * (1.0f - sv), w_bl = (1.0f - su) * sv, w_br = su * sv;
                 const int py = pc >> 2, px = pc & 3;
-                const uint8_t* q = cur_img + (v_cur_i + py - 2) * stride + (u_cur_i - 2) + px;
-                const float intensity = w_tl * q[0] + w_tr * q[1] + w_bl * q[stride] + w_br * q[stride + 1];
+                const uint8_t* q = cur_img + (v_cur_i + py - 2) * cstride + (u_cur_i - 2) + px;
+                const float intensity = w_tl * q[0] + w_tr * q[1] + w_bl * q[cstride] + w_br * q[cstride + 1];
                 const float res = intensity - ref_patch[f * 16 + pc];
                 acc[27] += res * res;
                 acc[28] += 1.f;
@@ -384,6 +385,8 @@ struct ygz_sia {
     float *d_q = nullptr, *d_t = nullptr, *d_H = nullptr, *d_trace = nullptr;
     int *d_ntr = nullptr, *d_trace_n = nullptr;
     int last_n = 0;
+    uint8_t* h_feat = nullptr;      // pinned staging of the per-problem feature arrays (px | xyz | valid), one H2D copy each
+    cudaEvent_t ev_dep = nullptr;   // orders this handle's stream behind the extractor streams in ygz_sia_run_orb
 };
 
 static int sia_free(ygz_sia* h) {
@@ -394,6 +397,8 @@ static int sia_free(ygz_sia* h) {
     cudaFree(h->d_ntr); cudaFree(h->d_trace_n);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_dep) cudaEventDestroy(h->ev_dep);
+    if (h->h_feat) cudaFreeHost(h->h_feat);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return YGZ_OK;
@@ -401,12 +406,51 @@ static int sia_free(ygz_sia* h) {
 
 static SiaArgs make_args(ygz_sia* h, int max_level, int min_level, int n_iter, float eps) {
     SiaArgs A;
-    A.prob = h->d_prob; A.arena = h->d_arena; A.ref_px = h->d_px; A.xyz = h->d_xyz; A.valid = h->d_valid;
+    A.prob = h->d_prob; A.ref_px = h->d_px; A.xyz = h->d_xyz; A.valid = h->d_valid;
     A.ref_patch = h->d_patch; A.jac = h->d_jac; A.visible = h->d_visible; A.maxN = h->maxN;
     A.max_level = max_level; A.min_level = min_level; A.n_iter = n_iter; A.eps = eps;
     A.out_q = h->d_q; A.out_t = h->d_t; A.out_H = h->d_H; A.out_ntracked = h->d_ntr;
     A.trace = h->d_trace; A.trace_n = h->d_trace_n;
     return A;
+}
+
+// Features of all problems through one pinned staging buffer (three H2D copies instead of 3 per problem), problem table, the
+// kernel, results back.  Shared tail of ygz_sia_run / ygz_sia_run_orb.
+static int sia_finish(ygz_sia* h, const ygz_sia_problem* problems, const std::vector<SiaProblemDev>& pd, int n_problems, int max_level, int min_level,
+                      int n_iter, float eps, float* out_q, float* out_t, float* out_H, int* out_n_tracked) {
+    const size_t N = h->maxN, P = n_problems;
+    float* s_px = (float*)h->h_feat;
+    float* s_xyz = (float*)(h->h_feat + (size_t)h->maxP * N * 8);
+    uint8_t* s_valid = h->h_feat + (size_t)h->maxP * N * 20;
+    for (int p = 0; p < n_problems; p++) {
+        const ygz_sia_problem& S = problems[p];
+        if (S.n > 0) {
+            YGZ_ARG_CHECK(S.ref_px && S.world_xyz && S.valid);
+            std::memcpy(s_px + p * N * 2, S.ref_px, (size_t)S.n * 8);
+            std::memcpy(s_xyz + p * N * 3, S.world_xyz, (size_t)S.n * 12);
+            std::memcpy(s_valid + p * N, S.valid, (size_t)S.n);
+        }
+    }
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_px, s_px, P * N * 8, cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_xyz, s_xyz, P * N * 12, cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_valid, s_valid, P * N, cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_prob, pd.data(), P * sizeof(SiaProblemDev), cudaMemcpyHostToDevice, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));      // pd / pageable sources must outlive the copies
+    SiaArgs A = make_args(h, max_level, min_level, n_iter, eps);
+    { NvtxRange nvtx_range("ygz/SparseImgAlign::run");
+    k_sia_align<<<n_problems, SIA_THREADS, 0, h->stream>>>(A);
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    h->last_n = n_problems;
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_q, h->d_q, P * 16, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_t, h->d_t, P * 12, cudaMemcpyDeviceToHost, h->stream));
+    if (out_H) YGZ_CUDA_TRY(cudaMemcpyAsync(out_H, h->d_H, P * 144, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(out_n_tracked, h->d_ntr, P * 4, cudaMemcpyDeviceToHost, h->stream));
+    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // run() returns 0 and leaves TCR untouched when the reference frame has no keys (:24-27)
+    for (int p = 0; p < n_problems; p++)
+        if (problems[p].n == 0) out_n_tracked[p] = 0;
+    return YGZ_OK;
 }
 
 extern "C" {
@@ -423,6 +467,8 @@ int ygz_sia_create(int device, int max_problems, int max_features, int max_level
     TRY_OR_FREE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     TRY_OR_FREE(cudaEventCreate(&h->ev0));
     TRY_OR_FREE(cudaEventCreate(&h->ev1));
+    TRY_OR_FREE(cudaEventCreateWithFlags(&h->ev_dep, cudaEventDisableTiming));
+    TRY_OR_FREE(cudaMallocHost(&h->h_feat, P * N * 21));
     TRY_OR_FREE(cudaMalloc(&h->d_prob, P * sizeof(SiaProblemDev)));
     TRY_OR_FREE(cudaMalloc(&h->d_arena, P * h->arena_per_problem));
     TRY_OR_FREE(cudaMalloc(&h->d_px, P * N * 8));
@@ -466,36 +512,66 @@ int ygz_sia_run(ygz_sia* h, const ygz_sia_problem* problems, int n_problems, int
             const size_t bytes = (size_t)S.level_w[l] * S.level_h[l];
             D.level_w[l] = S.level_w[l]; D.level_h[l] = S.level_h[l]; D.inv_scale[l] = S.inv_scale_factors[l];
             if (off + 2 * bytes > end) { set_last_error("level images exceed max_level_pixels"); return YGZ_ERR_CAPACITY; }
-            D.off_ref[l] = off;
+            D.img_ref[l] = h->d_arena + off; D.stride_ref[l] = S.level_w[l];
             YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_arena + off, S.ref_levels[l], bytes, cudaMemcpyHostToDevice, h->stream));
             off += bytes;
-            D.off_cur[l] = off;
+            D.img_cur[l] = h->d_arena + off; D.stride_cur[l] = S.level_w[l];
             YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_arena + off, S.cur_levels[l], bytes, cudaMemcpyHostToDevice, h->stream));
             off += bytes;
         }
-        if (S.n > 0) {
-            YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_px + (size_t)p * h->maxN * 2, S.ref_px, (size_t)S.n * 8, cudaMemcpyHostToDevice, h->stream));
-            YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_xyz + (size_t)p * h->maxN * 3, S.world_xyz, (size_t)S.n * 12, cudaMemcpyHostToDevice, h->stream));
-            YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_valid + (size_t)p * h->maxN, S.valid, (size_t)S.n, cudaMemcpyHostToDevice, h->stream));
+    }
+    return sia_finish(h, problems, pd, n_problems, max_level, min_level, n_iter, eps, out_q, out_t, out_H, out_n_tracked);
+}
+
+int ygz_sia_run_orb(ygz_sia* h, ygz_orb* orb_ref, ygz_orb* orb_cur, const ygz_sia_problem* problems, const int* ref_frame, const int* cur_frame,
+                    int n_problems, int max_level, int min_level, int n_iter, float eps,
+                    float* out_q, float* out_t, float* out_H, int* out_n_tracked) {
+    YGZ_ARG_CHECK(h && orb_ref && orb_cur && problems && ref_frame && cur_frame && n_problems >= 1 && n_problems <= h->maxP && out_q && out_t && out_n_tracked);
+    YGZ_ARG_CHECK(min_level >= 0 && max_level >= min_level && max_level < SIA_MAX_LEVELS && n_iter >= 0);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const int Bref = ygz_orb_max_batch(orb_ref), Bcur = ygz_orb_max_batch(orb_cur);
+    float scale[16], inv_scale[16], sg[16], isg[16];
+    int fpl[16];
+    int rc = ygz_orb_tables(orb_ref, scale, inv_scale, sg, isg, fpl);      // ref_frame->mvInvScaleFactors (src/SparseImageAlign.cc:86)
+    if (rc) return rc;
+    const uint8_t *base_ref[SIA_MAX_LEVELS] = {}, *base_cur[SIA_MAX_LEVELS] = {};
+    int pit_ref[SIA_MAX_LEVELS] = {}, pit_cur[SIA_MAX_LEVELS] = {}, lw[SIA_MAX_LEVELS] = {}, lh[SIA_MAX_LEVELS] = {};
+    size_t fs_ref[SIA_MAX_LEVELS] = {}, fs_cur[SIA_MAX_LEVELS] = {};
+    for (int l = min_level; l <= max_level; l++) {
+        int w2 = 0, h2 = 0;
+        void *pr = nullptr, *pc = nullptr;
+        if (ygz_orb_level_size(orb_ref, l, &lw[l], &lh[l]) != YGZ_OK || ygz_orb_level_size(orb_cur, l, &w2, &h2) != YGZ_OK) {
+            set_last_error("max_level exceeds the extractor's pyramid"); return YGZ_ERR_ARG;
+        }
+        if (w2 != lw[l] || h2 != lh[l]) { set_last_error("reference / current extractors differ"); return YGZ_ERR_ARG; }
+        ygz_orb_device_level(orb_ref, l, &pr, &pit_ref[l], &fs_ref[l]);
+        ygz_orb_device_level(orb_cur, l, &pc, &pit_cur[l], &fs_cur[l]);
+        base_ref[l] = (const uint8_t*)pr; base_cur[l] = (const uint8_t*)pc;
+    }
+    std::vector<SiaProblemDev> pd(n_problems);
+    for (int p = 0; p < n_problems; p++) {
+        const ygz_sia_problem& S = problems[p];
+        YGZ_ARG_CHECK(S.n >= 0 && S.n <= h->maxN && ref_frame[p] >= 0 && ref_frame[p] < Bref && cur_frame[p] >= 0 && cur_frame[p] < Bcur);
+        SiaProblemDev& D = pd[p];
+        std::memset(&D, 0, sizeof(D));
+        D.n_levels = max_level + 1; D.n = S.n;
+        D.fx = S.fx; D.fy = S.fy; D.cx = S.cx; D.cy = S.cy;
+        std::memcpy(D.ref_q, S.ref_q, 16); std::memcpy(D.ref_t, S.ref_t, 12);
+        std::memcpy(D.cur_q, S.cur_q, 16); std::memcpy(D.cur_t, S.cur_t, 12);
+        for (int l = min_level; l <= max_level; l++) {
+            D.level_w[l] = lw[l]; D.level_h[l] = lh[l]; D.inv_scale[l] = inv_scale[l];
+            D.img_ref[l] = base_ref[l] + (size_t)ref_frame[p] * fs_ref[l]; D.stride_ref[l] = pit_ref[l];
+            D.img_cur[l] = base_cur[l] + (size_t)cur_frame[p] * fs_cur[l]; D.stride_cur[l] = pit_cur[l];
         }
     }
-    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_prob, pd.data(), (size_t)n_problems * sizeof(SiaProblemDev), cudaMemcpyHostToDevice, h->stream));
-    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));      // pd / pageable sources must outlive the copies
-    SiaArgs A = make_args(h, max_level, min_level, n_iter, eps);
-    { NvtxRange nvtx_range("ygz/SparseImgAlign::run");
-    k_sia_align<<<n_problems, SIA_THREADS, 0, h->stream>>>(A);
+    // the pyramids are written on the extractors' streams: order this handle's stream behind both
+    YGZ_CUDA_TRY(cudaEventRecord(h->ev_dep, (cudaStream_t)ygz_orb_stream(orb_ref)));
+    YGZ_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_dep, 0));
+    if (orb_cur != orb_ref) {
+        YGZ_CUDA_TRY(cudaEventRecord(h->ev_dep, (cudaStream_t)ygz_orb_stream(orb_cur)));
+        YGZ_CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_dep, 0));
     }
-    YGZ_CUDA_TRY(cudaGetLastError());
-    h->last_n = n_problems;
-    YGZ_CUDA_TRY(cudaMemcpyAsync(out_q, h->d_q, (size_t)n_problems * 16, cudaMemcpyDeviceToHost, h->stream));
-    YGZ_CUDA_TRY(cudaMemcpyAsync(out_t, h->d_t, (size_t)n_problems * 12, cudaMemcpyDeviceToHost, h->stream));
-    if (out_H) YGZ_CUDA_TRY(cudaMemcpyAsync(out_H, h->d_H, (size_t)n_problems * 144, cudaMemcpyDeviceToHost, h->stream));
-    YGZ_CUDA_TRY(cudaMemcpyAsync(out_n_tracked, h->d_ntr, (size_t)n_problems * 4, cudaMemcpyDeviceToHost, h->stream));
-    YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    // run() returns 0 and leaves TCR untouched when the reference frame has no keys (:24-27)
-    for (int p = 0; p < n_problems; p++)
-        if (problems[p].n == 0) out_n_tracked[p] = 0;
-    return YGZ_OK;
+    return sia_finish(h, problems, pd, n_problems, max_level, min_level, n_iter, eps, out_q, out_t, out_H, out_n_tracked);
 }
 
 int ygz_sia_last_trace(ygz_sia* h, int problem, float* out, int cap, int* n) {

@@ -106,6 +106,8 @@ def lib(native=False):
     L.orc_search_by_projection_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int]
     L.orc_fuse_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
     L.orc_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, i32p, C.c_float, f32p, f32p, C.c_float]
+    L.orc_fuse_candidates.argtypes = [C.c_void_p, f32p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p, i32p]
+    L.orc_fuse_candidates.restype = None
     L.orc_features_in_area.argtypes = [C.POINTER(FrameView), C.c_float, C.c_float, C.c_float, C.c_int, C.c_int,
                                        i32p, C.c_int]
     L.orc_bf_top2.argtypes = [u8p, C.c_int, u8p, C.c_int, i32p, i32p, i32p]

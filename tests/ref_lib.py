@@ -234,6 +234,7 @@ def adapters_lib():
     L.adp_search_by_projection_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int]
     L.adp_fuse_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
     L.adp_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, i32p, C.c_float, f32p, f32p, C.c_float]
+    L.adp_fuse_kf.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int, C.c_float, u8p, i32p, i32p, i32p]
     return L
 
 
@@ -278,4 +279,8 @@ def matcher_sim3_lib():
     L.refm_search_by_projection_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int]
     L.refm_fuse_sim3.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
     L.refm_search_by_sim3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32p, i32p, C.c_float, f32p, f32p, C.c_float]
+    u8p = C.POINTER(C.c_uint8)
+    L.refm_fuse_kf.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, i32p, C.c_int, C.c_float, u8p, i32p, i32p, i32p]
+    L.refm_fuse_kf_each.argtypes = [C.c_void_p, f32p, C.c_void_p, i32p, C.c_int, C.c_float, i32p]
+    L.refm_fuse_kf_each.restype = None
     return L

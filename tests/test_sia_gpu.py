@@ -99,3 +99,48 @@ def test_sia_rollback_from_bad_init(gpu, oracle, synth):
     print("bad-init case: |gpu - cpu| = %.2e, |cpu(float sums) - cpu(exact sums)| = %.2e, traces %d / %d iterations" %
           (d_gpu, d_cpu, len(otr), len(wtr)))
     assert d_gpu <= max(POSE_TOL, d_cpu), (d_gpu, d_cpu)
+
+
+def test_sia_run_orb_reads_the_extractor_pyramids_in_place(gpu, oracle, synth):
+    """ygz_sia_run_orb (level images taken from ORBextractor handles, pitch != width) == ygz_sia_run on the downloaded levels, bit for
+    bit (same kernel, same pixels), and == the oracle within the pose tolerance.  One handle holds [ref0, cur0, ref1, cur1]; a second
+    single-frame handle provides a current frame from ANOTHER handle / stream."""
+    nl, W, Hh = 4, 752, 480
+    scenes = [synth.synth_sia_pair(sd, n_pts=200, w=W, h=Hh) for sd in (11, 12)]
+    ex = gpu.ORBextractor(100, 2.0, nl, 20, 7, width=W, height=Hh, max_batch=4)
+    ex2 = gpu.ORBextractor(100, 2.0, nl, 20, 7, width=W, height=Hh, max_batch=1)
+    ex.extract_batch([scenes[0]["ref"], scenes[0]["cur"], scenes[1]["ref"], scenes[1]["cur"]])
+    ex2.extract_batch([scenes[1]["cur"]])
+    inv = ex.tables()["inv_scale"]
+    rng = np.random.default_rng(3)
+    valid = [(rng.random(200) < 0.85).astype(np.uint8) for _ in scenes]
+    feats = [gpu.make_sia_features(s["K"], s["px"], s["xyz"], valid=v) for s, v in zip(scenes, valid)]
+    sia = gpu.SparseImgAlign(3, 1, 10, max_problems=4, max_features=256)
+    q, t, Hm, nt = sia.run_batch_orb(ex, ex, feats, [0, 2], [1, 3])
+    traces = [sia.trace(i) for i in range(2)]
+    # the same through host level images
+    host = []
+    for i, (s, v) in enumerate(zip(scenes, valid)):
+        ref = [ex.level(2 * i, l) for l in range(nl)]
+        cur = [ex.level(2 * i + 1, l) for l in range(nl)]
+        host.append(gpu.make_sia_problem(ref, cur, inv, s["K"], s["px"], s["xyz"], valid=v))
+    q2, t2, H2, nt2 = sia.run_batch(host)
+    assert (nt == nt2).all() and (nt > 120).all()
+    assert np.array_equal(q, q2) and np.array_equal(t, t2) and np.array_equal(Hm, H2)
+    for i in range(2):
+        assert np.array_equal(traces[i], sia.trace(i))
+    # current frame from a second handle (its own stream): same answer as problem 1
+    q3, t3, H3, nt3 = sia.run_batch_orb(ex, ex2, [feats[1]], [2], [0])
+    assert nt3[0] == nt[1] and np.array_equal(q3[0], q[1]) and np.array_equal(t3[0], t[1])
+    # oracle
+    for i, (s, v) in enumerate(zip(scenes, valid)):
+        po, _ = build_problem(gpu, oracle, synth, (11, 12)[i], oracle.SiaProblem, valid=v)
+        on, oq, ot, oH, _ = oracle.sia_run(po, 3, 1, 10, 1e-6)
+        assert nt[i] == on
+        assert pose_diff(q[i], t[i], oq, ot) <= POSE_TOL
+    # argument errors: frame index outside the handle, level beyond the pyramid
+    with pytest.raises(Exception):
+        sia.run_batch_orb(ex, ex, [feats[0]], [0], [4])
+    deep = gpu.SparseImgAlign(4, 1, 10, max_problems=1, max_features=256)
+    with pytest.raises(Exception):
+        deep.run_batch_orb(ex, ex, [feats[0]], [0], [1])
