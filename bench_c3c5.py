@@ -181,8 +181,8 @@ def run_c5(args, B, ctx):
     ctr = exL.counters()
     ctr["matches"] = n_match
     ctr["elapsed_ns"] = int(ms_dev * 1e6)
-    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e, t_orb])
-    t_dev, t_e, t_o = shard.timings_max(gathered, 3)
+    gathered = shard.gather_counters(dist, ctr, device="cuda" if dist is not None else None, timings_s=[ms_dev / 1e3, t_e2e])
+    t_dev, t_e = shard.timings_max(gathered, 2)
     if rank != 0:
         return
     total = world * B * args.steps

@@ -1475,6 +1475,7 @@ int ygz_fuse_candidates(ygz_matcher* h, const ygz_frame_view* kf, const float* O
         float dt = PO[0] * Pn[0]; dt += PO[1] * Pn[1]; dt += PO[2] * Pn[2];
         if (dt < 0.5 * dist3D) continue;
         const int lvl = predict_scale_h(mps->max_dist[pMP], dist3D, kf);
+        all.clear();                                                        // features_in_area appends
         features_in_area(kf, g, u, v, th * kf->scale_factors[lvl], -1, -1, all);
         const int first = (int)pq.size();
         for (int idx : all) {
