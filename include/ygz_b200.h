@@ -92,6 +92,12 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
  * SURVEY.md §8(f) rank 2. */
 int ygz_orb_extract_frame_dso(ygz_orb* h, const uint8_t* image, int row_stride, int n_existing, ygz_keypoint* kps,
                               uint8_t* desc, int* count, int cap, int* grid_size);
+/* The same for n_frames frames of n_frames independent streams in one call (batched over cameras / sequences; frames of ONE stream are
+ * sequential through mnGridSize).  images as in ygz_orb_upload; kps / desc are [n_frames][cap] rows whose first n_existing[f] entries are
+ * frame f's direct-tracked keys; counts[f] = keys of frame f after the call; grid_sizes[f] = that stream's mnGridSize, in / out (-1: first
+ * frame).  Results are identical to n_frames calls of ygz_orb_extract_frame_dso; the adaptive cell-size loop runs on the device. */
+int ygz_orb_extract_frame_dso_batch(ygz_orb* h, const uint8_t* images, int n_frames, size_t frame_stride, int row_stride,
+                                    const int* n_existing, ygz_keypoint* kps, uint8_t* desc, int* counts, int cap, int* grid_sizes);
 int ygz_orb_compute_pyramid(ygz_orb* h, const uint8_t* images, int n, size_t frame_stride, int row_stride);
 /* mvImagePyramid[level] of frame f (include/ORBextractor.h:106), continuous w*h bytes (step == cols,
  * as Frame clones it, src/Frame.cc:810-813).  border > 0 additionally reproduces the EDGE_THRESHOLD

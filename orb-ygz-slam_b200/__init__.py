@@ -90,7 +90,7 @@ class ProjectionCamera(C.Structure):      # ygz_projection_camera
 ABI_SYMBOLS = [
     "ygz_last_error", "ygz_device_count", "ygz_device_info",
     "ygz_orb_create", "ygz_orb_destroy", "ygz_orb_tables", "ygz_orb_level_size", "ygz_orb_max_keypoints", "ygz_orb_max_batch",
-    "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_extract_frame_dso",
+    "ygz_orb_extract", "ygz_orb_extract_async", "ygz_orb_wait", "ygz_orb_extract_frame", "ygz_orb_extract_frame_dso", "ygz_orb_extract_frame_dso_batch",
     "ygz_orb_compute_pyramid", "ygz_orb_get_level", "ygz_orb_get_blurred_level",
     "ygz_orb_upload", "ygz_orb_run", "ygz_orb_download", "ygz_orb_sync", "ygz_orb_get_candidates",
     "ygz_orb_time", "ygz_debug_cos_sin", "ygz_orb_device_outputs", "ygz_orb_device_level", "ygz_orb_stream", "ygz_orb_counters",
@@ -134,6 +134,7 @@ def lib():
     sigs.setdefault('ygz_orb_max_keypoints', {})['argtypes'] = [C.c_void_p]
     sigs.setdefault('ygz_orb_extract', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     sigs.setdefault('ygz_orb_extract_frame', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, i32p, C.c_int]
+    sigs.setdefault('ygz_orb_extract_frame_dso_batch', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, i32p, C.c_void_p, C.c_void_p, i32p, C.c_int, i32p]
     sigs.setdefault('ygz_orb_extract_frame_dso', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, i32p, C.c_int, i32p]
     sigs.setdefault('ygz_orb_compute_pyramid', {})['argtypes'] = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int]
     sigs.setdefault('ygz_orb_get_level', {})['argtypes'] = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -336,6 +337,24 @@ class ORBextractor:
         _check(self.L.ygz_orb_extract_frame_dso(self.h, image.ctypes.data, image.strides[0], ne, kps.ctypes.data,
                                                 desc.ctypes.data, C.byref(cnt), cap, C.byref(g)), "ygz_orb_extract_frame_dso")
         return kps[:cnt.value].copy(), desc[:cnt.value].copy(), g.value
+
+    def extract_frame_dso_batch(self, images, existing, grid_sizes, cap=None):
+        """ygz_orb_extract_frame_dso_batch: frame f of B independent streams with its own existing keys and mnGridSize.
+        Returns ([(keypoints, descriptors)] per frame, grid sizes after the call)."""
+        images = self._imgs(images)
+        B = images.shape[0]
+        ne = np.array([len(e) for e in existing], np.int32)
+        cap = cap or (3 * (images.shape[1] // 7) * (images.shape[2] // 7) + int(ne.max(initial=0)))
+        kps = np.zeros((B, cap), KP_DTYPE)
+        for f in range(B):
+            kps[f, :ne[f]] = existing[f]
+        desc = np.zeros((B, cap, 32), np.uint8)
+        counts = np.zeros(B, np.int32)
+        g = np.ascontiguousarray(grid_sizes, np.int32).copy()
+        _check(self.L.ygz_orb_extract_frame_dso_batch(self.h, images.ctypes.data, B, images.strides[0], images.strides[1], _ptr(ne, i32p),
+                                                      kps.ctypes.data, desc.ctypes.data, _ptr(counts, i32p), cap, _ptr(g, i32p)),
+               "ygz_orb_extract_frame_dso_batch")
+        return [(kps[f, :counts[f]].copy(), desc[f, :counts[f]].copy()) for f in range(B)], g
 
     def ComputePyramid(self, images):
         images = self._imgs(images)

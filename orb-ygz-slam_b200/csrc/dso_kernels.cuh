@@ -64,12 +64,10 @@ struct DsoParams {
 // better(a, b): a precedes b in the reference's order (score desc, raster index asc)
 __device__ __forceinline__ bool dso_better(float sa, int ia, float sb, int ib) { return sa > sb || (sa == sb && ia < ib); }
 
-__global__ void __launch_bounds__(DSO_WARPS * 32) k_dso_cells(DsoParams P, uint32_t* __restrict__ cell_keys,
-                                                               uint8_t* __restrict__ cell_cnt, int warp_smem) {
-    extern __shared__ __align__(16) uint8_t dso_smem[];
+// one warp, one grid cell k of the frame described by P
+__device__ __forceinline__ void dso_cell(const DsoParams& P, int k, uint32_t* __restrict__ cell_keys, uint8_t* __restrict__ cell_cnt,
+                                         uint8_t* dso_smem, int warp_smem) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k = blockIdx.x * DSO_WARPS + warp;
-    if (k >= P.n_rows * P.n_cols) return;
     const int nn = k / P.n_cols, col = k - nn * P.n_cols;
     if (nn == 0 || nn == P.n_rows - 1 || col == 0 || col == P.n_cols - 1) { if (lane == 0) cell_cnt[k] = 0; return; }   // :1319-1321
     const int g = P.g, x_start = col * g, y_start = nn * g;
@@ -132,9 +130,38 @@ __global__ void __launch_bounds__(DSO_WARPS * 32) k_dso_cells(DsoParams P, uint3
     if (lane == 0) cell_cnt[k] = (uint8_t)n_out;
 }
 
-// cell-order compaction of the per-cell winners (one CTA; cells <= (h/7) * (w/7))
-__global__ void __launch_bounds__(1024) k_dso_compact(const uint32_t* __restrict__ cell_keys, const uint8_t* __restrict__ cell_cnt,
-                                                      int n_cells, uint32_t* __restrict__ keys_out, int* __restrict__ total_out) {
+__global__ void __launch_bounds__(DSO_WARPS * 32) k_dso_cells(DsoParams P, uint32_t* __restrict__ cell_keys,
+                                                               uint8_t* __restrict__ cell_cnt, int warp_smem) {
+    extern __shared__ __align__(16) uint8_t dso_smem[];
+    const int k = blockIdx.x * DSO_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_rows * P.n_cols) return;
+    dso_cell(P, k, cell_keys, cell_cnt, dso_smem, warp_smem);
+}
+
+// ---- batched form: B independent streams, each with its own adaptive cell size.  The `while (cnt < n)` loop of :1300-1371 runs as a
+// fixed number of (cells, compact) launch pairs; a frame whose loop has ended is skipped on the device, so the host synchronises once
+// per group of passes instead of once per pass per frame.
+struct DsoFrameState { int g, cnt, done, n_existing; };
+
+__global__ void __launch_bounds__(DSO_WARPS * 32) k_dso_cells_batch(DsoParams P0, size_t img_stride, int max_cells,
+                                                                     const DsoFrameState* __restrict__ state,
+                                                                     uint32_t* __restrict__ cell_keys, uint8_t* __restrict__ cell_cnt) {
+    extern __shared__ __align__(16) uint8_t dso_smem[];
+    const int f = blockIdx.y;
+    const DsoFrameState st = state[f];
+    if (st.done) return;
+    DsoParams P = P0;
+    P.img += (size_t)f * img_stride;
+    P.occ += (size_t)f * P.w * P.h;
+    P.g = st.g; P.n_rows = P.h / st.g; P.n_cols = P.w / st.g;
+    const int k = blockIdx.x * DSO_WARPS + (threadIdx.x >> 5);
+    if (k >= P.n_rows * P.n_cols) return;
+    dso_cell(P, k, cell_keys + (size_t)f * max_cells * 3, cell_cnt + (size_t)f * max_cells, dso_smem, dso_warp_smem(st.g));
+}
+
+// cell-order compaction of the per-cell winners (one CTA; cells <= (h/7) * (w/7)); returns the total to every thread
+__device__ __forceinline__ int dso_compact(const uint32_t* __restrict__ cell_keys, const uint8_t* __restrict__ cell_cnt, int n_cells,
+                                           uint32_t* __restrict__ keys_out) {
     __shared__ int wsum[32];
     __shared__ int base;
     if (threadIdx.x == 0) base = 0;
@@ -161,7 +188,38 @@ __global__ void __launch_bounds__(1024) k_dso_compact(const uint32_t* __restrict
         if (threadIdx.x == 0) base += wsum[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total_out = base;
+    return base;
+}
+
+__global__ void __launch_bounds__(1024) k_dso_compact(const uint32_t* __restrict__ cell_keys, const uint8_t* __restrict__ cell_cnt,
+                                                      int n_cells, uint32_t* __restrict__ keys_out, int* __restrict__ total_out) {
+    const int total = dso_compact(cell_keys, cell_cnt, n_cells, keys_out);
+    if (threadIdx.x == 0) *total_out = total;
+}
+
+// one CTA per frame: compaction, then the loop control of :1300-1375 for that frame
+//   while (cnt < n) { if (cnt > 0) { g -= 5; if (g < 7) { g = 7; break; } }  <pass>  }   (a pass that finds nothing ends the loop, as the oracle)
+//   if (cnt > n) g += 5;
+__global__ void __launch_bounds__(1024) k_dso_compact_batch(const uint32_t* __restrict__ cell_keys, const uint8_t* __restrict__ cell_cnt,
+                                                            int w, int h, int max_cells, int n_wanted, uint32_t* __restrict__ keys_out,
+                                                            DsoFrameState* __restrict__ state) {
+    const int f = blockIdx.x;
+    DsoFrameState st = state[f];
+    if (st.done) return;
+    const int n_cells = (h / st.g) * (w / st.g);
+    const int total = dso_compact(cell_keys + (size_t)f * max_cells * 3, cell_cnt + (size_t)f * max_cells, n_cells,
+                                  keys_out + (size_t)f * max_cells * 3);
+    if (threadIdx.x == 0) {
+        st.cnt = total;
+        if (total == 0 || total >= n_wanted) {
+            st.done = 1;
+            if (total > n_wanted) st.g += 5;
+        } else {
+            st.g -= 5;
+            if (st.g < 7) { st.g = 7; st.done = 1; }
+        }
+        state[f] = st;
+    }
 }
 
 // mOccupancy.ptr(cvRound(kp.pt.y))[cvRound(kp.pt.x)] = 255, :1283-1285
@@ -170,6 +228,15 @@ __global__ void k_dso_mark_occupancy(const float2* __restrict__ pts, int n, uint
     if (i >= n) return;
     const int x = __float2int_rn(pts[i].x), y = __float2int_rn(pts[i].y);
     if (x >= 0 && y >= 0 && x < w && y < h) occ[(size_t)y * w + x] = 255;
+}
+
+// the same for a batch: pts[i] belongs to frame fid[i]
+__global__ void k_dso_mark_occupancy_batch(const float2* __restrict__ pts, const int* __restrict__ fid, int n, uint8_t* __restrict__ occ,
+                                           int w, int h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = __float2int_rn(pts[i].x), y = __float2int_rn(pts[i].y);
+    if (x >= 0 && y >= 0 && x < w && y < h) occ[(size_t)fid[i] * w * h + (size_t)y * w + x] = 255;
 }
 
 }  // namespace ygz_b200

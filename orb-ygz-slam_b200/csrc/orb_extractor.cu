@@ -86,6 +86,10 @@ struct ygz_orb {
     float2* d_dso_pts = nullptr;
     int dso_pts_cap = 0;
     int dso_grid = -1;
+    int dso_frames = 0;                 // frames the DSO scratch (d_occ, d_cell_*, d_dso_keys) is allocated for
+    DsoFrameState* d_dso_state = nullptr;
+    int* d_dso_fid = nullptr;           // frame id per existing key point of a batch (k_dso_mark_occupancy_batch)
+    int dso_fid_cap = 0;
     int last_n = 0;
 };
 
@@ -124,7 +128,7 @@ static int orb_free(ygz_orb* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
-    cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_pts);
+    cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_pts); cudaFree(h->d_dso_state); cudaFree(h->d_dso_fid);
     cudaFree(h->d_cells); cudaFree(h->d_pool); cudaFree(h->d_cell_count); cudaFree(h->d_keys);
     cudaFree(h->d_keynode); cudaFree(h->d_nkeys); cudaFree(h->d_sel); cudaFree(h->d_nsel);
     cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_counts); cudaFree(h->d_existing); cudaFree(h->d_stage); cudaFree(h->d_pattern);
@@ -735,6 +739,26 @@ int ygz_orb_extract_frame(ygz_orb* h, const uint8_t* image, int row_stride, int 
     return YGZ_OK;
 }
 
+// scratch of the DSO selection for `frames` frames: occupancy maps, per-cell winners, compacted key lists, loop state
+static int dso_ensure(ygz_orb* h, int frames) {
+    if (frames <= h->dso_frames) return YGZ_OK;
+    const int W = h->cfg.width, H = h->cfg.height;
+    const size_t max_cells = (size_t)std::max((H / 7) * (W / 7), 1), F = (size_t)frames;
+    cudaFree(h->d_occ); cudaFree(h->d_cell_keys); cudaFree(h->d_cell_cnt); cudaFree(h->d_dso_keys); cudaFree(h->d_dso_total); cudaFree(h->d_dso_state);
+    h->d_occ = nullptr; h->d_cell_keys = nullptr; h->d_cell_cnt = nullptr; h->d_dso_keys = nullptr; h->d_dso_total = nullptr; h->d_dso_state = nullptr;
+    h->dso_frames = 0;
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_occ, F * W * H));
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_cell_keys, F * max_cells * 3 * 4));
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_cell_cnt, F * max_cells));
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_keys, F * max_cells * 3 * 4));
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_total, 4));
+    YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_state, F * sizeof(DsoFrameState)));
+    YGZ_CUDA_TRY(cudaFuncSetAttribute(k_dso_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, DSO_WARPS * dso_warp_smem(DSO_GMAX)));
+    YGZ_CUDA_TRY(cudaFuncSetAttribute(k_dso_cells_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, DSO_WARPS * dso_warp_smem(DSO_GMAX)));
+    h->dso_frames = frames;
+    return YGZ_OK;
+}
+
 // operator()(Frame*, keypoints, descriptors, DSO_KEYPOINT), src/ORBextractor.cc:1031-1127: ComputeKeyPointsDSOSingleLevel
 // (:1277-1381) on level 0 + descriptors of the pre-existing and the new keys.  One frame per call: the adaptive cell size
 // mnGridSize is state carried from frame to frame (*grid_size in/out; NULL = the handle keeps it).
@@ -744,16 +768,8 @@ int ygz_orb_extract_frame_dso(ygz_orb* h, const uint8_t* image, int row_stride, 
     YGZ_CUDA_TRY(cudaSetDevice(h->device));
     const int W = h->cfg.width, H = h->cfg.height, n = h->cfg.nfeatures;
     const LevelHost& L0 = h->lv[0];
-    const int max_cells = (H / 7) * (W / 7);
-    if (!h->d_occ) {
-        YGZ_CUDA_TRY(cudaMalloc(&h->d_occ, (size_t)W * H));
-        YGZ_CUDA_TRY(cudaMalloc(&h->d_cell_keys, (size_t)std::max(max_cells, 1) * 3 * 4));
-        YGZ_CUDA_TRY(cudaMalloc(&h->d_cell_cnt, (size_t)std::max(max_cells, 1)));
-        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_keys, (size_t)std::max(max_cells, 1) * 3 * 4));
-        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_total, 4));
-        YGZ_CUDA_TRY(cudaFuncSetAttribute(k_dso_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, DSO_WARPS * dso_warp_smem(DSO_GMAX)));
-    }
     int rc;
+    if ((rc = dso_ensure(h, 1))) return rc;
     if ((rc = ygz_orb_upload(h, image, 1, (size_t)row_stride * H, row_stride))) return rc;
     if (n_existing > h->existing_cap) {
         cudaFree(h->d_existing); h->d_existing = nullptr;
@@ -847,6 +863,150 @@ int ygz_orb_extract_frame_dso(ygz_orb* h, const uint8_t* image, int row_stride, 
     h->ctr.kernel_launches += launches;
     h->ctr.frames += 1;
     h->ctr.keypoints += *count;
+    return YGZ_OK;
+}
+
+// The same for n_frames frames of n_frames INDEPENDENT streams (one mnGridSize each: grid_sizes[f] in / out, -1 before a stream's first
+// frame).  kps / desc are [n_frames][cap]; the first n_existing[f] key points of row f are that frame's direct-tracked keys.
+// The adaptive loop runs on the device (k_dso_cells_batch / k_dso_compact_batch, four passes per host synchronisation).
+int ygz_orb_extract_frame_dso_batch(ygz_orb* h, const uint8_t* images, int n_frames, size_t frame_stride, int row_stride, const int* n_existing,
+                                    ygz_keypoint* kps, uint8_t* desc, int* counts, int cap, int* grid_sizes) {
+    YGZ_ARG_CHECK(h && images && n_frames >= 1 && n_frames <= h->cfg.max_batch && n_existing && kps && desc && counts && grid_sizes && cap >= 0);
+    YGZ_CUDA_TRY(cudaSetDevice(h->device));
+    const int W = h->cfg.width, H = h->cfg.height, n = h->cfg.nfeatures, B = n_frames;
+    const LevelHost& L0 = h->lv[0];
+    const int max_cells = std::max((H / 7) * (W / 7), 1);
+    int rc;
+    if ((rc = dso_ensure(h, B))) return rc;
+    int ex_stride = 1, ex_total = 0;
+    for (int f = 0; f < B; f++) {
+        YGZ_ARG_CHECK(n_existing[f] >= 0 && n_existing[f] <= cap);
+        ex_stride = std::max(ex_stride, n_existing[f]);
+        ex_total += n_existing[f];
+    }
+    if ((rc = ygz_orb_upload(h, images, B, frame_stride, row_stride))) return rc;
+    if (B * ex_stride > h->existing_cap) {
+        cudaFree(h->d_existing); h->d_existing = nullptr; h->existing_cap = 0;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_existing, (size_t)B * ex_stride * sizeof(ExistingKey)));
+        h->existing_cap = B * ex_stride;
+    }
+    if (ex_total > h->dso_pts_cap) {
+        cudaFree(h->d_dso_pts); h->d_dso_pts = nullptr; h->dso_pts_cap = 0;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_pts, (size_t)ex_total * sizeof(float2)));
+        h->dso_pts_cap = ex_total;
+    }
+    if (ex_total > h->dso_fid_cap) {
+        cudaFree(h->d_dso_fid); h->d_dso_fid = nullptr; h->dso_fid_cap = 0;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_dso_fid, (size_t)ex_total * sizeof(int)));
+        h->dso_fid_cap = ex_total;
+    }
+    std::vector<ExistingKey> ek((size_t)B * ex_stride);
+    std::vector<float2> pts((size_t)ex_total);
+    std::vector<int> fid((size_t)ex_total);
+    std::vector<DsoFrameState> st(B);
+    int gmax = 0, gmin = 1 << 30;
+    for (int f = 0, o = 0; f < B; f++) {
+        const ygz_keypoint* K = kps + (size_t)f * cap;
+        for (int i = 0; i < n_existing[f]; i++, o++) {
+            const int oct = K[i].octave;
+            if (oct < 0 || oct >= h->cfg.nlevels) { set_last_error("existing key octave out of range"); return YGZ_ERR_ARG; }
+            ExistingKey& e = ek[(size_t)f * ex_stride + i];
+            e.x = K[i].x * h->inv_scale[oct];          // kp.pt * mvInvScaleFactor[kp.octave], :1095 and :1379
+            e.y = K[i].y * h->inv_scale[oct];
+            e.angle = K[i].angle;
+            e.octave = oct;
+            pts[o] = make_float2(K[i].x, K[i].y);
+            fid[o] = f;
+        }
+        int g = grid_sizes[f];
+        if (g < 0) g = static_cast<int>(std::sqrt(1.0 * H * W / n));
+        if (g < 7 || g > DSO_GMAX) { set_last_error("DSO grid size outside [7, 96]"); return YGZ_ERR_ARG; }
+        st[f] = DsoFrameState{g, 0, 0, n_existing[f]};
+        gmax = std::max(gmax, g); gmin = std::min(gmin, g);
+    }
+    YGZ_CUDA_TRY(cudaMemsetAsync(h->d_occ, 0, (size_t)B * W * H, h->stream));
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_dso_state, st.data(), (size_t)B * sizeof(DsoFrameState), cudaMemcpyHostToDevice, h->stream));
+    if (ex_total) {
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_existing, ek.data(), ek.size() * sizeof(ExistingKey), cudaMemcpyHostToDevice, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_dso_pts, pts.data(), (size_t)ex_total * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_dso_fid, fid.data(), (size_t)ex_total * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        k_dso_mark_occupancy_batch<<<ceil_div(ex_total, 256), 256, 0, h->stream>>>(h->d_dso_pts, h->d_dso_fid, ex_total, h->d_occ, W, H);
+    }
+    if ((rc = launch_pyramid(h, B))) return rc;
+    if ((rc = launch_blur(h, B))) return rc;
+    int launches = (h->cfg.nlevels - 1) + 1 + (ex_total > 0);
+    DsoParams D;
+    D.img = L0.d_base; D.occ = h->d_occ; D.w = W; D.h = H; D.pitch = L0.pitch; D.g = 0; D.n_rows = 0; D.n_cols = 0;
+    const size_t smem = (size_t)DSO_WARPS * dso_warp_smem(gmax);          // cell sizes only shrink inside the loop
+    int passes = 0;
+    for (bool all_done = false; !all_done;) {
+        for (int k = 0; k < 4; k++, passes++) {
+            const int g_lo = std::max(7, gmin - 5 * passes);               // smallest cell size any frame can have in this pass
+            const int cells = (H / g_lo) * (W / g_lo);
+            if (cells > 0)
+                k_dso_cells_batch<<<dim3(ceil_div(cells, DSO_WARPS), B), DSO_WARPS * 32, smem, h->stream>>>(D, L0.frame_stride, max_cells, h->d_dso_state,
+                                                                                                           h->d_cell_keys, h->d_cell_cnt);
+            k_dso_compact_batch<<<B, 1024, 0, h->stream>>>(h->d_cell_keys, h->d_cell_cnt, W, H, max_cells, n, h->d_dso_keys, h->d_dso_state);
+            launches += 2;
+        }
+        YGZ_CUDA_TRY(cudaGetLastError());
+        YGZ_CUDA_TRY(cudaMemcpyAsync(st.data(), h->d_dso_state, (size_t)B * sizeof(DsoFrameState), cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        all_done = true;
+        for (int f = 0; f < B; f++) all_done = all_done && st[f].done;
+        if (passes > 40) { set_last_error("DSO selection did not terminate"); return YGZ_ERR_CUDA; }
+    }
+    int max_cnt = 0, max_count = 0;
+    for (int f = 0; f < B; f++) {
+        grid_sizes[f] = st[f].g;
+        counts[f] = n_existing[f] + st[f].cnt;
+        max_cnt = std::max(max_cnt, st[f].cnt);
+        max_count = std::max(max_count, counts[f]);
+    }
+    if (max_count > h->P.out_cap) {
+        const int MB = h->cfg.max_batch;
+        cudaFree(h->d_kps); cudaFree(h->d_desc);
+        h->d_kps = nullptr; h->d_desc = nullptr;
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_kps, (size_t)max_count * MB * sizeof(ygz_keypoint)));
+        YGZ_CUDA_TRY(cudaMalloc(&h->d_desc, (size_t)max_count * MB * 32));
+        h->P.out_cap = max_count;
+    }
+    if (max_count > cap) { set_last_error("keypoint buffer too small"); return YGZ_ERR_CAPACITY; }
+    const int4* per_frame = reinterpret_cast<const int4*>(h->d_dso_state);
+    if (ex_total > 0) {
+        k_orient_describe<<<dim3(ceil_div(ex_stride, DESC_WARPS), B), DESC_THREADS, 0, h->stream>>>(
+            h->P, h->patch, 3, ex_stride, ex_stride, h->d_pattern, h->d_sel, h->d_nsel, h->d_existing, h->d_kps, h->d_desc, h->d_counts, per_frame);
+        launches++;
+    }
+    if (max_cnt > 0) {
+        k_orient_describe<<<dim3(ceil_div(max_cnt, DESC_WARPS), B), DESC_THREADS, 0, h->stream>>>(
+            h->P, h->patch, 2, ex_stride, max_cells * 3, h->d_pattern, h->d_dso_keys, h->d_nsel, nullptr, h->d_kps, h->d_desc, h->d_counts, per_frame);
+        launches++;
+    }
+    YGZ_CUDA_TRY(cudaGetLastError());
+    YGZ_CUDA_TRY(cudaMemcpyAsync(h->d_counts, counts, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, h->stream));     // zero-copy chaining sees the counts
+    uint64_t total = 0;
+    if (max_count > 0) {
+        const int oc = h->P.out_cap;
+        std::vector<ygz_keypoint> tmp((size_t)B * max_count);
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(tmp.data(), (size_t)max_count * sizeof(ygz_keypoint), h->d_kps, (size_t)oc * sizeof(ygz_keypoint),
+                                       (size_t)max_count * sizeof(ygz_keypoint), B, cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)oc * 32, (size_t)max_count * 32, B, cudaMemcpyDeviceToHost, h->stream));
+        YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int f = 0; f < B; f++) {
+            ygz_keypoint* K = kps + (size_t)f * cap;
+            const ygz_keypoint* T = tmp.data() + (size_t)f * max_count;
+            for (int i = 0; i < n_existing[f]; i++) K[i].angle = T[i].angle;
+            for (int i = n_existing[f]; i < counts[f]; i++) K[i] = T[i];
+            total += counts[f];
+        }
+    } else {
+        YGZ_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->ctr.kernel_launches += launches;
+    h->ctr.frames += B;
+    h->ctr.keypoints += total;
+    h->last_n = B;
     return YGZ_OK;
 }
 

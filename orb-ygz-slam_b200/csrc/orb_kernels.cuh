@@ -913,7 +913,8 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
                                                                   const ExistingKey* __restrict__ existing,
                                                                   ygz_keypoint* __restrict__ kps_out,
                                                                   uint8_t* __restrict__ desc_out,
-                                                                  int* __restrict__ counts_out) {
+                                                                  int* __restrict__ counts_out,
+                                                                  const int4* __restrict__ per_frame = nullptr) {
     __shared__ __align__(128) uint8_t smem[DESC_WARPS * DESC_WARP_SMEM];
     __shared__ __align__(8) unsigned long long tma_bar[DESC_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -948,13 +949,18 @@ __global__ void __launch_bounds__(DESC_THREADS, 6) k_orient_describe(const __gri
         score = cand_s(c);
         out_idx = before + slot;
     } else if (mode == 2) {
-        const uint32_t c = sel_all[item];
+        // batched DSO selection (per_frame = DsoFrameState {g, cnt, done, n_existing} per frame): n_items is the stride of the key
+        // lists, n_existing the stride of the existing-key lists; the frame's own counts come from its state
+        int ne = n_existing, ni = n_items;
+        if (per_frame) { const int4 st = per_frame[frame]; ne = st.w; ni = st.y; if (item >= ni) return; }
+        const uint32_t c = sel_all[(per_frame ? (size_t)frame * n_items : 0) + item];
         level = 0;
         cx = (int)(c & 0xFFFu);
         cy = (int)((c >> 12) & 0xFFFu);
-        out_idx = n_existing + item;
-        if (item == 0 && lane == 0) counts_out[frame] = n_existing + n_items;
+        out_idx = ne + item;
+        if (item == 0 && lane == 0) counts_out[frame] = ne + ni;
     } else {
+        if (per_frame && item >= per_frame[frame].w) return;
         const ExistingKey ek = existing[(size_t)frame * n_existing + item];
         level = ek.octave;
         cx = __float2int_rn(ek.x);             // cvRound(kpt.pt.x), :111
