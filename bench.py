@@ -438,6 +438,36 @@ def aux_metrics(m, device):
                                   "ms_kernel": r["ms"], "descriptors_per_s": nd / (r["ms"] / 1e3)}
     except Exception as e:
         aux["vocab_transform"] = {"error": str(e)[:200]}
+    try:
+        # DSO_KEYPOINT extraction (YGZ's detector) for a batch of independent streams vs the per-frame entry, host buffers
+        Bd = 64
+        fr = make_frames(91, Bd)
+        exd = m.ORBextractor(width=W, height=H, max_batch=Bd, device=device, **ORB)
+        none = [np.zeros(0, m.KP_DTYPE)] * Bd
+        g0 = np.full(Bd, -1, np.int32)
+        res, g1 = exd.extract_frame_dso_batch(fr, none, g0)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            res, g2 = exd.extract_frame_dso_batch(fr, none, g1)
+        dt_b = (time.perf_counter() - t0) / 3
+        t0 = time.perf_counter()
+        for f in range(Bd):
+            exd.extract_frame_dso(fr[f], none[0], int(g1[f]))
+        dt_s = time.perf_counter() - t0
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O3                                   # CPU arm of this aux line + parity gate (checker only)
+        oxd = O3.Extractor(ORB["nfeatures"], ORB["scaleFactor"], ORB["nlevels"], ORB["iniThFAST"], ORB["minThFAST"])
+        t0 = time.perf_counter(); same = True
+        for f in range(4):
+            ok_, od_, og_ = oxd.extract_frame_dso(fr[f], none[0], int(g1[f]))
+            same = bool(same and og_ == int(g2[f]) and len(ok_) == len(res[f][0]) and bool((od_ == res[f][1]).all()))
+        cdt = (time.perf_counter() - t0) / 4
+        aux["dso_batch"] = {"frames": Bd, "keypoints_per_frame": float(np.mean([len(r[0]) for r in res])),
+                            "frames_per_s_batched_host_buffers": Bd / dt_b, "frames_per_s_per_frame_calls": Bd / dt_s,
+                            "cpu_baseline": {"frames_per_s_1_thread": 1.0 / cdt, "kind": "port"}, "parity_gate_4_frames_identical": same,
+                            "note": "ygz_orb_extract_frame_dso_batch: adaptive cell-size loop on the device, one host sync per four passes"}
+    except Exception as e:
+        aux["dso_batch"] = {"error": str(e)[:200]}
     return aux
 
 
