@@ -344,16 +344,20 @@ class ORBextractor:
         images = self._imgs(images)
         B = images.shape[0]
         ne = np.array([len(e) for e in existing], np.int32)
-        cap = cap or (3 * (images.shape[1] // 7) * (images.shape[2] // 7) + int(ne.max(initial=0)))
-        kps = np.zeros((B, cap), KP_DTYPE)
-        for f in range(B):
-            kps[f, :ne[f]] = existing[f]
-        desc = np.zeros((B, cap, 32), np.uint8)
-        counts = np.zeros(B, np.int32)
-        g = np.ascontiguousarray(grid_sizes, np.int32).copy()
-        _check(self.L.ygz_orb_extract_frame_dso_batch(self.h, images.ctypes.data, B, images.strides[0], images.strides[1], _ptr(ne, i32p),
-                                                      kps.ctypes.data, desc.ctypes.data, _ptr(counts, i32p), cap, _ptr(g, i32p)),
-               "ygz_orb_extract_frame_dso_batch")
+        full = 3 * (images.shape[1] // 7) * (images.shape[2] // 7) + int(ne.max(initial=0))     # three winners in every 7 x 7 cell
+        # the selection stops near nfeatures new keys (overshoot below 3 x): try a tight buffer first, the worst case on YGZ_ERR_CAPACITY
+        for c in ([cap] if cap else [min(full, 4 * self.cfg.nfeatures + int(ne.max(initial=0))), full]):
+            kps = np.zeros((B, c), KP_DTYPE)
+            for f in range(B):
+                kps[f, :ne[f]] = existing[f]
+            desc = np.zeros((B, c, 32), np.uint8)
+            counts = np.zeros(B, np.int32)
+            g = np.ascontiguousarray(grid_sizes, np.int32).copy()
+            rc = self.L.ygz_orb_extract_frame_dso_batch(self.h, images.ctypes.data, B, images.strides[0], images.strides[1], _ptr(ne, i32p),
+                                                        kps.ctypes.data, desc.ctypes.data, _ptr(counts, i32p), c, _ptr(g, i32p))
+            if rc != -3 or c == full or cap:            # YGZ_ERR_CAPACITY
+                break
+        _check(rc, "ygz_orb_extract_frame_dso_batch")
         return [(kps[f, :counts[f]].copy(), desc[f, :counts[f]].copy()) for f in range(B)], g
 
     def ComputePyramid(self, images):

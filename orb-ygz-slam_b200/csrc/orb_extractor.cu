@@ -958,11 +958,12 @@ int ygz_orb_extract_frame_dso_batch(ygz_orb* h, const uint8_t* images, int n_fra
     }
     int max_cnt = 0, max_count = 0;
     for (int f = 0; f < B; f++) {
-        grid_sizes[f] = st[f].g;
-        counts[f] = n_existing[f] + st[f].cnt;
+        counts[f] = n_existing[f] + st[f].cnt;                  // also on YGZ_ERR_CAPACITY: tells the caller what to allocate
         max_cnt = std::max(max_cnt, st[f].cnt);
         max_count = std::max(max_count, counts[f]);
     }
+    if (max_count > cap) { set_last_error("keypoint buffer too small"); return YGZ_ERR_CAPACITY; }     // grid_sizes untouched: the call can be repeated
+    for (int f = 0; f < B; f++) grid_sizes[f] = st[f].g;
     if (max_count > h->P.out_cap) {
         const int MB = h->cfg.max_batch;
         cudaFree(h->d_kps); cudaFree(h->d_desc);
@@ -971,7 +972,6 @@ int ygz_orb_extract_frame_dso_batch(ygz_orb* h, const uint8_t* images, int n_fra
         YGZ_CUDA_TRY(cudaMalloc(&h->d_desc, (size_t)max_count * MB * 32));
         h->P.out_cap = max_count;
     }
-    if (max_count > cap) { set_last_error("keypoint buffer too small"); return YGZ_ERR_CAPACITY; }
     const int4* per_frame = reinterpret_cast<const int4*>(h->d_dso_state);
     if (ex_total > 0) {
         k_orient_describe<<<dim3(ceil_div(ex_stride, DESC_WARPS), B), DESC_THREADS, 0, h->stream>>>(

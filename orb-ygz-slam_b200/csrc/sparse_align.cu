@@ -120,52 +120,95 @@ __device__ inline SE3 se3_exp(const float* a) {                     // se3.hpp:4
     return T;
 }
 
-// Eigen LDLT<Matrix6f>::compute + solve: symmetric pivoting on the largest diagonal entry, pseudo-inverse of D
-__device__ void ldlt_solve6(const float* Ain, const float* b, float* x) {
-    const int n = 6;
+// Eigen LDLT<Matrix6f>::compute + solve: symmetric pivoting on the largest diagonal entry, pseudo-inverse of D.
+// Every loop is unrolled and the data-dependent transposition (k <-> big) is dispatched over the possible values of `big`, so that all
+// indices are compile-time and the 6 x 6 matrix stays in registers (with run-time indices it lived in local memory: the one thread that
+// solves was a chain of ~300 dependent L1 accesses per iteration, and the other 255 waited at the barrier — 42 % of the stall samples
+// of the r2 profile).  Same operations in the same order as before.
+__device__ __forceinline__ void swapf(float& a, float& b) { const float t = a; a = b; b = t; }
+__device__ __forceinline__ void ldlt_solve6(const float* Ain, const float* b, float* x) {
+    constexpr int n = 6;
     float m[36];
+#pragma unroll
     for (int i = 0; i < 36; i++) m[i] = Ain[i];
-    int tr[6];
+    int tr[6] = {0, 1, 2, 3, 4, 5};
     bool zero_first = false;
 #define M(r, c) m[(r) * 6 + (c)]
+#pragma unroll
     for (int k = 0; k < n; k++) {
+        if (zero_first) continue;                               // (the `break` of the rolled loop)
         int big = k;
         float bigv = fabsf(M(k, k));
-        for (int i = k + 1; i < n; i++) if (fabsf(M(i, i)) > bigv) { bigv = fabsf(M(i, i)); big = i; }
+#pragma unroll
+        for (int i = k + 1; i < n; i++) { const float v = fabsf(M(i, i)); if (v > bigv) { bigv = v; big = i; } }
         tr[k] = big;
-        if (k != big) {
-            const int s = n - big - 1;
-            for (int c = 0; c < k; c++) { float t = M(k, c); M(k, c) = M(big, c); M(big, c) = t; }
-            for (int i = 0; i < s; i++) { float t = M(big + 1 + i, k); M(big + 1 + i, k) = M(big + 1 + i, big); M(big + 1 + i, big) = t; }
-            { float t = M(k, k); M(k, k) = M(big, big); M(big, big) = t; }
-            for (int i = k + 1; i < big; i++) { float t = M(i, k); M(i, k) = M(big, i); M(big, i) = t; }
+#pragma unroll
+        for (int B = k + 1; B < n; B++) {
+            if (big == B) {
+#pragma unroll
+                for (int c = 0; c < k; c++) swapf(M(k, c), M(B, c));
+#pragma unroll
+                for (int i = B + 1; i < n; i++) swapf(M(i, k), M(i, B));
+                swapf(M(k, k), M(B, B));
+#pragma unroll
+                for (int i = k + 1; i < B; i++) swapf(M(i, k), M(B, i));
+            }
         }
-        const int rs = n - k - 1;
         if (k > 0) {
             float temp[6];
+#pragma unroll
             for (int j = 0; j < k; j++) temp[j] = M(j, j) * M(k, j);
             float s = 0;
+#pragma unroll
             for (int j = 0; j < k; j++) s += M(k, j) * temp[j];
             M(k, k) -= s;
-            for (int i = 0; i < rs; i++) {
+#pragma unroll
+            for (int i = k + 1; i < n; i++) {
                 float a = 0;
-                for (int j = 0; j < k; j++) a += M(k + 1 + i, j) * temp[j];
-                M(k + 1 + i, k) -= a;
+#pragma unroll
+                for (int j = 0; j < k; j++) a += M(i, j) * temp[j];
+                M(i, k) -= a;
             }
         }
         const float akk = M(k, k);
         const bool valid = fabsf(akk) > 0;
-        if (k == 0 && !valid) { zero_first = true; break; }
-        if (rs > 0 && valid) for (int i = 0; i < rs; i++) M(k + 1 + i, k) /= akk;
+        if (k == 0 && !valid) { zero_first = true; continue; }
+        if (valid) {
+#pragma unroll
+            for (int i = k + 1; i < n; i++) M(i, k) /= akk;
+        }
     }
     float y[6];
+#pragma unroll
     for (int i = 0; i < n; i++) y[i] = b[i];
-    if (zero_first) { for (int i = 0; i < n; i++) x[i] = 0; return; }
-    for (int k = 0; k < n; k++) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) y[i] -= M(i, j) * y[j];
+    if (zero_first) {
+#pragma unroll
+        for (int i = 0; i < n; i++) x[i] = 0;
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < n; k++) {
+#pragma unroll
+        for (int B = k + 1; B < n; B++) if (tr[k] == B) swapf(y[k], y[B]);
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+#pragma unroll
+        for (int j = 0; j < i; j++) y[i] -= M(i, j) * y[j];
+    }
+#pragma unroll
     for (int i = 0; i < n; i++) { if (fabsf(M(i, i)) > 1.17549435e-38f) y[i] /= M(i, i); else y[i] = 0; }
-    for (int i = n - 1; i >= 0; i--) for (int j = i + 1; j < n; j++) y[i] -= M(j, i) * y[j];
-    for (int k = n - 1; k >= 0; k--) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+#pragma unroll
+        for (int j = i + 1; j < n; j++) y[i] -= M(j, i) * y[j];
+    }
+#pragma unroll
+    for (int k = n - 1; k >= 0; k--) {
+#pragma unroll
+        for (int B = k + 1; B < n; B++) if (tr[k] == B) swapf(y[k], y[B]);
+    }
+#pragma unroll
     for (int i = 0; i < n; i++) x[i] = y[i];
 #undef M
 }
@@ -185,7 +228,18 @@ struct SiaArgs {
     float* trace; int* trace_n;     // [P][TRACE_CAP][8]
 };
 
-__global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
+// One CTA per problem, one THREAD per feature (patch): the projection of a feature is computed once for its 16 pixels, the 5x5 pixels
+// its bilinear taps touch, the 16 cached reference values and the 96 cached Jacobian entries are independent loads issued back to back
+// (one memory round trip per Gauss-Newton iteration instead of one per pixel item), and the 29 sums are accumulated over the patch in
+// registers.  Per-pixel arithmetic is the reference's (same expressions as computeResiduals :130-231); partial sums are float per
+// thread, double across threads.  Solver state lives in shared memory; the cross-warp totals are formed by 29 threads, thread 0 solves
+// (register-resident LDLT above).  Measured on B200, C3 (592 problems of 200 patches per launch; one problem alone):
+//   pixel item per thread, LDLT in local memory (round 1)   533 k alignments/s   0.407 ms
+//   thread per feature                                       613 k                0.336 ms
+//   + register-resident LDLT                                 803 k                0.239 ms
+//   a WARP per problem instead of a CTA (8 problems per CTA, no block barrier): 565 k — the 77 KB Jacobian cache of a problem then
+//   streams from L2 every iteration (16 problems per SM do not fit L1), which costs more than the overlapped solves gain; not kept.
+__global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SiaProblemDev& P = A.prob[p];
     const int N = P.n;
@@ -197,7 +251,9 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
     uint8_t* visible = A.visible + (size_t)p * A.maxN;
 
     __shared__ double s_red[SIA_THREADS / 32][NACC];
-    __shared__ SE3 s_T;
+    __shared__ double s_tot[NACC];
+    __shared__ SE3 s_T, s_old;      // current model, model before the last accepted update (old_model_)
+    __shared__ float s_H[36];       // H_ of the last evaluated iteration
     __shared__ int s_ctl;           // 0 continue, 1 leave the level loop
     __shared__ int s_nmeas;
 
@@ -208,18 +264,16 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
     // thread-0 solver state (NLLSSolver members)
     float chi2_ = 1e10f;
     bool stop_ = false;
-    SE3 old_model;
     int trace_count = 0;
-    float H_last[36];
 
     for (int i = tid; i < N; i += SIA_THREADS) visible[i] = 0;         // visible_fts_ = vector<bool>(N, false), :35
+    if (tid < 36) s_H[tid] = 0.f;
     if (tid == 0) {
         SE3 cur;
         for (int i = 0; i < 4; i++) cur.q[i] = P.cur_q[i];
         for (int i = 0; i < 3; i++) cur.t[i] = P.cur_t[i];
         s_T = se3_mul(cur, se3_inv(refT));                             // T_cur_from_ref, :37
         s_nmeas = 0;
-        for (int i = 0; i < 36; i++) H_last[i] = 0.f;
     }
     __syncthreads();
 
@@ -229,16 +283,23 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
         const uint8_t* cur_img = P.img_cur[level];
         const float scale = P.inv_scale[level];
         const int stride = P.stride_ref[level], cstride = P.stride_cur[level];
-        // ---- jacobian_cache_.setZero() (:41) + precomputeReferencePatches (:57-128)
-        for (int i = tid; i < N * 96; i += SIA_THREADS) jac[i] = 0.f;
-        __syncthreads();
-        for (int it = tid; it < N * 16; it += SIA_THREADS) {
-            const int f = it >> 4, pc = it & 15;
-            if (!valid[f]) continue;
-            const float u_ref = ref_px[2 * f] * scale, v_ref = ref_px[2 * f + 1] * scale;
-            const int u_ref_i = (int)floorf(u_ref), v_ref_i = (int)floorf(v_ref);
-            if (u_ref_i - 3 < 0 || v_ref_i - 3 < 0 || u_ref_i + 3 >= cols || v_ref_i + 3 >= rows) continue;
-            if (pc == 0) visible[f] = 1;
+        // ---- jacobian_cache_.setZero() (:41) + precomputeReferencePatches (:57-128); each thread owns the rows of its features
+        for (int f = tid; f < N; f += SIA_THREADS) {
+            float4* Jf = reinterpret_cast<float4*>(jac + (size_t)f * 96);
+            bool ok = valid[f] != 0;
+            float u_ref = 0.f, v_ref = 0.f;
+            int u_ref_i = 0, v_ref_i = 0;
+            if (ok) {
+                u_ref = ref_px[2 * f] * scale; v_ref = ref_px[2 * f + 1] * scale;
+                u_ref_i = (int)floorf(u_ref); v_ref_i = (int)floorf(v_ref);
+                ok = !(u_ref_i - 3 < 0 || v_ref_i - 3 < 0 || u_ref_i + 3 >= cols || v_ref_i + 3 >= rows);
+            }
+            if (!ok) {                                                  // the row keeps its zeros; ref_patch_cache_ keeps the coarser level's values
+#pragma unroll
+                for (int k = 0; k < 24; k++) Jf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            visible[f] = 1;
             float xyz[3];
             se3_apply(refT, xyz_w + 3 * f, xyz);
             float J0[6], J1[6];                                         // JacobXYZ2Cam, include/SparseImageAlign.h:90-111
@@ -253,20 +314,38 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
             }
             const float su = u_ref - u_ref_i, sv = v_ref - v_ref_i;
             const float w_tl = (1.0f - su) * (1.0f - sv), w_tr = su * (1.0f - sv), w_bl = (1.0f - su) * sv, w_br = su * sv;
-            const int py = pc >> 2, px = pc & 3;
-            const uint8_t* q = ref_img + (v_ref_i + py - 2) * stride + (u_ref_i - 2) + px;
-            ref_patch[f * 16 + pc] = w_tl * q[0] + w_tr * q[1] + w_bl * q[stride] + w_br * q[stride + 1];
-            const float dx = 0.5f * ((w_tl * q[1] + w_tr * q[2] + w_bl * q[stride + 1] + w_br * q[stride + 2]) -
-                                     (w_tl * q[-1] + w_tr * q[0] + w_bl * q[stride - 1] + w_br * q[stride]));
-            const float dy = 0.5f * ((w_tl * q[stride] + w_tr * q[1 + stride] + w_bl * q[stride * 2] + w_br * q[stride * 2 + 1]) -
-                                     (w_tl * q[-stride] + w_tr * q[1 - stride] + w_bl * q[0] + w_br * q[1]));
             const float fs = P.fx * scale;
-            float* Jc = jac + (size_t)it * 6;
+            // the 7 x 7 pixels the values and the central differences of the 4 x 4 patch touch
+            float R[7][7];
+            const uint8_t* r0 = ref_img + (v_ref_i - 3) * stride + (u_ref_i - 3);
 #pragma unroll
-            for (int k = 0; k < 6; k++) Jc[k] = (dx * J0[k] + dy * J1[k]) * fs;
+            for (int r = 0; r < 7; r++)
+#pragma unroll
+                for (int c = 0; c < 7; c++) R[r][c] = (float)r0[r * stride + c];
+            float* rp = ref_patch + (size_t)f * 16;
+#pragma unroll
+            for (int pp = 0; pp < 8; pp++) {                            // two pixels = 12 Jacobian entries = 3 float4
+                float Jr[12];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    const int pc = 2 * pp + h2, py = pc >> 2, px = pc & 3;
+                    // q = pixel (v_ref_i + py - 2, u_ref_i - 2 + px) = R[py + 1][px + 1]
+#define Q(dy, dx) R[py + 1 + (dy)][px + 1 + (dx)]
+                    rp[pc] = w_tl * Q(0, 0) + w_tr * Q(0, 1) + w_bl * Q(1, 0) + w_br * Q(1, 1);
+                    const float dx = 0.5f * ((w_tl * Q(0, 1) + w_tr * Q(0, 2) + w_bl * Q(1, 1) + w_br * Q(1, 2)) -
+                                             (w_tl * Q(0, -1) + w_tr * Q(0, 0) + w_bl * Q(1, -1) + w_br * Q(1, 0)));
+                    const float dy = 0.5f * ((w_tl * Q(1, 0) + w_tr * Q(1, 1) + w_bl * Q(2, 0) + w_br * Q(2, 1)) -
+                                             (w_tl * Q(-1, 0) + w_tr * Q(-1, 1) + w_bl * Q(0, 0) + w_br * Q(0, 1)));
+#undef Q
+#pragma unroll
+                    for (int k = 0; k < 6; k++) Jr[h2 * 6 + k] = (dx * J0[k] + dy * J1[k]) * fs;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) Jf[pp * 3 + k] = make_float4(Jr[4 * k], Jr[4 * k + 1], Jr[4 * k + 2], Jr[4 * k + 3]);
+            }
         }
         __syncthreads();
-        if (tid == 0) old_model = s_T;
+        if (tid == 0) s_old = s_T;
 
         // ---- optimizeGaussNewton (include/NLSSolver_impl.hpp:17-91)
         for (int iter = 0; iter < A.n_iter; ++iter) {
@@ -274,8 +353,7 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
             float acc[NACC];
 #pragma unroll
             for (int k = 0; k < NACC; k++) acc[k] = 0.f;
-            for (int it = tid; it < N * 16; it += SIA_THREADS) {
-                const int f = it >> 4, pc = it & 15;
+            for (int f = tid; f < N; f += SIA_THREADS) {
                 if (!visible[f]) continue;
                 float xyz_ref[3], xyz_cur[3];
                 se3_apply(refT, xyz_w + 3 * f, xyz_ref);
@@ -288,22 +366,39 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
                     continue;
                 const float su = u_cur - u_cur_i, sv = v_cur - v_cur_i;
                 const float w_tl = (1.0f - su) * (1.0f - sv), w_tr = su * (1.0f - sv), w_bl = (1.0f - su) * sv, w_br = su * sv;
-                const int py = pc >> 2, px = pc & 3;
-                const uint8_t* q = cur_img + (v_cur_i + py - 2) * cstride + (u_cur_i - 2) + px;
-                const float intensity = w_tl * q[0] + w_tr * q[1] + w_bl * q[cstride] + w_br * q[cstride + 1];
-                const float res = intensity - ref_patch[f * 16 + pc];
-                acc[27] += res * res;
-                acc[28] += 1.f;
-                const float* J = jac + (size_t)it * 6;
-                const float j0 = J[0], j1 = J[1], j2 = J[2], j3 = J[3], j4 = J[4], j5 = J[5];
-                acc[0] += j0 * j0; acc[1] += j0 * j1; acc[2] += j0 * j2; acc[3] += j0 * j3; acc[4] += j0 * j4; acc[5] += j0 * j5;
-                acc[6] += j1 * j1; acc[7] += j1 * j2; acc[8] += j1 * j3; acc[9] += j1 * j4; acc[10] += j1 * j5;
-                acc[11] += j2 * j2; acc[12] += j2 * j3; acc[13] += j2 * j4; acc[14] += j2 * j5;
-                acc[15] += j3 * j3; acc[16] += j3 * j4; acc[17] += j3 * j5;
-                acc[18] += j4 * j4; acc[19] += j4 * j5; acc[20] += j5 * j5;
-                acc[21] -= j0 * res; acc[22] -= j1 * res; acc[23] -= j2 * res; acc[24] -= j3 * res; acc[25] -= j4 * res; acc[26] -= j5 * res;
+                float C[5][5];                                           // rows v-2 .. v+2, columns u-2 .. u+2
+                const uint8_t* c0 = cur_img + (v_cur_i - 2) * cstride + (u_cur_i - 2);
+#pragma unroll
+                for (int r = 0; r < 5; r++)
+#pragma unroll
+                    for (int c = 0; c < 5; c++) C[r][c] = (float)c0[r * cstride + c];
+                const float4* rp4 = reinterpret_cast<const float4*>(ref_patch + (size_t)f * 16);
+                const float4* J4 = reinterpret_cast<const float4*>(jac + (size_t)f * 96);
+#pragma unroll
+                for (int qd = 0; qd < 4; qd++) {                        // one patch row = 4 pixels = 6 float4 of Jacobian rows at a time
+                    const float4 rv = rp4[qd];
+                    const float rpv[4] = {rv.x, rv.y, rv.z, rv.w};
+                    float Jv[24];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { const float4 v = J4[qd * 6 + k]; Jv[4 * k] = v.x; Jv[4 * k + 1] = v.y; Jv[4 * k + 2] = v.z; Jv[4 * k + 3] = v.w; }
+#pragma unroll
+                    for (int px = 0; px < 4; px++) {
+                        const int py = qd;
+                        const float intensity = w_tl * C[py][px] + w_tr * C[py][px + 1] + w_bl * C[py + 1][px] + w_br * C[py + 1][px + 1];
+                        const float res = intensity - rpv[px];
+                        acc[27] += res * res;
+                        acc[28] += 1.f;
+                        const float j0 = Jv[px * 6], j1 = Jv[px * 6 + 1], j2 = Jv[px * 6 + 2], j3 = Jv[px * 6 + 3], j4 = Jv[px * 6 + 4], j5 = Jv[px * 6 + 5];
+                        acc[0] += j0 * j0; acc[1] += j0 * j1; acc[2] += j0 * j2; acc[3] += j0 * j3; acc[4] += j0 * j4; acc[5] += j0 * j5;
+                        acc[6] += j1 * j1; acc[7] += j1 * j2; acc[8] += j1 * j3; acc[9] += j1 * j4; acc[10] += j1 * j5;
+                        acc[11] += j2 * j2; acc[12] += j2 * j3; acc[13] += j2 * j4; acc[14] += j2 * j5;
+                        acc[15] += j3 * j3; acc[16] += j3 * j4; acc[17] += j3 * j5;
+                        acc[18] += j4 * j4; acc[19] += j4 * j5; acc[20] += j5 * j5;
+                        acc[21] -= j0 * res; acc[22] -= j1 * res; acc[23] -= j2 * res; acc[24] -= j3 * res; acc[25] -= j4 * res; acc[26] -= j5 * res;
+                    }
+                }
             }
-            // block reduction in double
+            // block reduction in double: warp shuffles, then one thread per sum over the warps
 #pragma unroll
             for (int k = 0; k < NACC; k++) {
                 double v = (double)acc[k];
@@ -312,13 +407,16 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
                 if (lane == 0) s_red[warp][k] = v;
             }
             __syncthreads();
-            if (tid == 0) {
-                double tot[NACC];
-                for (int k = 0; k < NACC; k++) {
+            if (warp == 0) {
+                if (lane < NACC) {
                     double s = 0;
-                    for (int w = 0; w < SIA_THREADS / 32; w++) s += s_red[w][k];
-                    tot[k] = s;
+                    for (int w = 0; w < SIA_THREADS / 32; w++) s += s_red[w][lane];
+                    s_tot[lane] = s;
                 }
+                __syncwarp();
+            }
+            if (tid == 0) {
+                const double* tot = s_tot;
                 float H[36], Jres[6], x[6];
                 {
                     int k = 0;
@@ -326,7 +424,7 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
                         for (int c = r; c < 6; c++) { H[r * 6 + c] = (float)tot[k]; H[c * 6 + r] = (float)tot[k]; k++; }
                     for (int r = 0; r < 6; r++) Jres[r] = (float)tot[21 + r];
                 }
-                for (int i = 0; i < 36; i++) H_last[i] = H[i];
+                for (int i = 0; i < 36; i++) s_H[i] = H[i];
                 const int n_meas = (int)(tot[28] + 0.5);
                 s_nmeas = n_meas;
                 const float new_chi2 = (float)tot[27] / (float)n_meas;         // chi2 / n_meas_ (NaN when nothing is visible)
@@ -343,13 +441,13 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
                 }
                 int ctl = 0;
                 if (rejected) {
-                    s_T = old_model;                                            // rollback, impl:63-64
+                    s_T = s_old;                                                // rollback, impl:63-64
                     ctl = 1;
                 } else {
                     float nx[6];
                     for (int i = 0; i < 6; i++) nx[i] = -x[i];
                     const SE3 nm = se3_mul(T, se3_exp(nx));                     // update() :240-244
-                    old_model = T;
+                    s_old = T;
                     s_T = nm;
                     chi2_ = new_chi2;
                     if (xmax <= A.eps) ctl = 1;                                 // impl:87-89
@@ -364,7 +462,7 @@ __global__ void __launch_bounds__(SIA_THREADS) k_sia_align(SiaArgs A) {
     if (tid == 0) {
         for (int i = 0; i < 4; i++) A.out_q[p * 4 + i] = s_T.q[i];
         for (int i = 0; i < 3; i++) A.out_t[p * 3 + i] = s_T.t[i];
-        if (A.out_H) for (int i = 0; i < 36; i++) A.out_H[p * 36 + i] = H_last[i];
+        if (A.out_H) for (int i = 0; i < 36; i++) A.out_H[p * 36 + i] = s_H[i];
         A.out_ntracked[p] = s_nmeas / 16;                                       // n_meas_ / patch_area_, :48
         if (A.trace_n) A.trace_n[p] = trace_count;
     }
