@@ -1,5 +1,4 @@
-"""One C3-shaped SparseImgAlign launch for ncu (P problems; P < 64 -> a CTA per problem, else a warp per problem unless YGZ_SIA_WARP_FROM says
-otherwise).  Warm-up call, then ONE call between cudaProfilerStart/Stop.  usage: python profiles/scripts/prof_sia.py [P]"""
+"""One C3-shaped SparseImgAlign launch for ncu (P problems, a CTA each).  Warm-up call, then ONE call between cudaProfilerStart/Stop.  usage: python profiles/scripts/prof_sia.py [P]"""
 import ctypes, sys, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import __graft_entry__ as g
