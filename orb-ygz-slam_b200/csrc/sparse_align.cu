@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
     float* ref_patch = A.ref_patch + (size_t)p * A.maxN * 16;
     float* jac = A.jac + (size_t)p * A.maxN * 96;
     uint8_t* visible = A.visible + (size_t)p * A.maxN;
+    const int MN = A.maxN;
 
     __shared__ double s_red[SIA_THREADS / 32][NACC];
     __shared__ double s_tot[NACC];
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
         const int stride = P.stride_ref[level], cstride = P.stride_cur[level];
         // ---- jacobian_cache_.setZero() (:41) + precomputeReferencePatches (:57-128); each thread owns the rows of its features
         for (int f = tid; f < N; f += SIA_THREADS) {
-            float4* Jf = reinterpret_cast<float4*>(jac + (size_t)f * 96);
+            float4* Jf = reinterpret_cast<float4*>(jac) + f;                    // plane layout [24][maxN] float4: lanes read / write neighbours
             bool ok = valid[f] != 0;
             float u_ref = 0.f, v_ref = 0.f;
             int u_ref_i = 0, v_ref_i = 0;
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
             }
             if (!ok) {                                                  // the row keeps its zeros; ref_patch_cache_ keeps the coarser level's values
 #pragma unroll
-                for (int k = 0; k < 24; k++) Jf[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 24; k++) Jf[(size_t)k * MN] = make_float4(0.f, 0.f, 0.f, 0.f);
                 continue;
             }
             visible[f] = 1;
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
             for (int r = 0; r < 7; r++)
 #pragma unroll
                 for (int c = 0; c < 7; c++) R[r][c] = (float)r0[r * stride + c];
-            float* rp = ref_patch + (size_t)f * 16;
+            float4* rpw = reinterpret_cast<float4*>(ref_patch) + f;                // [4][maxN] float4
+            float rp[16];
 #pragma unroll
             for (int pp = 0; pp < 8; pp++) {                            // two pixels = 12 Jacobian entries = 3 float4
                 float Jr[12];
@@ -341,8 +343,10 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
                     for (int k = 0; k < 6; k++) Jr[h2 * 6 + k] = (dx * J0[k] + dy * J1[k]) * fs;
                 }
 #pragma unroll
-                for (int k = 0; k < 3; k++) Jf[pp * 3 + k] = make_float4(Jr[4 * k], Jr[4 * k + 1], Jr[4 * k + 2], Jr[4 * k + 3]);
+                for (int k = 0; k < 3; k++) Jf[(size_t)(pp * 3 + k) * MN] = make_float4(Jr[4 * k], Jr[4 * k + 1], Jr[4 * k + 2], Jr[4 * k + 3]);
             }
+#pragma unroll
+            for (int k = 0; k < 4; k++) rpw[(size_t)k * MN] = make_float4(rp[4 * k], rp[4 * k + 1], rp[4 * k + 2], rp[4 * k + 3]);
         }
         __syncthreads();
         if (tid == 0) s_old = s_T;
@@ -372,15 +376,15 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
                 for (int r = 0; r < 5; r++)
 #pragma unroll
                     for (int c = 0; c < 5; c++) C[r][c] = (float)c0[r * cstride + c];
-                const float4* rp4 = reinterpret_cast<const float4*>(ref_patch + (size_t)f * 16);
-                const float4* J4 = reinterpret_cast<const float4*>(jac + (size_t)f * 96);
+                const float4* rp4 = reinterpret_cast<const float4*>(ref_patch) + f;
+                const float4* J4 = reinterpret_cast<const float4*>(jac) + f;
 #pragma unroll
                 for (int qd = 0; qd < 4; qd++) {                        // one patch row = 4 pixels = 6 float4 of Jacobian rows at a time
-                    const float4 rv = rp4[qd];
+                    const float4 rv = rp4[(size_t)qd * MN];
                     const float rpv[4] = {rv.x, rv.y, rv.z, rv.w};
                     float Jv[24];
 #pragma unroll
-                    for (int k = 0; k < 6; k++) { const float4 v = J4[qd * 6 + k]; Jv[4 * k] = v.x; Jv[4 * k + 1] = v.y; Jv[4 * k + 2] = v.z; Jv[4 * k + 3] = v.w; }
+                    for (int k = 0; k < 6; k++) { const float4 v = J4[(size_t)(qd * 6 + k) * MN]; Jv[4 * k] = v.x; Jv[4 * k + 1] = v.y; Jv[4 * k + 2] = v.z; Jv[4 * k + 3] = v.w; }
 #pragma unroll
                     for (int px = 0; px < 4; px++) {
                         const int py = qd;
