@@ -373,9 +373,17 @@ __global__ void __launch_bounds__(SIA_THREADS, 2) k_sia_align(SiaArgs A) {
                 float C[5][5];                                           // rows v-2 .. v+2, columns u-2 .. u+2
                 const uint8_t* c0 = cur_img + (v_cur_i - 2) * cstride + (u_cur_i - 2);
 #pragma unroll
-                for (int r = 0; r < 5; r++)
-#pragma unroll
-                    for (int c = 0; c < 5; c++) C[r][c] = (float)c0[r * cstride + c];
+                for (int r = 0; r < 5; r++) {
+                    // the five bytes of a row sit in two aligned words (two L1 requests per lane instead of five; the bytes outside
+                    // the five belong to the same image: the patch is at least 3 pixels and one row away from its borders)
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(c0 + r * cstride);
+                    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                    const uint32_t w0 = w[0], w1 = w[1];
+                    const unsigned sh = ((unsigned)a & 3u) * 8u;
+                    const uint32_t lo = __funnelshift_r(w0, w1, sh);
+                    C[r][0] = (float)(lo & 0xFFu); C[r][1] = (float)((lo >> 8) & 0xFFu); C[r][2] = (float)((lo >> 16) & 0xFFu);
+                    C[r][3] = (float)(lo >> 24); C[r][4] = (float)((w1 >> sh) & 0xFFu);
+                }
                 const float4* rp4 = reinterpret_cast<const float4*>(ref_patch) + f;
                 const float4* J4 = reinterpret_cast<const float4*>(jac) + f;
 #pragma unroll
