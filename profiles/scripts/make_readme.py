@@ -46,7 +46,9 @@ def main():
     w("| `r2_bench_N1.json`, `r2_bench_reference_arm.json` | C2 headline line and `--impl reference` (oracle port, all host threads, B = 256 frames/step) on the same box |")
     w("| `r2_bench_c5_N1.json`, `r2_bench_c5_N8.json`, `r2_bench_c5_reference_arm.json` | `bench.py --workload c5` (stereo 1242x375 x2, 2000 features, extractor x2 + ComputeStereoMatches + brute force) at 1 and 8 GPUs, CPU arm |")
     w("| `r2_bench_c3_N1.json`, `r2_bench_c3_N8.json`, `r2_bench_c3_reference_arm.json` | `bench.py --workload c3` (SparseImgAlign, 592 problems/step) at 1 and 8 GPUs, CPU arm |")
+    w("| `r2_sia_P592_raw.csv`, `r2_sia_stalls_by_line.txt` | `ncu --set full` of `k_sia_align` on one C3-shaped launch (592 problems; `scripts/prof_sia.sh`) and its warp-stall samples per source line (`scripts/stall_hist.py`): what the kernel waits for after this round's rewrite |")
     w("| `r2_sanitizer_memcheck_smoke.log`, `r2_sanitizer_racecheck_smoke.log` | `compute-sanitizer --tool memcheck / racecheck python __graft_entry__.py smoke` |")
+    w("| `r2_sanitizer_memcheck_tests.log` | `compute-sanitizer --tool memcheck` over the GPU tests of the entry points added late in the round (`scripts/sanitize_tests.sh`: batched DSO selection, SparseImgAlign over extractor pyramids, Fuse, Sim3 family, batched projection, stereo) |")
     w("| `r1_*` | round-1 artefacts, kept for comparison |\n")
     w("## Launch list of one C2 step (ncu, cold cache, serialised) vs the bench's own stage timing\n")
     w("| # | kernel | grid | block | device time (us) | share of step |\n|---|---|---|---|---:|---:|")
@@ -95,6 +97,13 @@ def main():
                  ("; **%.0f** / %.0f at 8 GPUs" % (j8["value"], j8["e2e"]["value"])) if j8 else "",
                  "%.0f" % cb["value"] if cb.get("value") else "n/a", cb.get("cores", "?"),
                  "; in-bench parity gate: %s" % (cb.get("parity_gate_pair0_bit_exact", cb.get("parity_gate_max_pose_diff")),) if cb else ""))
+            if j1.get("e2e_device_pyramids"):
+                w("  * with the level images read in place from the extractor handles (`ygz_sia_run_orb`): **%.0f %s** end to end; one problem alone: %.3f ms."
+                  % (j1["e2e_device_pyramids"]["value"], unit, j1.get("single_problem_latency_ms") or float("nan")))
+    dso = ((b.get("aux") or {}).get("dso_batch") or {})
+    if dso.get("frames_per_s_batched_host_buffers"):
+        w("* DSO_KEYPOINT extraction (`aux.dso_batch`, %d independent streams per call, Python marshalling included): %.0f frames/s batched vs %.0f with per-frame calls; CPU port %.0f frames/s on one thread; parity gate %s."
+          % (dso["frames"], dso["frames_per_s_batched_host_buffers"], dso["frames_per_s_per_frame_calls"], dso["cpu_baseline"]["frames_per_s_1_thread"], dso.get("parity_gate_4_frames_identical")))
     w("")
     w("## Per-kernel summary (ncu --set full, B = 256)\n")
     w("| stage | kernel | ms (ncu) | issue active | ALU / FMA / LSU pipe | warps active | DRAM read + write | warp instructions | regs |\n|---|---|---:|---:|---|---:|---|---:|---:|")
