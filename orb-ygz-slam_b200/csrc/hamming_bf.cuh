@@ -13,6 +13,17 @@ __device__ __forceinline__ void merge_top2(int& b, int& bi, int& s, int ob, int 
     else s = min(s, ob);
 }
 
+// The same over the 32 lanes of a warp in two REDUX instructions (result on every lane).  Positions must be below 65536 (INT_MAX, "no
+// candidate", folds to 0xFFFF and only ever meets b = 256).  K = min of (b << 16 | position): best distance, earliest position on ties;
+// the second smallest value of the multiset is the minimum of the owner's own second and every other lane's best.
+__device__ __forceinline__ void warp_top2(int& b, int& bi, int& s) {
+    const unsigned key = ((unsigned)b << 16) | ((unsigned)bi & 0xFFFFu);
+    const unsigned K = __reduce_min_sync(0xffffffffu, key);
+    s = (int)__reduce_min_sync(0xffffffffu, (unsigned)(key == K ? s : b));
+    b = (int)(K >> 16);
+    bi = (int)(K & 0xFFFFu);
+}
+
 constexpr int BF_WARPS = 8;
 constexpr int BF_QPW = 4;           // queries per warp
 constexpr int BF_TILE = 256;        // targets per shared-memory tile

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A)
     __shared__ int s_n;
     __shared__ int s_wcnt[BOW_THREADS / 32];
     __shared__ int s_nseg;
+    __shared__ int s_next;
     const int cap = A.cap;
     int p2 = 1; while (p2 < cap) p2 <<= 1;
     unsigned long long* skf = reinterpret_cast<unsigned long long*>(bow_smem);   // (node << 32) | feature index, sorted
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A)
         sf[i] = i < nf ? ((node_of(fr, fds, i) << 32) | (unsigned)i) : ~0ull;
     for (int i = threadIdx.x; i < cap; i += BOW_THREADS) { match_of_f[i] = -1; bin_of_f[i] = -1; }
     if (threadIdx.x < HISTO_LENGTH) hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_n = 0; s_nseg = 0; }
+    if (threadIdx.x == 0) { s_n = 0; s_nseg = 0; s_next = 0; }
     __syncthreads();
     bitonic_sort_u64(skf, pk);
     bitonic_sort_u64(sf, pf);
@@ -156,7 +157,13 @@ __global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A)
     }
     const int nseg = s_nseg;
     // ---- one warp per common node: the reference's sequential loop over that node's KF features (:180-234)
-    for (int sgm = warp; sgm < nseg; sgm += nwarps) {
+    // nodes are drawn from a counter: bucket sizes are skewed, a static deal left the warps waiting at the barrier below (22 % of the
+    // kernel's stall samples); nodes are independent of each other, so the order does not matter
+    for (;;) {
+        int sgm = 0;
+        if (lane == 0) sgm = atomicAdd(&s_next, 1);
+        sgm = __shfl_sync(0xffffffffu, sgm, 0);
+        if (sgm >= nseg) break;
         const int i0 = seg_start[sgm];
         const uint32_t node = (uint32_t)(skf[i0] >> 32);
         int i1 = (sgm + 1 < nseg) ? (int)seg_start[sgm + 1] : nk;
@@ -178,13 +185,7 @@ __global__ void __launch_bounds__(BOW_THREADS) k_bow_match_batch(BowBatchArgs A)
                 if (d < b) { s = b; b = d; bi = j; }
                 else if (d < s) s = d;
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const int ob = __shfl_xor_sync(0xffffffffu, b, o);
-                const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const int os = __shfl_xor_sync(0xffffffffu, s, o);
-                merge_top2(b, bi, s, ob, obi, os);
-            }
+            warp_top2(b, bi, s);                                                  // two REDUX (the 15-shuffle merge was the loop's largest part)
             if (lane == 0 && b <= TH_LOW && (float)b < A.nnratio * (float)s) {    // :216-217
                 const int bestIdxF = (int)(sf[bi] & 0xFFFFFFFFu);
                 match_of_f[bestIdxF] = (short)realIdxKF;

@@ -58,34 +58,18 @@ __global__ void __launch_bounds__(256) k_vocab_transform(VocabDev V, const uint4
     const int nid_level = V.L - levelsup;
     int cur = 0, level = 0, nid_node = 0;
     int4 m = __ldg(V.meta);
-    const int base = grp * GROUP;
     while (m.y > 0) {
         ++level;
-        int best = INT_MAX, bestc = INT_MAX;
+        // first minimum in child order (the reference's strict <) = minimum of (distance << 20 | child): one REDUX over the group's lanes
+        unsigned key = 0xFFFFFFFFu;
         for (int c = gl; c < m.y; c += GROUP) {
             const uint4* b = V.desc + 2 * (size_t)(m.x + c);
             const uint4 b0 = __ldg(b), b1 = __ldg(b + 1);
             const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
                              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-            if (dist < best) { best = dist; bestc = c; }       // first minimum in child order (the reference's strict <)
+            key = min(key, ((unsigned)dist << 20) | (unsigned)c);
         }
-        // minimum over the group's lanes, result on every lane: a butterfly for power-of-two groups, otherwise a fold onto lane 0 of
-        // the group (offsets 8, 4, 2, 1; partners past the group are ignored) and a broadcast
-        if ((GROUP & (GROUP - 1)) == 0) {
-#pragma unroll
-            for (int o = GROUP / 2; o; o >>= 1) {
-                const int ob = __shfl_xor_sync(gmask, best, o), oc = __shfl_xor_sync(gmask, bestc, o);
-                if (ob < best || (ob == best && oc < bestc)) { best = ob; bestc = oc; }
-            }
-        } else {
-#pragma unroll
-            for (int o = 8; o; o >>= 1) {
-                const int src = min(lane + o, base + GROUP - 1);
-                const int ob = __shfl_sync(gmask, best, src), oc = __shfl_sync(gmask, bestc, src);
-                if (gl + o < GROUP && (ob < best || (ob == best && oc < bestc))) { best = ob; bestc = oc; }
-            }
-            bestc = __shfl_sync(gmask, bestc, base);
-        }
+        const int bestc = (int)(__reduce_min_sync(gmask, key) & 0xFFFFFu);
         cur = m.x + bestc;
         m = __ldg(V.meta + cur);
         if (level == nid_level) nid_node = m.w;
@@ -217,6 +201,7 @@ int ygz_vocab_from_memory(const uint8_t* buf, size_t bytes, int device, ygz_voca
         std::memcpy(&desc2[q * 32], &desc[(size_t)order[q] * 32], 32);
         weight2[q] = weight[order[q]];
     }
+    if (k >= (1 << 20)) { set_last_error("branching factor above 2^20"); return YGZ_ERR_ARG; }     // k_vocab_transform packs (distance, child) in 32 bits
     YGZ_CUDA_TRY(cudaSetDevice(device));
     ygz_vocab* v = new ygz_vocab();
     v->device = device; v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->n_nodes = (int)n; v->n_words = n_words;

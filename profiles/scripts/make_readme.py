@@ -113,9 +113,12 @@ def main():
              v.get("warps_active_pct", 0), v.get("dram_bytes_read", 0) / 1e6, v.get("dram_bytes_write", 0) / 1e6, v.get("warp_instructions", 0) / 1e6,
              int(v.get("registers", 0))))
     w("")
-    w("Every kernel of the step is issue-bound (59-87 % of the issue slots, ALU pipe 45-69 %) except the two latency-bound ones (`k_octree`, `k_bow_match_batch`);")
-    w("the step as a whole saturates at two batches in flight (`ygz_frontend_time_n`: 126 / 133 / 133 / 133 k frames/s at 1 / 2 / 3 / 4 in flight), i.e. it is bound by")
-    w("the aggregate instruction count (1.58 G warp instructions per 256 frames), not by bytes: DRAM traffic per step is within 1.1 x of the algorithmic bytes.")
+    tot_instr = sum(v.get("warp_instructions", 0) for v in (km.get("kernels") or {}).values())
+    w("The extractor kernels are issue-bound (59-87 % of the issue slots, ALU pipe 45-69 %) except the latency-bound `k_octree`; the step as a whole")
+    w("saturates at two batches in flight (`ygz_frontend_time_n`, measured earlier in the round: 126 / 133 / 133 / 133 k frames/s at 1 / 2 / 3 / 4 in flight),")
+    w("i.e. it is bound by the aggregate instruction count (%.2f G warp instructions per 256 frames in this build), not by bytes: DRAM traffic per step is" % (tot_instr / 1e9))
+    w("within 1.1 x of the algorithmic bytes.  `k_vocab_transform` and `k_bow_match_batch` lost 37 % / 25 % of their time in the last change of the round")
+    w("(argmin / top-2 over a warp or a lane group as REDUX instead of shuffle trees; BoW nodes drawn from a counter instead of dealt statically).")
     open(os.path.join(P, "README.md"), "w").write("\n".join(out) + "\n")
     print("written")
 
