@@ -348,7 +348,8 @@ int ygz_sia_run(ygz_sia* h, const ygz_sia_problem* problems, int n_problems, int
  * device).  Problem p aligns frame ref_frame[p] of orb_ref with frame cur_frame[p] of orb_cur (the same handle may be passed twice, e.g.
  * consecutive frames of one batch).  Of ygz_sia_problem only fx..cy, n, ref_px, world_xyz, valid and the poses are read; the level
  * fields (n_levels, *_levels, level_w/h, inv_scale_factors) are ignored - sizes and mvInvScaleFactors come from the handles.  No image
- * bytes cross PCIe; the call waits for the extractors' streams on the device, not on the host. */
+ * bytes cross PCIe; the call waits for the extractors' streams on the device, not on the host.  All three handles must live on the same
+ * device (the level pointers are used as they are), and the extractor handles must not be re-used for other frames until the call returns. */
 int ygz_sia_run_orb(ygz_sia* h, ygz_orb* orb_ref, ygz_orb* orb_cur, const ygz_sia_problem* problems, const int* ref_frame,
                     const int* cur_frame, int n_problems, int max_level, int min_level, int n_iter, float eps, float* out_q,
                     float* out_t, float* out_H, int* out_n_tracked);
