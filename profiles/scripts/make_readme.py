@@ -35,7 +35,9 @@ def main():
     out = []
     w = out.append
     w("# profiles/ — round 2 (B200, sm_100a, CUDA 12.9)\n")
-    w("Produced by `profiles/scripts/prof_r2_checkpoint.sh` / `prof_r2_ncu.sh` (one `gpurun` call each, fresh B200 box, SM clock %s MHz = max, throttle reasons %s)."
+    w("Produced by `profiles/scripts/prof_r2_final.sh` (GPU tests, bench lines, ncu passes, sanitizer, C3 / C5) and, for the C2 artefacts of the last kernel change of the round, "
+      "`verify_and_capture.sh` (GPU tests, then bench + the same ncu passes); C3 / C5 at 8 GPUs by `run_c5_8gpu.sh`, the SparseImgAlign capture by `prof_sia.sh` "
+      "(one `gpurun` call each, fresh B200 box, SM clock %s MHz = max, throttle reasons %s)."
       % (b["clocks"]["sm_mhz"], b["clocks"]["reasons"] or "none"))
     w("Numbers printed under ncu are never used as bench values; `r2_bench_N1.json` is the un-profiled `python bench.py --steps 20 --warmup 3` line of the same build")
     w("(`kernel_metrics.json` carries the sha1 of `orb-ygz-slam_b200/csrc/` it was captured from: `%s`; `bench.py` refuses to quote it for another build).\n" % km.get("csrc_sha", "?")[:12])
