@@ -1,4 +1,4 @@
-"""Write profiles/kernel_metrics.json from `ncu --set full` captures (.ncu-rep) of the bench-shaped step (prof_final.sh):
+"""Write profiles/kernel_metrics.json from `ncu --set full` captures (.ncu-rep) of the bench-shaped step (prof_r2_checkpoint.sh, verify_and_capture.sh):
 per kernel the DRAM bytes per launch and the utilisation numbers bench.py quotes in `roofline`.  Keyed by the sha1 of
 orb-ygz-slam_b200/csrc (bench.csrc_sha) so a stale capture is never quoted for a newer build.
 usage: python profiles/scripts/ncu_summary.py BATCH out.json rep1.ncu-rep [rep2 ...]"""
